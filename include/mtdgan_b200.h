@@ -1,0 +1,142 @@
+/* libmtdgan_sm100a.so — C ABI of the B200-native MTD-GAN hot path.
+ *
+ * The reference (babbu3682/MTD-GAN) is pure Python/PyTorch and has no FFI of its own; the interface
+ * each entry point replaces is therefore the PyTorch call the reference makes at the cited
+ * file:line (all under /root/reference).  INTEGRATION.md shows the ctypes binding a maintainer adds.
+ *
+ * Conventions
+ *  - Plain pointers and sizes only; every pointer is a DEVICE pointer to fp32 data unless stated.
+ *  - Activations are NHWC contiguous: (B, H, W, C).  The reference's NCHW tensors have C == 1 at the
+ *    module boundaries (images, decision maps), where both layouts coincide; mtd_layout_transpose
+ *    converts where a multi-channel module is called stand-alone.
+ *  - The caller owns all memory, including workspaces; nothing is allocated or freed here.
+ *  - All work is enqueued on `stream` (a cudaStream_t passed as void*); no implicit synchronisation;
+ *    graph-capturable.  Stateless and re-entrant.
+ *  - Return value: 0 ok; < 0 argument / shape error (MTD_EINVAL -1, MTD_EALIGN -2); > 0 a cudaError_t.
+ *  - There is NO CPU implementation behind any entry point.
+ */
+#ifndef MTDGAN_B200_H_
+#define MTDGAN_B200_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* activation codes */
+#define MTD_ACT_NONE_C 0
+#define MTD_ACT_RELU_C 1
+#define MTD_ACT_LEAKY_C 2
+
+/* ---- library info ---------------------------------------------------------------------------- */
+int mtd_abi_version(void);
+/* 1 if the running device is compute capability 10.x (B200), else 0; <0 on CUDA error */
+int mtd_device_ok(void);
+
+/* ---- convolution (conv_simt.cu, conv_tc.cu) ----------------------------------------------------
+ * Replaces nn.Conv2d / nn.ConvTranspose2d / nn.Linear forward and ATen convolution_backward:
+ * arch/Ours/networks.py:18-19 (FFT_ConvBlock convs), :41-46 (generator encoder/decoder), :170
+ * (UpsampleBlock), :181-306 (discriminator), applied at :32, :97-162, :385-472.
+ *
+ * Packed weight layouts (K-major for NHWC implicit GEMM):
+ *   forward : wp[Cout][kh*kw][Cin]
+ *   dgrad   : stride 1: wpd[Cin][kh*kw][Cout]; stride 2 (4x4, pad 1): wpd[4][Cin][4][Cout]
+ * `transposed` = 1 for a ConvTranspose2d(stride 1) weight (Cin, Cout, kh, kw)  (SURVEY A6).      */
+int mtd_conv_pack_fwd(const float* w_ref, int transposed, int Cout, int Cin, int kh, int kw, float* out, void* stream);
+int mtd_conv_pack_dgrad(const float* w_ref, int transposed, int Cout, int Cin, int kh, int kw, int stride, float* out,
+                        void* stream);
+/* y = post_act( pre_act( scale * conv(cat[x1,x2]) + bias ) + add1 + add2 );  aux (optional) receives the
+ * value after pre_act.  x2/C2 = second source concatenated along channels (torch.cat at
+ * networks.py:421-466) or null/0.  scale = device scalar 1/sigma of spectral norm, or null.       */
+int mtd_conv_fwd(const float* x1, const float* x2, const float* wp, const float* bias, const float* scale, float* y,
+                 float* aux, const float* add1, const float* add2, int B, int H, int W, int C1, int C2, int N, int kh,
+                 int kw, int stride, int pad, int pre_act, int post_act, float slope, void* stream);
+/* dx = (scale * dgrad(dz) + add1 + add2) * act'(mask_src);  (H, W) are the conv INPUT dims.        */
+int mtd_conv_dgrad(const float* dz, const float* wpd, float* dx, const float* scale, const float* add1,
+                   const float* add2, const float* mask_src, int mask_act, float slope, int B, int H, int W, int Cin,
+                   int Cout, int kh, int kw, int stride, int pad, void* stream);
+/* gp[N][kh*kw][C1+C2] = sum over output pixels of dz (x) x   (dL/dW~ in packed forward layout)      */
+int mtd_conv_wgrad(const float* x1, const float* x2, const float* dz, float* gp, int B, int H, int W, int C1, int C2,
+                   int N, int kh, int kw, int stride, int pad, void* stream);
+/* packed gradient -> reference layout; with inv_sigma != null applies the spectral-norm backward
+ * dW_orig = (G - <G,W~> u v^T)/sigma (torch.nn.utils.spectral_norm).  scratch: 16 bytes.  */
+int mtd_conv_wgrad_finish(const float* gp, float* dw_ref, int transposed, int Cout, int Cin, int kh, int kw,
+                          const float* w_ref, const float* u, const float* v, const float* inv_sigma, void* scratch,
+                          void* stream);
+/* dz = dy * act'(y) (F.relu / nn.LeakyReLU(0.2) backward); dbias[N] = column sums of dz (optional)  */
+int mtd_act_bwd(const float* dy, const float* y, float* dz, float* dbias, long long M, int N, int act, float slope,
+                void* stream);
+
+/* tcgen05 / TMEM TF32 implicit-GEMM forward for C % 32 == 0 layers (conv_tc.cu).  Same contract as
+ * mtd_conv_fwd restricted to one or two sources with C1 % 32 == 0 && C2 % 32 == 0, N % 16 == 0,
+ * stride 1, and TMA-tileable spatial dims; returns MTD_EINVAL for anything else (the caller then
+ * uses mtd_conv_fwd).  Numerics: TF32 operands, fp32 accumulate (rel. error <= 2e-3).             */
+int mtd_conv_fwd_tc_supported(int B, int H, int W, int C1, int C2, int N, int kh, int kw, int stride, int pad);
+int mtd_conv_fwd_tc(const float* x1, const float* x2, const float* wp, const float* bias, const float* scale, float* y,
+                    float* aux, const float* add1, const float* add2, int B, int H, int W, int C1, int C2, int N, int kh,
+                    int kw, int stride, int pad, int pre_act, int post_act, float slope, void* stream);
+
+/* ---- Res-FFT-Conv frequency branch (fft_block.cu) ------------------------------------------------
+ * Replaces torch.fft.rfft2 / cat / fft_conv 1x1 + ReLU / chunk / complex / torch.fft.irfft2 at
+ * arch/Ours/networks.py:24-29 and their autograd backward.  Half spectrum layout:
+ * spec[B][W/2+1][H][C] complex64 (interleaved).  H, W powers of two; C == 32 for the mix.          */
+long long mtd_fft_spec_elems(int B, int H, int W, int C);          /* floats in a spectrum buffer      */
+long long mtd_fft_bwd_part_elems(int B, int W);                    /* floats in the bwd partial buffer */
+int mtd_fft_rows_fwd(const float* x, float* spec, int B, int H, int W, int C, void* stream);
+int mtd_fft_cols_mix(const float* spec_in, float* spec_out, const float* w, const float* bias, int B, int H, int W,
+                     int C, void* stream);
+/* out = irfft-rows(spec) + add1 + add2  (the block's `x + img + fft`, networks.py:35)             */
+int mtd_fft_rows_inv(const float* spec, const float* add1, const float* add2, float* out, int B, int H, int W, int C,
+                     void* stream);
+int mtd_fft_cols_mix_bwd(const float* spec_x, const float* spec_g, float* spec_out, const float* w, const float* bias,
+                         float* part, float* dw, float* db, int B, int H, int W, int C, void* stream);
+
+/* ---- spectral norm (spectral_norm.cu) ------------------------------------------------------------
+ * Replaces the forward-pre-hook of nn.utils.spectral_norm (networks.py:181-300) for all layers of a
+ * discriminator forward at once.  Tables are device arrays built by the host mirror.              */
+int mtd_sn_rows_per_wtu_item(void);
+int mtd_sn_power_iter(const void* layer_tab, int n_layers, const void* work_wtu, int n_wtu, const void* work_wv,
+                      int n_wv, float* t_ws, long long t_elems, float* s_ws, float* u_snap, float* v_snap,
+                      float* inv_sigma, int update, float eps, void* stream);
+
+/* ---- resampling / elementwise (resample.cu) -------------------------------------------------------
+ * nn.Upsample(x2, bilinear) networks.py:230-260; nn.PixelShuffle(2) :171; .clip(0,1) :1969-1970;
+ * nn.Dropout mask multiply :417.                                                                  */
+int mtd_upsample2x_fwd(const float* in, float* out, int B, int H, int W, int C, void* stream);
+int mtd_upsample2x_bwd(const float* dout, float* din, int B, int H, int W, int C, void* stream);
+int mtd_pixel_shuffle2(const float* in, float* out, int B, int H, int W, int C, int backward, void* stream);
+int mtd_layout_transpose(const float* in, float* out, int B, int C, int HW, int to_nhwc, void* stream);
+int mtd_clip01_fwd(const float* x, float* y, long long n, void* stream);
+int mtd_clip01_bwd(const float* x, const float* dy, float* dx, long long n, void* stream);
+int mtd_mul(const float* a, const float* b, float* out, long long n, void* stream);
+int mtd_add3(const float* a, const float* b, const float* c, float* out, long long n, void* stream);
+
+/* ---- losses (losses.cu) ----------------------------------------------------------------------------
+ * ls_gan losses.py:10-11; NDS_Loss :13-15; F.l1_loss / F.mse_loss networks.py:1964-1975;
+ * CharbonnierLoss losses.py:108-111; EdgeLoss :122-138.  `acc` are fp64 device accumulators.       */
+int mtd_nds_mask(const float* x, const float* y, unsigned char* mask, long long n, void* stream);
+int mtd_sum_sqerr(const float* in, float target, const float* x, const float* y, long long n, double* acc, void* stream);
+int mtd_sqerr_bwd(const float* in, float target, const float* x, const float* y, long long n, const float* gout, int k,
+                  float scale, float* din, void* stream);
+int mtd_sum_diff(const float* a, const float* b, long long n, int mode, float eps, double* acc, void* stream);
+int mtd_diff_bwd(const float* a, const float* b, long long n, int mode, float eps, const float* gout, int k, float scale,
+                 float* da, float* db, void* stream);
+int mtd_sum_edge(const float* x, const float* y, int B, int H, int W, float eps, double* acc, void* stream);
+int mtd_edge_bwd(const float* x, const float* y, int B, int H, int W, float eps, const float* gout, int k_edge,
+                 float scale_edge, int k_pix, float scale_pix, float* dx, void* stream);
+int mtd_loss_finalize(const double* acc, int k, float s0, float s1, float s2, float s3, float* out, void* stream);
+
+/* ---- PCGrad (pcgrad.cu) -----------------------------------------------------------------------------
+ * Replaces PCGrad._project_conflicting of module/weight_methods.py:449-464 and module/pcgrad.py:50-70. */
+int mtd_pcgrad_chunk_elems(void);
+int mtd_pcgrad_project(const void* seg_tab, const void* chunk_tab, int n_chunks, int T, const int* orders, int mean,
+                       double* gram_ws, float* coef_out, float* cmat_out, double* gram_out, void* stream);
+
+/* ---- AdamW (adamw.cu) — "next" row: torch.optim.AdamW step of optimizers.py:9 / engine.py:44,52 ------
+ * seg table int64[nseg][8]: { param, grad, exp_avg, exp_avg_sq, numel, 0, 0, 0 }; chunk table as PCGrad. */
+int mtd_adamw_step(const void* seg_tab, const void* chunk_tab, int n_chunks, float lr, float beta1, float beta2,
+                   float eps, float weight_decay, float bias_corr1, float bias_corr2, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MTDGAN_B200_H_ */

@@ -1,0 +1,89 @@
+// Shared device/host helpers for libmtdgan_sm100a.so.  sm_100a only.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#define MTD_OK 0
+#define MTD_EINVAL (-1)     // bad argument / unsupported shape
+#define MTD_EALIGN (-2)     // pointer not 16-byte aligned where required
+
+// Return convention of every extern "C" entry point: 0 ok, <0 argument error,
+// >0 a cudaError_t.  Nothing throws across the ABI.
+#define MTD_CHECK_LAUNCH()                               \
+  do {                                                   \
+    cudaError_t e__ = cudaGetLastError();                \
+    if (e__ != cudaSuccess) return (int)e__;             \
+  } while (0)
+
+#define MTD_CUDA(x)                                      \
+  do {                                                   \
+    cudaError_t e__ = (x);                               \
+    if (e__ != cudaSuccess) return (int)e__;             \
+  } while (0)
+
+#define MTD_REQUIRE(cond)                                \
+  do {                                                   \
+    if (!(cond)) return MTD_EINVAL;                      \
+  } while (0)
+
+enum MtdAct { MTD_ACT_NONE = 0, MTD_ACT_RELU = 1, MTD_ACT_LEAKY = 2 };
+
+__device__ __forceinline__ float mtd_act(float v, int act, float slope) {
+  if (act == MTD_ACT_RELU) return v > 0.f ? v : 0.f;
+  if (act == MTD_ACT_LEAKY) return v > 0.f ? v : v * slope;
+  return v;
+}
+// derivative expressed on the ACTIVATED output y (sign(y) == sign(z) for relu/leaky; at 0 both
+// torch backward formulas give 0 / slope respectively — SURVEY A10).
+__device__ __forceinline__ float mtd_act_grad(float y, int act, float slope) {
+  if (act == MTD_ACT_RELU) return y > 0.f ? 1.f : 0.f;
+  if (act == MTD_ACT_LEAKY) return y > 0.f ? 1.f : slope;
+  return 1.f;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Block-wide sum; result valid in thread 0 (and broadcast to all when `bcast`).  `sh` needs 32 slots.
+template <typename T>
+__device__ __forceinline__ T block_sum(T v, T* sh, bool bcast = false) {
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) sh[w] = v;
+  __syncthreads();
+  if (w == 0) {
+    T t = lane < nw ? sh[lane] : T(0);
+    t = warp_sum(t);
+    if (lane == 0) sh[0] = t;
+  }
+  if (bcast) {
+    __syncthreads();
+    v = sh[0];
+  } else {
+    v = (threadIdx.x == 0) ? sh[0] : T(0);
+  }
+  return v;
+}
+
+static inline int mtd_sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+static inline bool mtd_aligned16(const void* p) { return (((uintptr_t)p) & 15u) == 0; }

@@ -1,0 +1,782 @@
+// NHWC fp32 implicit-GEMM convolution on the CUDA cores (exact fp32 FMA accumulation, rel. error
+// ~1e-6 vs the oracle).  One generic tap-table kernel serves forward convs (3x3 s1, 4x4 s2, 1x1,
+// Linear), stride-1 dgrad (tap offsets p-ky) and stride-2 dgrad (four output-parity classes of 2x2
+// taps).  It is the exact-precision path: the tcgen05 TF32 kernel (conv_tc.cu) takes the large-M
+// layers, this one keeps the skinny-M weight-streaming layers (split-K), the thin layers
+// (Cin or Cout == 1) and every weight-gradient GEMM.
+//
+// Replaces: every nn.Conv2d / nn.ConvTranspose2d / nn.Linear call of arch/Ours/networks.py:18-19,
+// 41-46, 170, 181-306 and their autograd backward (ATen convolution_backward).
+#include <algorithm>
+#include "common.cuh"
+#include "mtdgan_b200.h"
+
+namespace {
+
+constexpr int kMaxTaps = 16;
+
+struct ConvArgs {
+  const float* src1;
+  const float* src2;
+  int C1, C2;
+  int B, H, W;          // source spatial dims
+  const float* wp;      // packed weights [N][T][C1+C2]
+  int N, T;
+  int Ho, Wo;           // logical output grid of this launch
+  int sy, sx;           // source coord = o * s + d[t]
+  int dy[kMaxTaps], dx[kMaxTaps];
+  float* out;           // (B, outH, outW, N); pixel = (oy*omy+ooy, ox*omx+oox)
+  int outH, outW, omy, omx, ooy, oox;
+  // epilogue: v = acc*scale + bias; v = pre_act(v); aux = v; v += add1 + add2; v = post_act(v);
+  //           v *= act'(mask_src)
+  const float* scale;   // device scalar (1/sigma) or null
+  const float* bias;
+  int pre_act;
+  const float* add1;
+  const float* add2;
+  int post_act;
+  const float* mask_src;
+  int mask_act;
+  float slope;
+  float* aux;
+  // split-K: when splits > 1 raw partial sums are atomically added into `out` (pre-zeroed) and the
+  // epilogue runs in conv_epilogue_kernel.
+  int splits;
+};
+
+__device__ __forceinline__ float conv_epilogue_one(const ConvArgs& a, float v, size_t idx, int n) {
+  if (a.scale) v *= __ldg(a.scale);
+  if (a.bias) v += __ldg(a.bias + n);
+  v = mtd_act(v, a.pre_act, a.slope);
+  if (a.aux) a.aux[idx] = v;
+  if (a.add1) v += __ldg(a.add1 + idx);
+  if (a.add2) v += __ldg(a.add2 + idx);
+  v = mtd_act(v, a.post_act, a.slope);
+  if (a.mask_src) v *= mtd_act_grad(__ldg(a.mask_src + idx), a.mask_act, a.slope);
+  return v;
+}
+
+template <int TM, int TN, bool VEC>
+__global__ void __launch_bounds__(256) conv_igemm_kernel(const __grid_constant__ ConvArgs a) {
+  constexpr int BM = 16 * TM, BN = 16 * TN, BK = 16;
+  constexpr int A_PER = (BM * 4 + 255) / 256;
+  constexpr int B_PER = (BN * 4 + 255) / 256;
+  __shared__ __align__(16) float As[2][BK][BM];
+  __shared__ __align__(16) float Bs[2][BK][BN];
+
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  const int Ctot = a.C1 + a.C2;
+  const int HoWo = a.Ho * a.Wo;
+  const int M = a.B * HoWo;
+  const int nchunk = (Ctot + BK - 1) / BK;
+  const int niter = a.T * nchunk;
+  int it_begin = 0, it_end = niter;
+  if (a.splits > 1) {
+    int per = (niter + a.splits - 1) / a.splits;
+    it_begin = blockIdx.z * per;
+    it_end = min(niter, it_begin + per);
+    if (it_begin >= it_end) return;
+  }
+
+  // per-slot pixel decode for the A loader (rows are fixed per thread for the whole K loop)
+  int a_b[A_PER], a_ys[A_PER], a_xs[A_PER];
+  bool a_ok[A_PER];
+#pragma unroll
+  for (int p = 0; p < A_PER; ++p) {
+    int s = tid + p * 256;
+    int row = s >> 2;
+    int m = m0 + row;
+    a_ok[p] = (row < BM) && (m < M);
+    int mm = a_ok[p] ? m : 0;
+    int b = mm / HoWo, r = mm - b * HoWo;
+    int oy = r / a.Wo, ox = r - oy * a.Wo;
+    a_b[p] = b;
+    a_ys[p] = oy * a.sy;
+    a_xs[p] = ox * a.sx;
+  }
+
+  float4 ra[A_PER], rb[B_PER];
+
+  auto load_tiles = [&](int it) {
+    int t = it / nchunk;
+    int c0 = (it - t * nchunk) * BK;
+    int ddy = a.dy[t], ddx = a.dx[t];
+#pragma unroll
+    for (int p = 0; p < A_PER; ++p) {
+      int s = tid + p * 256;
+      int kq = s & 3;
+      int c = c0 + kq * 4;
+      int iy = a_ys[p] + ddy, ix = a_xs[p] + ddx;
+      bool ok = a_ok[p] && iy >= 0 && iy < a.H && ix >= 0 && ix < a.W;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (ok) {
+        size_t pix = ((size_t)a_b[p] * a.H + iy) * a.W + ix;
+        if (VEC) {
+          if (c < a.C1) v = __ldg(reinterpret_cast<const float4*>(a.src1 + pix * a.C1 + c));
+          else if (c < Ctot) v = __ldg(reinterpret_cast<const float4*>(a.src2 + pix * a.C2 + (c - a.C1)));
+        } else {
+          float tmp[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            int cc = c + j;
+            tmp[j] = cc < a.C1 ? __ldg(a.src1 + pix * a.C1 + cc)
+                               : (cc < Ctot ? __ldg(a.src2 + pix * a.C2 + (cc - a.C1)) : 0.f);
+          }
+          v = make_float4(tmp[0], tmp[1], tmp[2], tmp[3]);
+        }
+      }
+      ra[p] = v;
+    }
+#pragma unroll
+    for (int p = 0; p < B_PER; ++p) {
+      int s = tid + p * 256;
+      int row = s >> 2, kq = s & 3;
+      int n = n0 + row;
+      int c = c0 + kq * 4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (row < BN && n < a.N) {
+        const float* wrow = a.wp + ((size_t)n * a.T + t) * Ctot;
+        if (VEC) {
+          if (c < Ctot) v = __ldg(reinterpret_cast<const float4*>(wrow + c));
+        } else {
+          float tmp[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) tmp[j] = (c + j < Ctot) ? __ldg(wrow + c + j) : 0.f;
+          v = make_float4(tmp[0], tmp[1], tmp[2], tmp[3]);
+        }
+      }
+      rb[p] = v;
+    }
+  };
+
+  auto store_tiles = [&](int buf) {
+#pragma unroll
+    for (int p = 0; p < A_PER; ++p) {
+      int s = tid + p * 256;
+      int row = s >> 2, kq = s & 3;
+      if (row < BM) {
+        As[buf][kq * 4 + 0][row] = ra[p].x;
+        As[buf][kq * 4 + 1][row] = ra[p].y;
+        As[buf][kq * 4 + 2][row] = ra[p].z;
+        As[buf][kq * 4 + 3][row] = ra[p].w;
+      }
+    }
+#pragma unroll
+    for (int p = 0; p < B_PER; ++p) {
+      int s = tid + p * 256;
+      int row = s >> 2, kq = s & 3;
+      if (row < BN) {
+        Bs[buf][kq * 4 + 0][row] = rb[p].x;
+        Bs[buf][kq * 4 + 1][row] = rb[p].y;
+        Bs[buf][kq * 4 + 2][row] = rb[p].z;
+        Bs[buf][kq * 4 + 3][row] = rb[p].w;
+      }
+    }
+  };
+
+  float acc[TM][TN];
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+  load_tiles(it_begin);
+  store_tiles(0);
+  __syncthreads();
+  int buf = 0;
+  for (int it = it_begin; it < it_end; ++it) {
+    bool has_next = (it + 1) < it_end;
+    if (has_next) load_tiles(it + 1);
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      float av[TM], bv[TN];
+#pragma unroll
+      for (int i = 0; i < TM; ++i) av[i] = As[buf][k][ty * TM + i];
+#pragma unroll
+      for (int j = 0; j < TN; ++j) bv[j] = Bs[buf][k][tx * TN + j];
+#pragma unroll
+      for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    if (has_next) store_tiles(buf ^ 1);
+    __syncthreads();
+    buf ^= 1;
+  }
+
+  // epilogue
+#pragma unroll
+  for (int i = 0; i < TM; ++i) {
+    int m = m0 + ty * TM + i;
+    if (m >= M) continue;
+    int b = m / HoWo, r = m - b * HoWo;
+    int oy = r / a.Wo, ox = r - oy * a.Wo;
+    size_t pix = ((size_t)b * a.outH + (oy * a.omy + a.ooy)) * a.outW + (ox * a.omx + a.oox);
+#pragma unroll
+    for (int j = 0; j < TN; ++j) {
+      int n = n0 + tx * TN + j;
+      if (n >= a.N) continue;
+      size_t idx = pix * a.N + n;
+      if (a.splits > 1) atomicAdd(a.out + idx, acc[i][j]);
+      else a.out[idx] = conv_epilogue_one(a, acc[i][j], idx, n);
+    }
+  }
+}
+
+// second phase of a split-K conv: out holds raw sums
+__global__ void conv_epilogue_kernel(const __grid_constant__ ConvArgs a, size_t total) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < total; i += stride) {
+    int n = (int)(i % a.N);
+    a.out[i] = conv_epilogue_one(a, a.out[i], i, n);
+  }
+}
+
+int launch_conv(ConvArgs& a, cudaStream_t st) {
+  const int Ctot = a.C1 + a.C2;
+  const int M = a.B * a.Ho * a.Wo;
+  if (M <= 0 || a.N <= 0 || Ctot <= 0 || a.T <= 0 || a.T > kMaxTaps) return MTD_EINVAL;
+  bool vec = (a.C1 % 4 == 0) && (a.C2 % 4 == 0) && mtd_aligned16(a.src1) && mtd_aligned16(a.wp) &&
+             (a.C2 == 0 || mtd_aligned16(a.src2));
+  bool thin_n = a.N <= 16;
+  const int BM = thin_n ? 128 : 64, BN = thin_n ? 16 : 64;
+  dim3 grid((M + BM - 1) / BM, (a.N + BN - 1) / BN, 1);
+  const int niter = a.T * ((Ctot + 15) / 16);
+  int ctas = grid.x * grid.y;
+  int splits = 1;
+  const int target = 2 * mtd_sm_count();
+  bool full_out = (a.omy == 1 && a.omx == 1);   // split-K epilogue pass assumes a dense output
+  if (ctas < target && niter >= 16 && full_out) {
+    splits = std::min((target + ctas - 1) / ctas, niter / 8);
+    if (splits < 1) splits = 1;
+    if (splits > 64) splits = 64;
+  }
+  a.splits = splits;
+  grid.z = splits;
+  size_t total = (size_t)a.B * a.outH * a.outW * a.N;
+  if (splits > 1) MTD_CUDA(cudaMemsetAsync(a.out, 0, total * sizeof(float), st));
+  if (thin_n) {
+    if (vec) conv_igemm_kernel<8, 1, true><<<grid, 256, 0, st>>>(a);
+    else conv_igemm_kernel<8, 1, false><<<grid, 256, 0, st>>>(a);
+  } else {
+    if (vec) conv_igemm_kernel<4, 4, true><<<grid, 256, 0, st>>>(a);
+    else conv_igemm_kernel<4, 4, false><<<grid, 256, 0, st>>>(a);
+  }
+  MTD_CHECK_LAUNCH();
+  if (splits > 1) {
+    int blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)mtd_sm_count() * 8);
+    conv_epilogue_kernel<<<blocks, 256, 0, st>>>(a, total);
+    MTD_CHECK_LAUNCH();
+  }
+  return MTD_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// weight packing:  out[n][t][c] = w[n*sN + c*sC + toff[t]]   (and its inverse for gradients)
+// ---------------------------------------------------------------------------------------------
+struct PackArgs {
+  int N, T, C;
+  long long sN, sC;
+  int toff[kMaxTaps];
+};
+
+__global__ void pack_weights_kernel(const float* __restrict__ w, float* __restrict__ out, const __grid_constant__ PackArgs p) {
+  size_t total = (size_t)p.N * p.T * p.C;
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < total; i += stride) {
+    int c = (int)(i % p.C);
+    size_t r = i / p.C;
+    int t = (int)(r % p.T);
+    int n = (int)(r / p.T);
+    out[i] = __ldg(w + (size_t)n * p.sN + (size_t)c * p.sC + p.toff[t]);
+  }
+}
+
+// dw_ref[n*sN + c*sC + toff[t]] = alpha * (gp[n][t][c] - beta * u[n_sn] * v[k_sn])
+// where for spectral-normed layers alpha = 1/sigma, beta = <G,W>/sigma and (u,v) index the
+// (Cout, Cin*kh*kw) matrix view of the REFERENCE layout.
+struct UnpackArgs {
+  PackArgs p;
+  const float* inv_sigma;   // null => plain layer
+  const float* dotgw;       // device scalar <G, W_orig>
+  const float* u;
+  const float* v;
+  int sn_rows;              // Cout of the reference weight; row = ref_index / sn_cols
+  long long sn_cols;
+};
+
+__global__ void unpack_grad_kernel(const float* __restrict__ gp, float* __restrict__ dw, const __grid_constant__ UnpackArgs a) {
+  const PackArgs& p = a.p;
+  size_t total = (size_t)p.N * p.T * p.C;
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  float alpha = 1.f, beta = 0.f;
+  if (a.inv_sigma) {
+    alpha = __ldg(a.inv_sigma);
+    beta = __ldg(a.dotgw) * alpha;
+  }
+  for (; i < total; i += stride) {
+    int c = (int)(i % p.C);
+    size_t r = i / p.C;
+    int t = (int)(r % p.T);
+    int n = (int)(r / p.T);
+    size_t ref = (size_t)n * p.sN + (size_t)c * p.sC + p.toff[t];
+    float g = gp[i];
+    if (a.inv_sigma) {
+      size_t row = ref / a.sn_cols, col = ref - row * a.sn_cols;
+      g = alpha * (g - beta * __ldg(a.u + row) * __ldg(a.v + col));
+    }
+    dw[ref] = g;
+  }
+}
+
+// <gp, w_ref> with the same index mapping; fp64 accumulation, one atomicAdd(double) per block,
+// final value converted by dot_finish_kernel.
+__global__ void dot_packed_ref_kernel(const float* __restrict__ gp, const float* __restrict__ w, double* __restrict__ acc,
+                                      const __grid_constant__ PackArgs p) {
+  __shared__ double sh[32];
+  size_t total = (size_t)p.N * p.T * p.C;
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  double s = 0.0;
+  for (; i < total; i += stride) {
+    int c = (int)(i % p.C);
+    size_t r = i / p.C;
+    int t = (int)(r % p.T);
+    int n = (int)(r / p.T);
+    s += (double)gp[i] * (double)__ldg(w + (size_t)n * p.sN + (size_t)c * p.sC + p.toff[t]);
+  }
+  s = block_sum(s, sh);
+  if (threadIdx.x == 0) atomicAdd(acc, s);
+}
+__global__ void dot_finish_kernel(const double* acc, float* out) { *out = (float)(*acc); }
+
+// Fill the (sN, sC, toff) mapping for a reference weight tensor.
+//   transposed == 0: Conv2d / Linear layout (Cout, Cin, kh, kw)
+//   transposed == 1: ConvTranspose2d layout (Cin, Cout, kh, kw), stride 1: the equivalent conv
+//                    weight is W[co][ci][ky][kx] = Wt[ci][co][kh-1-ky][kw-1-kx]   
+// Forward orientation: n = co, c = ci, tap t = (ky, kx) with source offset (ky - pad, kx - pad).
+void fwd_mapping(PackArgs& p, int transposed, int Cout, int Cin, int kh, int kw) {
+  p.N = Cout; p.T = kh * kw; p.C = Cin;
+  if (!transposed) {
+    p.sN = (long long)Cin * kh * kw; p.sC = (long long)kh * kw;
+    for (int t = 0; t < p.T; ++t) p.toff[t] = t;
+  } else {
+    p.sN = (long long)kh * kw; p.sC = (long long)Cout * kh * kw;
+    for (int t = 0; t < p.T; ++t) p.toff[t] = p.T - 1 - t;
+  }
+}
+
+int pack_launch(const float* w, float* out, const PackArgs& p, cudaStream_t st) {
+  size_t total = (size_t)p.N * p.T * p.C;
+  int blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)mtd_sm_count() * 16);
+  pack_weights_kernel<<<blocks, 256, 0, st>>>(w, out, p);
+  MTD_CHECK_LAUNCH();
+  return MTD_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// weight gradient:  gp[n][t][c] = sum_p dz[p][n] * x[p@t][c]
+// ---------------------------------------------------------------------------------------------
+struct WgradArgs {
+  const float* src1;
+  const float* src2;
+  int C1, C2;
+  int B, H, W;
+  const float* dz;
+  int N, Ho, Wo;
+  int T, sy, sx;
+  int dy[kMaxTaps], dx[kMaxTaps];
+  float* gp;
+  int splits;
+};
+
+template <int TN, int TC, bool VEC>
+__global__ void __launch_bounds__(256) conv_wgrad_kernel(const __grid_constant__ WgradArgs a) {
+  constexpr int BN = 16 * TN, BC = 16 * TC, BK = 16;
+  constexpr int A_Q = BN / 4, B_Q = BC / 4;                 // float4 slots per pixel row
+  constexpr int A_PER = (BK * A_Q + 255) / 256, B_PER = (BK * B_Q + 255) / 256;
+  __shared__ __align__(16) float As[2][BK][BN];
+  __shared__ __align__(16) float Bs[2][BK][BC];
+
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int n0 = blockIdx.x * BN, c0 = blockIdx.y * BC;
+  const int t = blockIdx.z / a.splits, split = blockIdx.z - t * a.splits;
+  const int Ctot = a.C1 + a.C2;
+  const int HoWo = a.Ho * a.Wo;
+  const int M = a.B * HoWo;
+  const int per = (((M + a.splits - 1) / a.splits) + BK - 1) / BK * BK;
+  const int p_begin = split * per, p_end = min(M, p_begin + per);
+  if (p_begin >= p_end) return;
+  const int nsteps = (p_end - p_begin + BK - 1) / BK;
+  const int ddy = a.dy[t], ddx = a.dx[t];
+
+  float4 ra[A_PER], rb[B_PER];
+  auto load_tiles = [&](int step) {
+    int pbase = p_begin + step * BK;
+#pragma unroll
+    for (int q = 0; q < A_PER; ++q) {
+      int s = tid + q * 256;
+      int prow = s / A_Q, nq = s - prow * A_Q;
+      int p = pbase + prow;
+      int n = n0 + nq * 4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (prow < BK && p < p_end) {
+        const float* row = a.dz + (size_t)p * a.N;
+        if (VEC) { if (n < a.N) v = __ldg(reinterpret_cast<const float4*>(row + n)); }
+        else {
+          float tmp[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) tmp[j] = (n + j < a.N) ? __ldg(row + n + j) : 0.f;
+          v = make_float4(tmp[0], tmp[1], tmp[2], tmp[3]);
+        }
+      }
+      ra[q] = v;
+    }
+#pragma unroll
+    for (int q = 0; q < B_PER; ++q) {
+      int s = tid + q * 256;
+      int prow = s / B_Q, cq = s - prow * B_Q;
+      int p = pbase + prow;
+      int c = c0 + cq * 4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (prow < BK && p < p_end) {
+        int b = p / HoWo, r = p - b * HoWo;
+        int oy = r / a.Wo, ox = r - oy * a.Wo;
+        int iy = oy * a.sy + ddy, ix = ox * a.sx + ddx;
+        if (iy >= 0 && iy < a.H && ix >= 0 && ix < a.W) {
+          size_t pix = ((size_t)b * a.H + iy) * a.W + ix;
+          if (VEC) {
+            if (c < a.C1) v = __ldg(reinterpret_cast<const float4*>(a.src1 + pix * a.C1 + c));
+            else if (c < Ctot) v = __ldg(reinterpret_cast<const float4*>(a.src2 + pix * a.C2 + (c - a.C1)));
+          } else {
+            float tmp[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              int cc = c + j;
+              tmp[j] = cc < a.C1 ? __ldg(a.src1 + pix * a.C1 + cc)
+                                 : (cc < Ctot ? __ldg(a.src2 + pix * a.C2 + (cc - a.C1)) : 0.f);
+            }
+            v = make_float4(tmp[0], tmp[1], tmp[2], tmp[3]);
+          }
+        }
+      }
+      rb[q] = v;
+    }
+  };
+  auto store_tiles = [&](int buf) {
+#pragma unroll
+    for (int q = 0; q < A_PER; ++q) {
+      int s = tid + q * 256;
+      int prow = s / A_Q, nq = s - prow * A_Q;
+      if (prow < BK) *reinterpret_cast<float4*>(&As[buf][prow][nq * 4]) = ra[q];
+    }
+#pragma unroll
+    for (int q = 0; q < B_PER; ++q) {
+      int s = tid + q * 256;
+      int prow = s / B_Q, cq = s - prow * B_Q;
+      if (prow < BK) *reinterpret_cast<float4*>(&Bs[buf][prow][cq * 4]) = rb[q];
+    }
+  };
+
+  float acc[TN][TC];
+#pragma unroll
+  for (int i = 0; i < TN; ++i)
+#pragma unroll
+    for (int j = 0; j < TC; ++j) acc[i][j] = 0.f;
+
+  load_tiles(0);
+  store_tiles(0);
+  __syncthreads();
+  int buf = 0;
+  for (int step = 0; step < nsteps; ++step) {
+    bool has_next = step + 1 < nsteps;
+    if (has_next) load_tiles(step + 1);
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      float av[TN], bv[TC];
+#pragma unroll
+      for (int i = 0; i < TN; ++i) av[i] = As[buf][k][ty * TN + i];
+#pragma unroll
+      for (int j = 0; j < TC; ++j) bv[j] = Bs[buf][k][tx * TC + j];
+#pragma unroll
+      for (int i = 0; i < TN; ++i)
+#pragma unroll
+        for (int j = 0; j < TC; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    if (has_next) store_tiles(buf ^ 1);
+    __syncthreads();
+    buf ^= 1;
+  }
+#pragma unroll
+  for (int i = 0; i < TN; ++i) {
+    int n = n0 + ty * TN + i;
+    if (n >= a.N) continue;
+#pragma unroll
+    for (int j = 0; j < TC; ++j) {
+      int c = c0 + tx * TC + j;
+      if (c >= Ctot) continue;
+      float* dst = a.gp + ((size_t)n * a.T + t) * Ctot + c;
+      if (a.splits > 1) atomicAdd(dst, acc[i][j]);
+      else *dst = acc[i][j];
+    }
+  }
+}
+
+int launch_wgrad(WgradArgs& a, cudaStream_t st) {
+  const int Ctot = a.C1 + a.C2;
+  const int M = a.B * a.Ho * a.Wo;
+  if (M <= 0 || a.N <= 0 || Ctot <= 0 || a.T <= 0 || a.T > kMaxTaps) return MTD_EINVAL;
+  bool vec = (a.C1 % 4 == 0) && (a.C2 % 4 == 0) && (a.N % 4 == 0) && mtd_aligned16(a.src1) &&
+             mtd_aligned16(a.dz) && (a.C2 == 0 || mtd_aligned16(a.src2));
+  bool thin_n = a.N <= 16, thin_c = Ctot <= 16;
+  int BN = thin_n ? 16 : 64, BC = thin_c ? 16 : 64;
+  dim3 grid((a.N + BN - 1) / BN, (Ctot + BC - 1) / BC, a.T);
+  int tiles = grid.x * grid.y * grid.z;
+  int target = 4 * mtd_sm_count();
+  int splits = 1;
+  if (tiles < target) splits = std::min((target + tiles - 1) / tiles, std::max(1, M / 64));
+  if (splits > 256) splits = 256;
+  a.splits = splits;
+  grid.z = a.T * splits;
+  if (splits > 1) MTD_CUDA(cudaMemsetAsync(a.gp, 0, (size_t)a.N * a.T * Ctot * sizeof(float), st));
+#define WG_LAUNCH(TN_, TC_)                                                              \
+  do {                                                                                   \
+    if (vec) conv_wgrad_kernel<TN_, TC_, true><<<grid, 256, 0, st>>>(a);                 \
+    else conv_wgrad_kernel<TN_, TC_, false><<<grid, 256, 0, st>>>(a);                    \
+  } while (0)
+  if (thin_n && thin_c) WG_LAUNCH(1, 1);
+  else if (thin_n) WG_LAUNCH(1, 4);
+  else if (thin_c) WG_LAUNCH(4, 1);
+  else WG_LAUNCH(4, 4);
+#undef WG_LAUNCH
+  MTD_CHECK_LAUNCH();
+  return MTD_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// dz = dy * act'(y)  (+ per-channel sums of dz accumulated into dbias, pre-zeroed by the caller
+// wrapper).  (M, N) row-major, N = channels.
+// ---------------------------------------------------------------------------------------------
+__global__ void act_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y, float* __restrict__ dz,
+                               float* __restrict__ dbias, size_t total, int N, int act, float slope) {
+  extern __shared__ float colsum[];   // N floats when dbias != null
+  if (dbias) {
+    for (int i = threadIdx.x; i < N; i += blockDim.x) colsum[i] = 0.f;
+    __syncthreads();
+  }
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  const bool fixed = dbias && (stride % (size_t)N == 0);   // channel of this thread never changes
+  float priv = 0.f;
+  for (; i < total; i += stride) {
+    float g = dy[i];
+    if (act != MTD_ACT_NONE) g *= mtd_act_grad(__ldg(y + i), act, slope);
+    if (dz) dz[i] = g;
+    if (dbias) {
+      if (fixed) priv += g;
+      else atomicAdd(&colsum[i % N], g);
+    }
+  }
+  if (dbias) {
+    if (fixed) {
+      size_t first = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+      atomicAdd(&colsum[first % N], priv);
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < N; c += blockDim.x) {
+      float v = colsum[c];
+      if (v != 0.f) atomicAdd(dbias + c, v);
+    }
+  }
+}
+
+void tap_table_fwd(int* dy, int* dx, int kh, int kw, int pad) {
+  for (int ky = 0; ky < kh; ++ky)
+    for (int kx = 0; kx < kw; ++kx) {
+      dy[ky * kw + kx] = ky - pad;
+      dx[ky * kw + kx] = kx - pad;
+    }
+}
+
+}  // namespace
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+extern "C" {
+
+int mtd_conv_pack_fwd(const float* w_ref, int transposed, int Cout, int Cin, int kh, int kw, float* out, void* stream) {
+  MTD_REQUIRE(w_ref && out && Cout > 0 && Cin > 0 && kh > 0 && kw > 0 && kh * kw <= kMaxTaps);
+  PackArgs p;
+  fwd_mapping(p, transposed, Cout, Cin, kh, kw);
+  return pack_launch(w_ref, out, p, (cudaStream_t)stream);
+}
+
+// dgrad packing.  stride 1: out[ci][t][co] with t = ky*kw+kx (source offset pad-ky, pad-kx).
+// stride 2 (4x4, pad 1 only): out[cls][ci][t2][co], cls = py*2+px, t2 = a*2+b where
+// ky = (1-py) + 2a, kx = (1-px) + 2b.
+int mtd_conv_pack_dgrad(const float* w_ref, int transposed, int Cout, int Cin, int kh, int kw, int stride, float* out,
+                        void* stream) {
+  MTD_REQUIRE(w_ref && out && Cout > 0 && Cin > 0 && kh * kw <= kMaxTaps);
+  PackArgs f;
+  fwd_mapping(f, transposed, Cout, Cin, kh, kw);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (stride == 1) {
+    PackArgs p;
+    p.N = Cin; p.T = kh * kw; p.C = Cout; p.sN = f.sC; p.sC = f.sN;
+    for (int t = 0; t < p.T; ++t) p.toff[t] = f.toff[t];
+    return pack_launch(w_ref, out, p, st);
+  }
+  MTD_REQUIRE(stride == 2 && kh == 4 && kw == 4 && !transposed);
+  for (int py = 0; py < 2; ++py)
+    for (int px = 0; px < 2; ++px) {
+      PackArgs p;
+      p.N = Cin; p.T = 4; p.C = Cout; p.sN = f.sC; p.sC = f.sN;
+      for (int a = 0; a < 2; ++a)
+        for (int b = 0; b < 2; ++b) {
+          int ky = (1 - py) + 2 * a, kx = (1 - px) + 2 * b;
+          p.toff[a * 2 + b] = f.toff[ky * kw + kx];
+        }
+      int rc = pack_launch(w_ref, out + (size_t)(py * 2 + px) * Cin * 4 * Cout, p, st);
+      if (rc) return rc;
+    }
+  return MTD_OK;
+}
+
+int mtd_conv_fwd(const float* x1, const float* x2, const float* wp, const float* bias, const float* scale, float* y,
+                 float* aux, const float* add1, const float* add2, int B, int H, int W, int C1, int C2, int N, int kh,
+                 int kw, int stride, int pad, int pre_act, int post_act, float slope, void* stream) {
+  MTD_REQUIRE(x1 && wp && y && B > 0 && H > 0 && W > 0 && C1 > 0 && C2 >= 0 && N > 0);
+  MTD_REQUIRE((C2 == 0) == (x2 == nullptr));
+  MTD_REQUIRE(stride >= 1 && kh * kw <= kMaxTaps);
+  ConvArgs a{};
+  a.src1 = x1; a.src2 = x2; a.C1 = C1; a.C2 = C2; a.B = B; a.H = H; a.W = W;
+  a.wp = wp; a.N = N; a.T = kh * kw;
+  a.Ho = (H + 2 * pad - kh) / stride + 1;
+  a.Wo = (W + 2 * pad - kw) / stride + 1;
+  MTD_REQUIRE(a.Ho > 0 && a.Wo > 0);
+  a.sy = a.sx = stride;
+  tap_table_fwd(a.dy, a.dx, kh, kw, pad);
+  a.out = y; a.outH = a.Ho; a.outW = a.Wo; a.omy = a.omx = 1; a.ooy = a.oox = 0;
+  a.scale = scale; a.bias = bias; a.pre_act = pre_act; a.add1 = add1; a.add2 = add2; a.post_act = post_act;
+  a.mask_src = nullptr; a.mask_act = 0; a.slope = slope; a.aux = aux;
+  return launch_conv(a, (cudaStream_t)stream);
+}
+
+// dx (B,H,W,Cin) = scale * dgrad(dz (B,Ho,Wo,Cout)) [+ add1 + add2] [* act'(mask_src)]
+int mtd_conv_dgrad(const float* dz, const float* wpd, float* dx, const float* scale, const float* add1,
+                   const float* add2, const float* mask_src, int mask_act, float slope, int B, int H, int W, int Cin,
+                   int Cout, int kh, int kw, int stride, int pad, void* stream) {
+  MTD_REQUIRE(dz && wpd && dx && B > 0 && Cin > 0 && Cout > 0 && kh * kw <= kMaxTaps);
+  const int Ho = (H + 2 * pad - kh) / stride + 1, Wo = (W + 2 * pad - kw) / stride + 1;
+  ConvArgs a{};
+  a.src1 = dz; a.src2 = nullptr; a.C1 = Cout; a.C2 = 0; a.B = B; a.H = Ho; a.W = Wo;
+  a.N = Cin;
+  a.out = dx; a.outH = H; a.outW = W;
+  a.scale = scale; a.bias = nullptr; a.pre_act = 0; a.add1 = add1; a.add2 = add2; a.post_act = 0;
+  a.mask_src = mask_src; a.mask_act = mask_act; a.slope = slope; a.aux = nullptr;
+  if (stride == 1) {
+    a.wp = wpd; a.T = kh * kw; a.Ho = H; a.Wo = W; a.sy = a.sx = 1;
+    for (int ky = 0; ky < kh; ++ky)
+      for (int kx = 0; kx < kw; ++kx) {
+        a.dy[ky * kw + kx] = pad - ky;
+        a.dx[ky * kw + kx] = pad - kx;
+      }
+    a.omy = a.omx = 1; a.ooy = a.oox = 0;
+    return launch_conv(a, (cudaStream_t)stream);
+  }
+  MTD_REQUIRE(stride == 2 && kh == 4 && kw == 4 && pad == 1 && H % 2 == 0 && W % 2 == 0);
+  // y = 2i+py receives ky with (py+1-ky) even: ky = (1-py)+2a, source row i + (py+1-ky)/2
+  for (int py = 0; py < 2; ++py)
+    for (int px = 0; px < 2; ++px) {
+      ConvArgs c = a;
+      c.wp = wpd + (size_t)(py * 2 + px) * Cin * 4 * Cout;
+      c.T = 4; c.Ho = H / 2; c.Wo = W / 2; c.sy = c.sx = 1;
+      for (int aa = 0; aa < 2; ++aa)
+        for (int bb = 0; bb < 2; ++bb) {
+          int ky = (1 - py) + 2 * aa, kx = (1 - px) + 2 * bb;
+          c.dy[aa * 2 + bb] = (py + 1 - ky) / 2;
+          c.dx[aa * 2 + bb] = (px + 1 - kx) / 2;
+        }
+      c.omy = c.omx = 2; c.ooy = py; c.oox = px;
+      int rc = launch_conv(c, (cudaStream_t)stream);
+      if (rc) return rc;
+    }
+  return MTD_OK;
+}
+
+// gp[N][T][C1+C2] = sum over pixels dz x (packed, forward orientation).
+int mtd_conv_wgrad(const float* x1, const float* x2, const float* dz, float* gp, int B, int H, int W, int C1, int C2,
+                   int N, int kh, int kw, int stride, int pad, void* stream) {
+  MTD_REQUIRE(x1 && dz && gp && B > 0 && C1 > 0 && C2 >= 0 && N > 0 && kh * kw <= kMaxTaps);
+  MTD_REQUIRE((C2 == 0) == (x2 == nullptr));
+  WgradArgs a{};
+  a.src1 = x1; a.src2 = x2; a.C1 = C1; a.C2 = C2; a.B = B; a.H = H; a.W = W;
+  a.dz = dz; a.N = N;
+  a.Ho = (H + 2 * pad - kh) / stride + 1;
+  a.Wo = (W + 2 * pad - kw) / stride + 1;
+  a.T = kh * kw; a.sy = a.sx = stride;
+  tap_table_fwd(a.dy, a.dx, kh, kw, pad);
+  a.gp = gp;
+  return launch_wgrad(a, (cudaStream_t)stream);
+}
+
+// dw_ref (reference layout) from packed gp; spectral-norm correction when inv_sigma != null:
+//   dW_orig = (G - <G, W~> u v^T) / sigma,  W~ = W_orig / sigma        
+// `scratch` = 8 bytes (double) + 4 bytes (float) of device workspace.
+int mtd_conv_wgrad_finish(const float* gp, float* dw_ref, int transposed, int Cout, int Cin, int kh, int kw,
+                          const float* w_ref, const float* u, const float* v, const float* inv_sigma, void* scratch,
+                          void* stream) {
+  MTD_REQUIRE(gp && dw_ref && Cout > 0 && Cin > 0 && kh * kw <= kMaxTaps);
+  cudaStream_t st = (cudaStream_t)stream;
+  UnpackArgs a{};
+  fwd_mapping(a.p, transposed, Cout, Cin, kh, kw);
+  size_t total = (size_t)Cout * Cin * kh * kw;
+  int blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)mtd_sm_count() * 16);
+  if (inv_sigma) {
+    MTD_REQUIRE(w_ref && u && v && scratch && !transposed);
+    double* acc = (double*)scratch;
+    float* dotf = (float*)((char*)scratch + 8);
+    MTD_CUDA(cudaMemsetAsync(acc, 0, 8, st));
+    dot_packed_ref_kernel<<<blocks, 256, 0, st>>>(gp, w_ref, acc, a.p);
+    MTD_CHECK_LAUNCH();
+    dot_finish_kernel<<<1, 1, 0, st>>>(acc, dotf);
+    MTD_CHECK_LAUNCH();
+    a.inv_sigma = inv_sigma; a.dotgw = dotf; a.u = u; a.v = v;
+    a.sn_rows = Cout; a.sn_cols = (long long)Cin * kh * kw;
+  }
+  unpack_grad_kernel<<<blocks, 256, 0, st>>>(gp, dw_ref, a);
+  MTD_CHECK_LAUNCH();
+  return MTD_OK;
+}
+
+// dz = dy * act'(y); dbias[N] (optional) = column sums of dz.  dz may be null (colsum only) and may
+// alias dy.
+int mtd_act_bwd(const float* dy, const float* y, float* dz, float* dbias, long long M, int N, int act, float slope,
+                void* stream) {
+  MTD_REQUIRE(dy && M > 0 && N > 0 && (act == MTD_ACT_NONE || y));
+  cudaStream_t st = (cudaStream_t)stream;
+  size_t total = (size_t)M * N;
+  int blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)mtd_sm_count() * 8);
+  if (dbias) {
+    MTD_REQUIRE(N <= 8192);
+    MTD_CUDA(cudaMemsetAsync(dbias, 0, (size_t)N * sizeof(float), st));
+    // make the grid stride a multiple of N when possible (N is a power of two for every layer here)
+    size_t stride = (size_t)blocks * 256;
+    if (stride % N != 0 && (size_t)N <= stride) {
+      size_t s2 = stride / N * N;
+      if (s2 % 256 == 0 && s2 > 0) blocks = (int)(s2 / 256);
+    } else if ((size_t)N > stride) {
+      blocks = (N + 255) / 256;
+    }
+  }
+  act_bwd_kernel<<<blocks, 256, dbias ? N * sizeof(float) : 0, st>>>(dy, y, dz, dbias, total, N, act, slope);
+  MTD_CHECK_LAUNCH();
+  return MTD_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,364 @@
+"""B200-native MTD-GAN networks behind the reference's nn.Module surface.
+
+Same constructors, attribute names, parameter/buffer registration order, init RNG order and state_dict
+keys as arch/Ours/networks.py (FFT_ConvBlock :15-36, ResFFT_Generator :38-164, UpsampleBlock :166-175,
+Multi_Task_Discriminator_Skip :177-474, MTD_GAN_Method :1940-2009), so the reference's models.py /
+engine.py / train.py / test.py and its checkpoints work unchanged.  The torch layer objects only HOLD the
+parameters (they are never called): every forward/backward runs through the CUDA kernels of
+libmtdgan_sm100a.so on NHWC activations.  CPU tensors raise — there is no fallback path.
+"""
+from __future__ import annotations
+
+from itertools import chain
+from typing import Iterator, List, Optional
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import _ext
+from . import losses as L
+from .ops import (ACT_LEAKY, ACT_NONE, ACT_RELU, LEAK, Clip01Fn, ConvCfg, MulConstFn, PixelShuffle2Fn, Upsample2xFn,
+                  check_input, conv, fft_conv_block, to_nchw, to_nhwc)
+from ._ext import call, fptr, ptr, stream
+
+# test hook: fn(batch, features, device) -> already-scaled keep mask or None (None = draw from torch RNG)
+_dropout_mask_provider = None
+
+
+def set_dropout_mask_provider(fn):
+    global _dropout_mask_provider
+    _dropout_mask_provider = fn
+
+
+def _normal_init(module: nn.Module):
+    """`__init_weights` of the reference (networks.py:56-61, :310-315): N(0, 0.01) weights / zero bias for
+    modules whose type is EXACTLY Conv2d or Linear (so ConvTranspose2d keeps PyTorch's default init, and
+    spectral-normed layers are re-initialised through the `weight`/`weight_orig` storage alias)."""
+    for m in module.modules():
+        if type(m) in {nn.Conv2d, nn.Linear}:
+            m.weight.data.normal_(0, 0.01)
+            if hasattr(m.bias, 'data'):
+                m.bias.data.fill_(0)
+
+
+# ================================================================================================
+# Generator
+# ================================================================================================
+class FFT_ConvBlock(nn.Module):
+    def __init__(self, out_channels):
+        super().__init__()
+        self.img_conv = nn.Conv2d(out_channels, out_channels, kernel_size=3, stride=1, padding=1)
+        self.fft_conv = nn.Conv2d(out_channels * 2, out_channels * 2, kernel_size=1, stride=1, padding=0)
+
+    def forward_nhwc(self, x):
+        return fft_conv_block(x, self.img_conv.weight, self.img_conv.bias, self.fft_conv.weight, self.fft_conv.bias)
+
+    def forward(self, x):
+        """x: (B, C, H, W) like the reference; transposed to NHWC around the fused block."""
+        x = check_input(x, "FFT_ConvBlock")
+        return to_nchw(self.forward_nhwc(to_nhwc(x)))
+
+
+class ResFFT_Generator(nn.Module):
+    def __init__(self, in_channels=1, out_channels=96, num_layers=10, kernel_size=5, padding=0):
+        super().__init__()
+        enc = [nn.Conv2d(in_channels, out_channels, kernel_size=kernel_size, stride=1, padding=padding)]
+        dec = [nn.ConvTranspose2d(out_channels, in_channels, kernel_size=kernel_size, stride=1, padding=padding)]
+        for _ in range(num_layers):
+            enc.append(nn.Conv2d(out_channels, out_channels, kernel_size=kernel_size, stride=1, padding=padding))
+            dec.append(nn.ConvTranspose2d(out_channels, out_channels, kernel_size=kernel_size, stride=1, padding=padding))
+        self.encoder = nn.ModuleList(enc)
+        self.decoder = nn.ModuleList(dec)
+        self.enforce = nn.ModuleList([FFT_ConvBlock(out_channels) for _ in range(21)])   # hard-coded 21 (Q8)
+        self._geom = (in_channels, out_channels, num_layers, kernel_size, padding)
+        _normal_init(self)
+
+    # parameter partitions (networks.py:63-93): encoder[0..10] then decoder[-1..-11]; blocks excluded (Q7)
+    def shared_parameters(self) -> Iterator[nn.parameter.Parameter]:
+        return chain(*[self.encoder[i].parameters() for i in range(11)],
+                     *[self.decoder[-i].parameters() for i in range(1, 12)])
+
+    def task_specific_parameters(self) -> Iterator[nn.parameter.Parameter]:
+        return None
+
+    def last_shared_parameters(self) -> Iterator[nn.parameter.Parameter]:
+        return self.decoder[-11].parameters()
+
+    def forward(self, x: torch.Tensor):
+        cin, c, nl, k, p = self._geom
+        if nl != 10 or len(self.encoder) != 11:
+            raise _ext.MtdError("ResFFT_Generator.forward is defined for num_layers=10 only (reference hard-codes 11/11/21)")
+        if 2 * p != k - 1:
+            raise _ext.MtdError("B200 path needs a size-preserving conv (2*padding == kernel_size-1), e.g. k=3, p=1")
+        x = check_input(x, "ResFFT_Generator")
+        xin = to_nhwc(x)
+        e_cfg0 = ConvCfg(cin=cin, cout=c, kh=k, kw=k, stride=1, pad=p, pre_act=ACT_RELU)
+        e_cfg = ConvCfg(cin=c, cout=c, kh=k, kw=k, stride=1, pad=p, pre_act=ACT_RELU)
+        d_cfg = ConvCfg(cin=c, cout=c, kh=k, kw=k, stride=1, pad=p, transposed=1, post_act=ACT_RELU)
+        d_cfg0 = ConvCfg(cin=c, cout=cin, kh=k, kw=k, stride=1, pad=p, transposed=1, post_act=ACT_RELU)
+        enc, dec, blk = self.encoder, self.decoder, self.enforce
+        skips: List[torch.Tensor] = []
+        t = xin
+        for i in range(10):                                                   # networks.py:97-125
+            t = conv(t, enc[i].weight, enc[i].bias, e_cfg0 if i == 0 else e_cfg)
+            t = blk[i].forward_nhwc(t)
+            skips.append(t)
+        t = blk[10].forward_nhwc(conv(t, enc[10].weight, enc[10].bias, e_cfg))  # :128-129
+        t = conv(t, dec[10].weight, dec[10].bias, d_cfg, add1=skips[9])         # :132
+        for i in range(9, 0, -1):                                             # :134-159
+            t = blk[20 - i].forward_nhwc(t)
+            t = conv(t, dec[i].weight, dec[i].bias, d_cfg, add1=skips[i - 1])
+        t = blk[20].forward_nhwc(t)                                           # :161
+        t = conv(t, dec[0].weight, dec[0].bias, d_cfg0, add1=xin)             # :162
+        return to_nchw(t)
+
+
+# ================================================================================================
+# Discriminator
+# ================================================================================================
+class UpsampleBlock(nn.Module):
+    def __init__(self, scale, input_channels, output_channels):
+        super().__init__()
+        self.upsample = nn.Sequential(
+            nn.Conv2d(input_channels, output_channels * (scale ** 2), kernel_size=1, stride=1, padding=0),
+            nn.PixelShuffle(upscale_factor=scale))
+        self._scale = scale
+
+    def forward_nhwc(self, x, freeze=False):
+        cv = self.upsample[0]
+        if self._scale != 2:
+            raise _ext.MtdError("UpsampleBlock on the B200 path supports scale=2 (the only value the reference uses)")
+        w, b = (cv.weight.detach(), cv.bias.detach()) if freeze else (cv.weight, cv.bias)
+        t = conv(x, w, b, ConvCfg(cin=cv.in_channels, cout=cv.out_channels, kh=1, kw=1, stride=1, pad=0))
+        return PixelShuffle2Fn.apply(t)
+
+    def forward(self, input):
+        input = check_input(input, "UpsampleBlock")
+        return to_nchw(self.forward_nhwc(to_nhwc(input)))
+
+
+class _SNState:
+    """Device tables for the batched spectral-norm kernel (rebuilt when parameter storage moves)."""
+
+    def __init__(self, mods: List[nn.Module], device):
+        rows_per = _ext.load().mtd_sn_rows_per_wtu_item()
+        tab, wtu, wv = [], [], []
+        uoff = voff = 0
+        self.slices = []
+        for i, m in enumerate(mods):
+            w = m.weight_orig
+            rows, cols = w.shape[0], w.numel() // w.shape[0]
+            tab.append([w.data_ptr(), m.weight_u.data_ptr(), m.weight_v.data_ptr(), rows, cols, uoff, voff, 0])
+            for c0 in range(0, cols, 256):
+                for r0 in range(0, rows, rows_per):
+                    wtu.append([i, c0, r0, 0])
+            for r0 in range(0, rows, 8):
+                wv.append([i, r0])
+            self.slices.append((uoff, rows, voff, cols))
+            uoff += rows
+            voff += cols
+        self.key = tuple(t[0] for t in tab) + tuple(t[1] for t in tab) + tuple(t[2] for t in tab)
+        self.n_layers, self.n_wtu, self.n_wv = len(mods), len(wtu), len(wv)
+        self.u_total, self.v_total = uoff, voff
+        self.tab = torch.tensor(tab, dtype=torch.int64).to(device)
+        self.wtu = torch.tensor(wtu, dtype=torch.int32).to(device)
+        self.wv = torch.tensor(wv, dtype=torch.int32).to(device)
+        self.t_ws = torch.empty(voff, dtype=torch.float32, device=device)
+        self.s_ws = torch.empty(uoff, dtype=torch.float32, device=device)
+
+    @staticmethod
+    def key_of(mods):
+        return (tuple(m.weight_orig.data_ptr() for m in mods) + tuple(m.weight_u.data_ptr() for m in mods)
+                + tuple(m.weight_v.data_ptr() for m in mods))
+
+
+class Multi_Task_Discriminator_Skip(nn.Module):
+    def __init__(self, in_channels, out_channels):
+        super().__init__()
+        c = out_channels
+        sn = nn.utils.spectral_norm
+        conv3 = lambda a, b: sn(nn.Conv2d(a, b, kernel_size=3, stride=1, padding=1))
+        act = lambda: nn.LeakyReLU(0.2)
+        self._sn_names: List[str] = []
+
+        def reg(name, module, is_sn=True):
+            setattr(self, name, module)
+            if is_sn:
+                self._sn_names.append(name)
+
+        # Enc (networks.py:181-215)
+        widths = [(in_channels, c), (c, 2 * c), (2 * c, 4 * c), (4 * c, 8 * c), (8 * c, 8 * c), (8 * c, 8 * c)]
+        for i, (a, b) in enumerate(widths, 1):
+            reg(f"conv{i}1", conv3(a, b)); reg(f"relu{i}1", act(), False)
+            reg(f"conv{i}2", conv3(b, b)); reg(f"relu{i}2", act(), False)
+            reg(f"down{i}", sn(nn.Conv2d(b, b, kernel_size=4, stride=2, padding=1)))
+        # Bot (:218-221)
+        reg("bconv1", sn(nn.Conv2d(8 * c, 8 * c, kernel_size=1, stride=1, padding=0))); reg("brelu1", act(), False)
+        reg("bconv2", sn(nn.Conv2d(8 * c, 8 * c, kernel_size=1, stride=1, padding=0))); reg("brelu2", act(), False)
+        # CLS Dec (:224-227)
+        self.c_flatten = nn.Flatten()
+        reg("c_fc", sn(nn.Linear(512, 512, True)))
+        self.c_relu = act()
+        self.c_drop = nn.Dropout(p=0.3)
+        # SEG / REC Dec (:230-301)
+        dec = [(16 * c, 8 * c), (16 * c, 8 * c), (16 * c, 4 * c), (8 * c, 2 * c), (4 * c, c), (2 * c, 1)]
+        ups = [8 * c, 8 * c, 8 * c, 4 * c, 2 * c, c]
+        for i, (a, b) in enumerate(dec, 1):
+            reg(f"s_up{i}", nn.Upsample(scale_factor=2, mode='bilinear', align_corners=False), False)
+            reg(f"s_dconv{i}1", conv3(a, b)); reg(f"s_drelu{i}1", act(), False)
+            reg(f"s_dconv{i}2", conv3(b, b)); reg(f"s_drelu{i}2", act(), False)
+        for i, ((a, b), uc) in enumerate(zip(dec, ups), 1):
+            reg(f"r_up{i}", UpsampleBlock(scale=2, input_channels=uc, output_channels=uc), False)
+            reg(f"r_dconv{i}1", conv3(a, b)); reg(f"r_drelu{i}1", act(), False)
+            reg(f"r_dconv{i}2", conv3(b, b)); reg(f"r_drelu{i}2", act(), False)
+        # Heads (:304-306)
+        self.enc_out = nn.Linear(512, 1)
+        self.dec_out = nn.Conv2d(in_channels, 1, 1)
+        self.rec_out = nn.Conv2d(in_channels, 1, 1)
+        self._sn_state: Optional[_SNState] = None
+        _normal_init(self)
+
+    # ---- parameter partitions (networks.py:318-380) -------------------------------------------------
+    def _params_of(self, names):
+        return chain(*[getattr(self, n).parameters() for n in names])
+
+    def shared_parameters(self) -> Iterator[nn.parameter.Parameter]:
+        names = []
+        for i in range(1, 7):
+            names += [f"conv{i}1", f"conv{i}2", f"down{i}"]
+        return self._params_of(names + ["bconv1", "bconv2"])
+
+    def task_specific_parameters(self) -> Iterator[nn.parameter.Parameter]:
+        names = [f"s_dconv{i}{j}" for i in range(1, 7) for j in (1, 2)]
+        for i in range(1, 7):
+            names += [f"r_up{i}", f"r_dconv{i}1", f"r_dconv{i}2"]
+        return self._params_of(names + ["enc_out", "dec_out", "rec_out"])
+
+    def last_shared_parameters(self) -> Iterator[nn.parameter.Parameter]:
+        return self.bconv2.parameters()
+
+    # ---- spectral norm -------------------------------------------------------------------------------
+    def _spectral_norm_step(self, device):
+        mods = [getattr(self, n) for n in self._sn_names]
+        if self._sn_state is None or self._sn_state.key != _SNState.key_of(mods):
+            self._sn_state = _SNState(mods, device)
+        s = self._sn_state
+        u_snap = torch.empty(s.u_total, dtype=torch.float32, device=device)
+        v_snap = torch.empty(s.v_total, dtype=torch.float32, device=device)
+        inv_sigma = torch.empty(s.n_layers, dtype=torch.float32, device=device)
+        call("mtd_sn_power_iter", ptr(s.tab), s.n_layers, ptr(s.wtu), s.n_wtu, ptr(s.wv), s.n_wv, fptr(s.t_ws), s.v_total,
+             fptr(s.s_ws), fptr(u_snap), fptr(v_snap), fptr(inv_sigma), 1 if self.training else 0, 1e-12, stream())
+        out = {}
+        for i, n in enumerate(self._sn_names):
+            uo, r, vo, cdim = s.slices[i]
+            out[n] = (inv_sigma[i:i + 1], u_snap[uo:uo + r], v_snap[vo:vo + cdim])
+        return out
+
+    # ---- forward (networks.py:383-474) -----------------------------------------------------------------
+    def forward(self, input, weight_grads: bool = True, need_rec: bool = True):
+        """Returns (x_enc (B,1), x_dec (B,1,64,64), x_rec (B,1,64,64)).
+
+        weight_grads=False treats the weights as constants (used by g_loss, where the reference's D weight
+        gradients are dead work wiped by the next zero_grad, engine.py:40-41,51); need_rec=False skips the
+        restoration decoder when the caller discards x_rec (networks.py:1969-1970, 1996) and returns None.
+        """
+        x = check_input(input, "Multi_Task_Discriminator_Skip")
+        if x.dim() != 4 or x.shape[2] != 64 or x.shape[3] != 64:
+            raise RuntimeError(f"Multi_Task_Discriminator_Skip expects (B, C, 64, 64) inputs, got {tuple(x.shape)}")
+        sn = self._spectral_norm_step(x.device)
+        frz = (lambda t: t.detach()) if not weight_grads else (lambda t: t)
+
+        def layer(name, x1, x2=None, act=ACT_LEAKY):
+            m = getattr(self, name)
+            if name in sn:
+                inv, u, v = sn[name]
+                w = m.weight_orig
+            else:
+                inv = u = v = None
+                w = m.weight
+            if isinstance(m, nn.Linear):
+                kh = kw = 1; stride, pad = 1, 0; cin, cout = m.in_features, m.out_features
+            else:
+                kh, kw = m.kernel_size; stride, pad = m.stride[0], m.padding[0]; cin, cout = m.in_channels, m.out_channels
+            cfg = ConvCfg(cin=cin, cout=cout, kh=kh, kw=kw, stride=stride, pad=pad, pre_act=act)
+            return conv(x1, frz(w), frz(m.bias), cfg, x2=x2, inv_sigma=inv, u=u, v=v)
+
+        t = to_nhwc(x)
+        skips = []
+        for i in range(1, 7):
+            t = layer(f"conv{i}1", t)
+            t = layer(f"conv{i}2", t)
+            skips.append(t)
+            t = layer(f"down{i}", t, act=ACT_NONE)          # no activation after down* (:387-407)
+        t = layer("bconv1", t)
+        x_bot = layer("bconv2", t)                          # (B,1,1,512)
+
+        # CLS decoder (:414-417, :470)
+        h = layer("c_fc", x_bot)
+        B = x.shape[0]
+        if self.training and self.c_drop.p > 0:
+            mask = _dropout_mask_provider(B, 512, x.device) if _dropout_mask_provider is not None else None
+            if mask is None:
+                mask = F.dropout(torch.ones(B, 512, device=x.device), self.c_drop.p, True)
+            h = MulConstFn.apply(h, mask.to(torch.float32).contiguous())
+        x_enc = layer("enc_out", h, act=ACT_NONE).reshape(B, 1)
+
+        # SEG decoder (:420-442, :471)
+        t = x_bot
+        for i in range(1, 7):
+            t = Upsample2xFn.apply(t)
+            t = layer(f"s_dconv{i}1", t, x2=skips[6 - i])
+            t = layer(f"s_dconv{i}2", t)
+        x_dec = to_nchw(layer("dec_out", t, act=ACT_NONE))
+
+        # REC decoder (:445-467, :472)
+        x_rec = None
+        if need_rec:
+            t = x_bot
+            for i in range(1, 7):
+                t = getattr(self, f"r_up{i}").forward_nhwc(t, freeze=not weight_grads)
+                t = layer(f"r_dconv{i}1", t, x2=skips[6 - i])
+                t = layer(f"r_dconv{i}2", t)
+            x_rec = to_nchw(layer("rec_out", t, act=ACT_NONE))
+        return x_enc, x_dec, x_rec
+
+
+# ================================================================================================
+# Method wrapper (networks.py:1940-2009)
+# ================================================================================================
+class MTD_GAN_Method(nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.Generator = ResFFT_Generator(in_channels=1, out_channels=32, num_layers=10, kernel_size=3, padding=1)
+        self.Discriminator = Multi_Task_Discriminator_Skip(in_channels=1, out_channels=64)
+        self.gan_metric_cls = L.ls_gan
+        self.gan_metric_seg = L.NDS_Loss
+        self.pixel_loss = L.CharbonnierLoss()
+        self.edge_loss = L.EdgeLoss()
+
+    def d_loss(self, x, y):
+        x, y = check_input(x, "d_loss"), check_input(y, "d_loss")
+        with torch.no_grad():                                               # == G(x).detach()  (:1958)
+            fake = self.Generator(x)
+        D = self.Discriminator
+        real_enc, real_dec, real_rec = D(y)                                 # :1959
+        fake_enc, fake_dec, fake_rec = D(fake)                              # :1960
+        dt = L.disc_terms(real_enc, fake_enc, real_dec, fake_dec, x, y)     # :1962
+        rt = L.rec_terms(real_rec, y, fake_rec, fake)                       # :1964-1966
+        rr_enc, rr_dec, _ = D(Clip01Fn.apply(real_rec), need_rec=False)     # :1969
+        rf_enc, rf_dec, _ = D(Clip01Fn.apply(fake_rec), need_rec=False)     # :1970
+        ct = L.consist_terms(real_enc, rr_enc, real_dec, rr_dec, fake_enc, rf_enc, fake_dec, rf_dec)   # :1972-1977
+        details = {'D/real_enc': dt[1], 'D/fake_enc': dt[2], 'D/real_dec': dt[3], 'D/fake_dec': dt[4],
+                   'D/rec_loss_real': rt[1], 'D/rec_loss_fake': rt[2],
+                   'D/consist_loss_real_enc': ct[1], 'D/consist_loss_real_dec': ct[2],
+                   'D/consist_loss_fake_enc': ct[3], 'D/consist_loss_fake_dec': ct[4]}
+        return torch.stack([dt[0], rt[0], ct[0]]), details                  # :1992
+
+    def g_loss(self, x, y):
+        x, y = check_input(x, "g_loss"), check_input(y, "g_loss")
+        fake = self.Generator(x)                                            # :1995
+        gen_enc, gen_dec, _ = self.Discriminator(fake, weight_grads=False, need_rec=False)   # :1996
+        gt = L.g_terms(gen_enc, gen_dec, fake, x, y, eps=self.pixel_loss.eps)                # :1998-2002
+        details = {'G/gen_enc': gt[1], 'G/gen_dec': gt[2], 'G/pix_loss': gt[3], 'G/edge_loss': gt[4]}
+        return gt[0], details

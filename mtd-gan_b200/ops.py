@@ -1,0 +1,388 @@
+"""Autograd-connected host wrappers over the C-ABI kernels.  All activations are NHWC fp32 CUDA
+tensors of shape (B, H, W, C); every op is a torch.autograd.Function whose forward AND backward are
+calls into libmtdgan_sm100a.so — PyTorch supplies memory, streams and the autograd tape only.
+"""
+from __future__ import annotations
+
+import os
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+from torch.autograd import Function
+
+from . import _ext
+from ._ext import call, fptr, ptr, stream
+
+ACT_NONE, ACT_RELU, ACT_LEAKY = 0, 1, 2
+LEAK = 0.2
+
+
+def _empty(shape, like):
+    return torch.empty(shape, dtype=torch.float32, device=like.device)
+
+
+# ------------------------------------------------------------------------------------------------
+# packed-weight cache: reference-layout Parameters stay the masters (state_dict / optimizer
+# compatible); K-major packed copies are rebuilt when the parameter's version counter or storage moves.
+# ------------------------------------------------------------------------------------------------
+_pack_cache: dict = {}
+
+
+def _packed(weight: torch.Tensor, kind: str, cfg: "ConvCfg") -> torch.Tensor:
+    """K-major packed copy of a reference-layout weight, cached on (storage pointer, version)."""
+    key = (weight.data_ptr(), weight.numel(), kind, cfg.transposed, cfg.stride)
+    ent = _pack_cache.get(key)
+    if ent is not None and ent[0] == weight._version:
+        return ent[1]
+    w = weight.detach()
+    out = _empty((w.numel(),), w)
+    if kind == "fwd":
+        call("mtd_conv_pack_fwd", fptr(w), cfg.transposed, cfg.cout, cfg.cin, cfg.kh, cfg.kw, fptr(out), stream())
+    else:
+        call("mtd_conv_pack_dgrad", fptr(w), cfg.transposed, cfg.cout, cfg.cin, cfg.kh, cfg.kw, cfg.stride, fptr(out),
+             stream())
+    _pack_cache[key] = (weight._version, out)
+    return out
+
+
+# Weight-gradient request filter.  torch.autograd.grad(l, inputs=...) prunes built-in ops' unused
+# outputs, but a Python Function only sees the static `needs_input_grad`; the PCGrad driver
+# (weight_methods.py) names the parameters it is asking for so the other layers skip their wgrad GEMMs.
+_wgrad_filter = None          # None = compute for every weight that requires grad
+
+
+class wgrad_only_for:
+    def __init__(self, params):
+        self.ptrs = None if params is None else {p.data_ptr() for p in params}
+
+    def __enter__(self):
+        global _wgrad_filter
+        self.prev, _wgrad_filter = _wgrad_filter, self.ptrs
+        return self
+
+    def __exit__(self, *exc):
+        global _wgrad_filter
+        _wgrad_filter = self.prev
+        return False
+
+
+def _wgrad_wanted(weight) -> bool:
+    return _wgrad_filter is None or weight.data_ptr() in _wgrad_filter
+
+
+@dataclass(frozen=True)
+class ConvCfg:
+    cin: int                 # total input channels (C1 + C2)
+    cout: int
+    kh: int = 3
+    kw: int = 3
+    stride: int = 1
+    pad: int = 1
+    transposed: int = 0      # weight stored in ConvTranspose2d layout (Cin, Cout, kh, kw)
+    pre_act: int = ACT_NONE
+    post_act: int = ACT_NONE
+    slope: float = LEAK
+    fuse_add1_is_input: bool = False   # add1 is x1 itself (block residual): its gradient is fused into dgrad
+
+
+_USE_TC = os.environ.get("MTDGAN_CONV", "auto")      # "simt" forces the exact-fp32 kernel everywhere
+
+
+def _conv_forward_launch(x1, x2, wp, bias, scale, y, aux, add1, add2, cfg: ConvCfg):
+    B, H, W, C1 = x1.shape
+    C2 = 0 if x2 is None else x2.shape[3]
+    args = (fptr(x1), fptr(x2), fptr(wp), fptr(bias), fptr(scale), fptr(y), fptr(aux), fptr(add1), fptr(add2), B, H, W, C1,
+            C2, cfg.cout, cfg.kh, cfg.kw, cfg.stride, cfg.pad, cfg.pre_act, cfg.post_act, cfg.slope, stream())
+    if _USE_TC != "simt" and _ext.load().mtd_conv_fwd_tc_supported(B, H, W, C1, C2, cfg.cout, cfg.kh, cfg.kw, cfg.stride,
+                                                                    cfg.pad) == 1:
+        call("mtd_conv_fwd_tc", *args)
+    else:
+        call("mtd_conv_fwd", *args)
+
+
+class ConvFn(Function):
+    """y = post_act( pre_act( scale * conv(cat[x1, x2], W) + b ) + add1 + add2 ).
+
+    `weight` is the reference-layout parameter (Conv2d / ConvTranspose2d / Linear).  For spectrally
+    normalised layers `inv_sigma` (1-element), `u`, `v` are this call's power-iteration results and the
+    backward applies dW_orig = (G - <G,W~> u v^T)/sigma.
+    """
+
+    @staticmethod
+    def forward(ctx, x1, x2, weight, bias, inv_sigma, u, v, add1, add2, cfg: ConvCfg):
+        B, H, W, C1 = x1.shape
+        C2 = 0 if x2 is None else x2.shape[3]
+        assert C1 + C2 == cfg.cin, (C1, C2, cfg)
+        Ho = (H + 2 * cfg.pad - cfg.kh) // cfg.stride + 1
+        Wo = (W + 2 * cfg.pad - cfg.kw) // cfg.stride + 1
+        wp = _packed(weight, "fwd", cfg) if cfg.kh * cfg.kw > 1 or cfg.transposed else weight.detach()
+        y = _empty((B, Ho, Wo, cfg.cout), x1)
+        has_add = add1 is not None or add2 is not None
+        need_graph = any(ctx.needs_input_grad)
+        aux = _empty(y.shape, x1) if (need_graph and cfg.pre_act != ACT_NONE and has_add) else None
+        _conv_forward_launch(x1, x2, wp, bias, inv_sigma, y, aux, add1, add2, cfg)
+        ctx.cfg = cfg
+        ctx.has_add = has_add
+        ctx.shapes = (B, H, W, C1, C2)
+        ctx.save_for_backward(x1, x2, weight, inv_sigma, u, v, y, aux)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        cfg: ConvCfg = ctx.cfg
+        x1, x2, weight, inv_sigma, u, v, y, aux = ctx.saved_tensors
+        B, H, W, C1, C2 = ctx.shapes
+        need = ctx.needs_input_grad
+        dy = dy.contiguous()
+        M = dy.numel() // cfg.cout
+        st = stream()
+        # 1) through post_act, then the adds, then pre_act
+        g1 = dy
+        if cfg.post_act != ACT_NONE:
+            g1 = _empty(dy.shape, dy)
+            call("mtd_act_bwd", fptr(dy), fptr(y), fptr(g1), None, M, cfg.cout, cfg.post_act, cfg.slope, st)
+        d_add = g1 if ctx.has_add else None
+        dbias = _empty((cfg.cout,), dy) if need[3] else None
+        if cfg.pre_act != ACT_NONE:
+            pre_out = aux if aux is not None else y
+            dz = _empty(dy.shape, dy)
+            call("mtd_act_bwd", fptr(g1), fptr(pre_out), fptr(dz), fptr(dbias), M, cfg.cout, cfg.pre_act, cfg.slope, st)
+        else:
+            dz = g1
+            if dbias is not None:
+                call("mtd_act_bwd", fptr(g1), None, None, fptr(dbias), M, cfg.cout, ACT_NONE, cfg.slope, st)
+        # 2) data gradients
+        dx1 = dx2 = None
+        if need[0] or need[1]:
+            wpd = _packed(weight, "dgrad", cfg)
+            T = cfg.kh * cfg.kw
+            fuse = g1 if (cfg.fuse_add1_is_input and need[0]) else None
+            if cfg.stride == 1:
+                if need[0]:
+                    dx1 = _empty((B, H, W, C1), dy)
+                    call("mtd_conv_dgrad", fptr(dz), fptr(wpd), fptr(dx1), fptr(inv_sigma), fptr(fuse), None, None, 0,
+                         cfg.slope, B, H, W, C1, cfg.cout, cfg.kh, cfg.kw, 1, cfg.pad, st)
+                if C2 and need[1]:
+                    dx2 = _empty((B, H, W, C2), dy)
+                    call("mtd_conv_dgrad", fptr(dz), wpd.data_ptr() + 4 * C1 * T * cfg.cout, fptr(dx2), fptr(inv_sigma),
+                         None, None, None, 0, cfg.slope, B, H, W, C2, cfg.cout, cfg.kh, cfg.kw, 1, cfg.pad, st)
+            else:
+                assert C2 == 0
+                dx1 = _empty((B, H, W, C1), dy)
+                call("mtd_conv_dgrad", fptr(dz), fptr(wpd), fptr(dx1), fptr(inv_sigma), None, None, None, 0, cfg.slope, B,
+                     H, W, C1, cfg.cout, cfg.kh, cfg.kw, cfg.stride, cfg.pad, st)
+        # 3) weight gradient (packed), then to reference layout (+ spectral-norm correction)
+        dw = None
+        if need[2] and _wgrad_wanted(weight):
+            gp = _empty((weight.numel(),), dy)
+            call("mtd_conv_wgrad", fptr(x1), fptr(x2), fptr(dz), fptr(gp), B, H, W, C1, C2, cfg.cout, cfg.kh, cfg.kw,
+                 cfg.stride, cfg.pad, st)
+            dw = torch.empty_like(weight)
+            scratch = torch.empty(4, dtype=torch.float32, device=dy.device) if inv_sigma is not None else None
+            call("mtd_conv_wgrad_finish", fptr(gp), fptr(dw), cfg.transposed, cfg.cout, cfg.cin, cfg.kh, cfg.kw,
+                 fptr(weight.detach()) if inv_sigma is not None else None, fptr(u), fptr(v), fptr(inv_sigma), ptr(scratch),
+                 st)
+        d_add1 = d_add if (need[7] and not cfg.fuse_add1_is_input) else None
+        d_add2 = d_add if need[8] else None
+        return dx1, dx2, dw, dbias, None, None, None, d_add1, d_add2, None
+
+
+def conv(x1, weight, bias, cfg: ConvCfg, x2=None, inv_sigma=None, u=None, v=None, add1=None, add2=None):
+    return ConvFn.apply(x1, x2, weight, bias, inv_sigma, u, v, add1, add2, cfg)
+
+
+# ------------------------------------------------------------------------------------------------
+# Res-FFT-Conv block: out = x + relu(img_conv(x)) + irfft2(relu(fft_conv(cat[Re,Im] rfft2(x))))
+# ------------------------------------------------------------------------------------------------
+_IMG_CFG = {}
+
+
+def _img_cfg(c):
+    if c not in _IMG_CFG:
+        _IMG_CFG[c] = ConvCfg(cin=c, cout=c, kh=3, kw=3, stride=1, pad=1, pre_act=ACT_RELU)
+    return _IMG_CFG[c]
+
+
+class FFTConvBlockFn(Function):
+    """One fused FFT_ConvBlock (arch/Ours/networks.py:21-36) on an NHWC tensor."""
+
+    @staticmethod
+    def forward(ctx, x, img_w, img_b, fft_w, fft_b):
+        B, H, W, C = x.shape
+        st = stream()
+        cfg = _img_cfg(C)
+        need_graph = any(ctx.needs_input_grad)
+        spec = _empty((_ext.load().mtd_fft_spec_elems(B, H, W, C),), x)
+        call("mtd_fft_rows_fwd", fptr(x), fptr(spec), B, H, W, C, st)
+        spec2 = _empty(spec.shape, x) if need_graph else spec          # in place when nothing is saved
+        call("mtd_fft_cols_mix", fptr(spec), fptr(spec2), fptr(fft_w.detach()), fptr(fft_b.detach()), B, H, W, C, st)
+        img = _empty(x.shape, x)
+        _conv_forward_launch(x, None, _packed(img_w, "fwd", cfg), img_b.detach(), None, img, None, None, None, cfg)
+        out = _empty(x.shape, x)
+        call("mtd_fft_rows_inv", fptr(spec2), fptr(x), fptr(img), fptr(out), B, H, W, C, st)
+        if need_graph:
+            ctx.save_for_backward(x, img_w, fft_w, fft_b, spec, img)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, img_w, fft_w, fft_b, spec, img = ctx.saved_tensors
+        B, H, W, C = x.shape
+        st = stream()
+        cfg = _img_cfg(C)
+        need = ctx.needs_input_grad
+        dout = dout.contiguous()
+        lib = _ext.load()
+        # frequency branch
+        gspec = _empty(spec.shape, x)
+        call("mtd_fft_rows_fwd", fptr(dout), fptr(gspec), B, H, W, C, st)
+        part = _empty((lib.mtd_fft_bwd_part_elems(B, W),), x)
+        dfw = torch.empty_like(fft_w)
+        dfb = torch.empty_like(fft_b)
+        call("mtd_fft_cols_mix_bwd", fptr(spec), fptr(gspec), fptr(gspec), fptr(fft_w.detach()), fptr(fft_b.detach()),
+             fptr(part), fptr(dfw), fptr(dfb), B, H, W, C, st)
+        # image branch
+        M = B * H * W
+        dz = _empty(x.shape, x)
+        dib = _empty((C,), x)
+        call("mtd_act_bwd", fptr(dout), fptr(img), fptr(dz), fptr(dib), M, C, ACT_RELU, LEAK, st)
+        dx = None
+        if need[0]:
+            dxc = _empty(x.shape, x)      # dgrad(dz) + dout   (residual path fused)
+            call("mtd_conv_dgrad", fptr(dz), fptr(_packed(img_w, "dgrad", cfg)), fptr(dxc), None, fptr(dout), None, None, 0,
+                 LEAK, B, H, W, C, C, 3, 3, 1, 1, st)
+            dx = _empty(x.shape, x)       # + frequency-branch gradient, fused into the inverse row pass
+            call("mtd_fft_rows_inv", fptr(gspec), fptr(dxc), None, fptr(dx), B, H, W, C, st)
+        diw = None
+        if need[1] and _wgrad_wanted(img_w):
+            gp = _empty((img_w.numel(),), x)
+            call("mtd_conv_wgrad", fptr(x), None, fptr(dz), fptr(gp), B, H, W, C, 0, C, 3, 3, 1, 1, st)
+            diw = torch.empty_like(img_w)
+            call("mtd_conv_wgrad_finish", fptr(gp), fptr(diw), 0, C, C, 3, 3, None, None, None, None, None, st)
+        return dx, diw, dib, dfw, dfb
+
+
+def fft_conv_block(x, img_w, img_b, fft_w, fft_b):
+    return FFTConvBlockFn.apply(x, img_w, img_b, fft_w, fft_b)
+
+
+# ------------------------------------------------------------------------------------------------
+# resampling / elementwise
+# ------------------------------------------------------------------------------------------------
+class Upsample2xFn(Function):
+    @staticmethod
+    def forward(ctx, x):
+        B, H, W, C = x.shape
+        out = _empty((B, 2 * H, 2 * W, C), x)
+        call("mtd_upsample2x_fwd", fptr(x), fptr(out), B, H, W, C, stream())
+        ctx.dims = (B, H, W, C)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        B, H, W, C = ctx.dims
+        dout = dout.contiguous()
+        din = _empty((B, H, W, C), dout)
+        call("mtd_upsample2x_bwd", fptr(dout), fptr(din), B, H, W, C, stream())
+        return din
+
+
+class PixelShuffle2Fn(Function):
+    @staticmethod
+    def forward(ctx, x):
+        B, H, W, C4 = x.shape
+        C = C4 // 4
+        out = _empty((B, 2 * H, 2 * W, C), x)
+        call("mtd_pixel_shuffle2", fptr(x), fptr(out), B, H, W, C, 0, stream())
+        ctx.dims = (B, H, W, C)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        B, H, W, C = ctx.dims
+        dout = dout.contiguous()
+        din = _empty((B, H, W, 4 * C), dout)
+        call("mtd_pixel_shuffle2", fptr(dout), fptr(din), B, H, W, C, 1, stream())
+        return din
+
+
+class Clip01Fn(Function):
+    @staticmethod
+    def forward(ctx, x):
+        x = x.contiguous()
+        y = torch.empty_like(x)
+        call("mtd_clip01_fwd", fptr(x), fptr(y), x.numel(), stream())
+        ctx.save_for_backward(x)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        dy = dy.contiguous()
+        dx = torch.empty_like(x)
+        call("mtd_clip01_bwd", fptr(x), fptr(dy), fptr(dx), x.numel(), stream())
+        return dx
+
+
+class MulConstFn(Function):
+    """x * m with m a constant (dropout keep-mask already scaled by 1/(1-p))."""
+
+    @staticmethod
+    def forward(ctx, x, m):
+        x = x.contiguous()
+        out = torch.empty_like(x)
+        call("mtd_mul", fptr(x), fptr(m), fptr(out), x.numel(), stream())
+        ctx.save_for_backward(m)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        (m,) = ctx.saved_tensors
+        dout = dout.contiguous()
+        dx = torch.empty_like(dout)
+        call("mtd_mul", fptr(dout), fptr(m), fptr(dx), dout.numel(), stream())
+        return dx, None
+
+
+class LayoutFn(Function):
+    """NCHW <-> NHWC (only where a multi-channel drop-in module is called stand-alone)."""
+
+    @staticmethod
+    def forward(ctx, x, to_nhwc: bool):
+        x = x.contiguous()
+        if to_nhwc:
+            B, C, H, W = x.shape
+            out = _empty((B, H, W, C), x)
+        else:
+            B, H, W, C = x.shape
+            out = _empty((B, C, H, W), x)
+        call("mtd_layout_transpose", fptr(x), fptr(out), B, C, H * W, 1 if to_nhwc else 0, stream())
+        ctx.to_nhwc = to_nhwc
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        return LayoutFn.apply(dout, not ctx.to_nhwc), None
+
+
+def to_nhwc(x):
+    """(B,C,H,W) -> (B,H,W,C); free (a view) when C == 1."""
+    if x.shape[1] == 1:
+        return x.reshape(x.shape[0], x.shape[2], x.shape[3], 1)
+    return LayoutFn.apply(x, True)
+
+
+def to_nchw(x):
+    if x.shape[3] == 1:
+        return x.reshape(x.shape[0], 1, x.shape[1], x.shape[2])
+    return LayoutFn.apply(x, False)
+
+
+def check_input(x: torch.Tensor, what: str):
+    if not isinstance(x, torch.Tensor) or not x.is_cuda:
+        raise _ext.MtdError(f"{what}: expected a CUDA tensor — the B200 hot path has no CPU fallback")
+    if x.dtype != torch.float32:
+        raise _ext.MtdError(f"{what}: expected float32, got {x.dtype}")
+    _ext.load()
+    return x.contiguous()
