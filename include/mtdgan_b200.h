@@ -132,9 +132,10 @@ int mtd_pcgrad_project(const void* seg_tab, const void* chunk_tab, int n_chunks,
                        double* gram_ws, float* coef_out, float* cmat_out, double* gram_out, void* stream);
 
 /* ---- AdamW (adamw.cu) — "next" row: torch.optim.AdamW step of optimizers.py:9 / engine.py:44,52 ------
- * seg table int64[nseg][8]: { param, grad, exp_avg, exp_avg_sq, numel, 0, 0, 0 }; chunk table as PCGrad. */
+ * seg table int64[nseg][8]: { param, grad, exp_avg, exp_avg_sq, numel, bits(1-b1^t), bits(1-b2^t), 0 };
+ * chunk table as PCGrad.                                                                             */
 int mtd_adamw_step(const void* seg_tab, const void* chunk_tab, int n_chunks, float lr, float beta1, float beta2,
-                   float eps, float weight_decay, float bias_corr1, float bias_corr2, void* stream);
+                   float eps, float weight_decay, void* stream);
 
 #ifdef __cplusplus
 }

@@ -51,7 +51,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         list(ex.map(compile_one, jobs))
     objs = [os.path.join(OBJ, src[:-3] + ".o") for src in _sources()]
     if force or jobs or _stale(LIB, objs):
-        cmd = [NVCC, "-shared", "-o", LIB] + objs
+        cmd = [NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")

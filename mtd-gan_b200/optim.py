@@ -1,0 +1,57 @@
+"""Fused multi-tensor AdamW: drop-in for the torch.optim.AdamW the reference builds in
+optimizers.py:9 / train.py:122-124 and steps at engine.py:44,52.  Same hyper-parameters, same per-parameter
+state keys ('step', 'exp_avg', 'exp_avg_sq') so optimizer state_dicts interchange with torch's; parameters
+whose .grad is None are skipped; empty parameter groups are accepted (A12).
+One kernel launch per parameter group instead of torch's foreach chain."""
+from __future__ import annotations
+
+import torch
+
+from ._ext import call, ptr, stream
+from .weight_methods import _chunk_table, _float_bits
+
+
+class FusedAdamW(torch.optim.Optimizer):
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2):
+        defaults = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay)
+        super().__init__(params, defaults)
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        for group in self.param_groups:
+            b1, b2 = group["betas"]
+            rows, numels, keep = [], [], []
+            device = None
+            for p in group["params"]:
+                if p.grad is None:
+                    continue
+                if not p.is_cuda or p.dtype != torch.float32:
+                    raise RuntimeError("FusedAdamW handles fp32 CUDA parameters only (no CPU fallback)")
+                st = self.state[p]
+                if len(st) == 0:
+                    st["step"] = torch.tensor(0.0, dtype=torch.float32)
+                    st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                    st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                st["step"] += 1
+                t = float(st["step"])
+                g = p.grad.contiguous()
+                keep.append(g)
+                rows.append([p.data_ptr(), g.data_ptr(), st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr(), p.numel(),
+                             _float_bits(1.0 - b1 ** t), _float_bits(1.0 - b2 ** t), 0])
+                numels.append(p.numel())
+                device = p.device
+            if not rows:
+                continue
+            seg = torch.tensor(rows, dtype=torch.int64).to(device, non_blocking=True)
+            chunks, n_chunks = _chunk_table(numels, device)
+            lr = group["lr"]
+            call("mtd_adamw_step", ptr(seg), ptr(chunks), n_chunks, float(lr), float(b1), float(b2), float(group["eps"]),
+                 float(group["weight_decay"]), stream())
+            for p in group["params"]:
+                if p.grad is not None:
+                    torch.autograd.graph.increment_version(p)      # the kernel wrote p in place (pack caches key on it)
+        return loss

@@ -1,0 +1,168 @@
+"""GPU parity tests of the drop-in modules (generator, discriminator, method wrapper, PCGrad, one full
+training step) against the golden vectors generated from the live reference and against the CPU oracle on
+the same seeded inputs.  Tolerances are the north_star's: fp32 path <= 1e-4 (norm-wise relative error),
+stated per check; bit-exact for the NDS mask (test_gpu_kernels.py)."""
+import random
+
+import pytest
+import torch
+
+from _golden_util import check_summary, load, rel_err
+from oracle import mtdgan_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def drop_mask(b, seed):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.rand(b, 512, generator=g) >= 0.3).float() / 0.7
+
+
+def seeded_model():
+    from arch.Ours.networks import MTD_GAN_Method
+    torch.manual_seed(2024)
+    random.seed(2024)
+    return MTD_GAN_Method().to(DEV)
+
+
+@pytest.fixture()
+def masks():
+    from mtdgan_b200 import networks as NW
+    queue = []
+    NW.set_dropout_mask_provider(lambda b, n, dev: queue.pop(0).to(dev) if queue else None)
+    yield queue
+    NW.set_dropout_mask_provider(None)
+
+
+def test_generator_forward_64():
+    m = seeded_model().eval()
+    x = O.synthetic_pair(2, 64, seed=11)[0].to(DEV)
+    with torch.no_grad():
+        out = m.Generator(x)
+    assert out.shape == (2, 1, 64, 64) and float(out.min()) >= 0.0
+    assert rel_err(out, load("gen_fwd_64.pt")["out"]) <= 1e-4
+
+
+def test_generator_forward_512():
+    m = seeded_model().eval()
+    x = O.synthetic_pair(1, 512, seed=12)[0].to(DEV)
+    with torch.no_grad():
+        out = m.Generator(x)
+    assert rel_err(out, load("gen_fwd_512.pt")["out"].float()) <= 1e-3      # fixture stored in fp16
+    # batch independence: slices of a batch equal single-slice calls (inference shards by slice)
+    with torch.no_grad():
+        xb = torch.cat([x, x.flip(-1)], 0)
+        ob = m.Generator(xb)
+    assert rel_err(ob[:1], out) <= 1e-5
+
+
+def test_generator_backward_vs_oracle():
+    m = seeded_model()
+    x = O.synthetic_pair(2, 64, seed=41)[0]
+    sd = {k: v.detach().cpu().clone().requires_grad_(True) for k, v in m.Generator.state_dict().items()}
+    g = torch.Generator().manual_seed(42)
+    w = torch.randn(2, 1, 64, 64, generator=g)
+    (O.generator_forward(sd, x) * w).sum().backward()
+    out = m.Generator(x.to(DEV))
+    (out * w.to(DEV)).sum().backward()
+    for k, p in m.Generator.named_parameters():
+        assert rel_err(p.grad, sd[k].grad) <= 1e-4, k
+
+
+def test_discriminator_vs_golden(masks):
+    fix = load("disc_64.pt")
+    m = seeded_model()
+    D = m.Discriminator.train()
+    y = O.synthetic_pair(2, 64, seed=13)[1].to(DEV)
+    masks.append(drop_mask(2, 14))
+    enc, dec, rec = D(y)
+    assert enc.shape == (2, 1) and dec.shape == (2, 1, 64, 64) and rec.shape == (2, 1, 64, 64)
+    for got, key in ((enc, "enc"), (dec, "dec"), (rec, "rec")):
+        assert rel_err(got, fix[key]) <= 1e-4, key
+    g = torch.Generator().manual_seed(15)
+    a, b, c = (torch.randn(s, generator=g).to(DEV) for s in (enc.shape, dec.shape, rec.shape))
+    ((enc * a).sum() + (dec * b).sum() / 64 + (rec * c).sum() / 64).backward()
+    for k, p in D.named_parameters():
+        if k in fix["grads"]:
+            check_summary(p.grad, fix["grads"][k], 1e-4, k)
+        else:
+            assert p.grad is None, k
+    for k, v in D.named_buffers():
+        check_summary(v, fix["buffers"][k], 1e-5, k)
+    D.eval()
+    with torch.no_grad():
+        e2, d2, r2 = D(y)
+    assert rel_err(e2, fix["eval_enc"]) <= 1e-4 and rel_err(d2, fix["eval_dec"]) <= 1e-4 and rel_err(r2, fix["eval_rec"]) <= 1e-4
+    with pytest.raises(RuntimeError):
+        D(torch.zeros(1, 1, 512, 512, device=DEV))            # D only accepts 64 x 64
+
+
+def test_full_train_step_b4_vs_golden(masks):
+    """BASELINE configs[0]: one MTD_GAN_Method train step (engine.py:40-55) on 4 synthetic 64^2 patches."""
+    from module.weight_methods import WeightMethods
+    fix = load("train_step_b4.pt")
+    m = seeded_model().train()
+    D, G = m.Discriminator, m.Generator
+    x, y = (t.to(DEV) for t in O.synthetic_pair(4, 64, seed=1234))
+    masks.extend(drop_mask(4, 21 + i) for i in range(5))
+    opt_D = torch.optim.AdamW(D.parameters(), lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=5e-4)
+    opt_G = torch.optim.AdamW(G.parameters(), lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=5e-4)
+    wm = WeightMethods('pcgrad', n_tasks=3, device=torch.device(DEV))
+    random.seed(99)
+    opt_D.zero_grad(); D.zero_grad()
+    d_losses, det = m.d_loss(x, y)
+    assert d_losses.shape == (3,)
+    assert torch.allclose(d_losses.cpu(), fix["d_losses"], rtol=1e-4, atol=1e-10)
+    for k, v in fix["d_details"].items():
+        assert torch.allclose(det[k].cpu(), v, rtol=1e-3, atol=1e-10), k
+    loss_D, extra = wm.backward(losses=d_losses, shared_parameters=list(D.shared_parameters()),
+                                task_specific_parameters=list(D.task_specific_parameters()),
+                                last_shared_parameters=list(D.last_shared_parameters()))
+    assert loss_D is None and extra == {}
+    for k, p in D.named_parameters():
+        if fix["d_grads"][k] is None:
+            assert p.grad is None, k                               # c_fc.* 
+        else:
+            check_summary(p.grad, fix["d_grads"][k], 2e-4, k)
+    opt_D.step()
+    opt_G.zero_grad(); G.zero_grad()
+    g_loss, gdet = m.g_loss(x, y)
+    assert abs(float(g_loss) - float(fix["g_loss"])) <= 1e-4 * abs(float(fix["g_loss"]))
+    for k, v in fix["g_details"].items():
+        assert torch.allclose(gdet[k].cpu(), v, rtol=1e-4, atol=1e-8), k
+    g_loss.backward()
+    for k, p in G.named_parameters():
+        check_summary(p.grad, fix["g_grads"][k], 2e-4, k)
+    opt_G.step()
+    sd = m.state_dict()
+    for k, s in fix["state_after"].items():
+        check_summary(sd[k], s, 1e-4, k)
+
+
+def test_two_steps_fused_adamw_runs_and_decreases_nothing_nan():
+    """Two steps with the fused optimizer: finite losses, weights move, u/v buffers stay unit-norm."""
+    from module.weight_methods import WeightMethods
+    from mtdgan_b200.optim import FusedAdamW
+    m = seeded_model().train()
+    D, G = m.Discriminator, m.Generator
+    x, y = (t.to(DEV) for t in O.synthetic_pair(4, 64, seed=5))
+    opt_D = FusedAdamW([{"params": D.parameters()}, {"params": [], "lr": 0.025}], lr=1e-4, weight_decay=5e-4)
+    opt_G = FusedAdamW(G.parameters(), lr=1e-4, weight_decay=5e-4)
+    wm = WeightMethods('pcgrad', n_tasks=3, device=torch.device(DEV))
+    w0 = D.conv12.weight_orig.detach().clone()
+    for _ in range(2):
+        opt_D.zero_grad(); D.zero_grad()
+        d_losses, _ = m.d_loss(x, y)
+        wm.backward(losses=d_losses, shared_parameters=list(D.shared_parameters()),
+                    task_specific_parameters=list(D.task_specific_parameters()),
+                    last_shared_parameters=list(D.last_shared_parameters()))
+        opt_D.step()
+        opt_G.zero_grad(); G.zero_grad()
+        g_loss, _ = m.g_loss(x, y)
+        g_loss.backward()
+        opt_G.step()
+        assert torch.isfinite(d_losses).all() and torch.isfinite(g_loss)
+    assert not torch.equal(w0, D.conv12.weight_orig)
+    assert abs(float(D.conv12.weight_u.norm()) - 1.0) < 1e-4
+    assert D.c_fc.weight_orig.grad is None
