@@ -1,0 +1,394 @@
+#!/usr/bin/env python
+"""MTD-GAN hot-path benchmark (contract: `python bench.py --gpus N --steps K --warmup W [--impl reference]`).
+
+Own arm (default): the full MTD-GAN train step — G forward, 4 D forwards, RC/NDS losses, PCGrad (3+1 backward
+passes), AdamW on D, G forward + D forward, backward, AdamW on G (the reference's engine.py:40-55) — on
+20 synthetic 64x64 patches per GPU (BASELINE.json configs[2]; configs[3] at N > 1), every kernel of which is
+launched from libmtdgan_sm100a.so.  Also reports generator inference on 1x512x512 slices (configs[1]).
+Reference arm (`--impl reference`): the CPU oracle port of the same step on the box's host cores (the Python
+reference cannot travel to the GPU box).
+
+One JSON line on stdout (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import random
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+PATCH, BATCH = 64, 20
+F_ALG_TRAIN = 99.3e9          # useful conv+linear FLOP per patch per train step
+B_ALG_INFER = 3.22e9          # algorithmic HBM bytes per 512^2 slice
+N_SHARED = 28_609_920
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "tflops_burst": d["bf16_tflops"], "tflops_sustained": d["bf16_tflops_sustained"],
+                "source": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "tflops_burst": 1590.0, "tflops_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx = float(f[2])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+# ----------------------------------------------------------------------------------------------------
+# own arm
+# ----------------------------------------------------------------------------------------------------
+def flops_of(name, a):
+    """Algorithmic FLOPs (2*MAC) of one conv entry-point call from its argument list."""
+    if name in ("mtd_conv_fwd", "mtd_conv_fwd_tc"):
+        B, H, W, C1, C2, N, kh, kw, s, p = a[9:19]
+        Ho, Wo = (H + 2 * p - kh) // s + 1, (W + 2 * p - kw) // s + 1
+        return 2.0 * B * Ho * Wo * N * (C1 + C2) * kh * kw
+    if name == "mtd_conv_dgrad":
+        B, H, W, Cin, Cout, kh, kw, s, p = a[9:18]
+        Ho, Wo = (H + 2 * p - kh) // s + 1, (W + 2 * p - kw) // s + 1
+        return 2.0 * B * Ho * Wo * Cout * Cin * kh * kw
+    if name == "mtd_conv_wgrad":
+        B, H, W, C1, C2, N, kh, kw, s, p = a[4:14]
+        Ho, Wo = (H + 2 * p - kh) // s + 1, (W + 2 * p - kw) // s + 1
+        return 2.0 * B * Ho * Wo * N * (C1 + C2) * kh * kw
+    return 0.0
+
+
+GROUPS = {"conv": ("mtd_conv_fwd", "mtd_conv_fwd_tc", "mtd_conv_dgrad", "mtd_conv_wgrad"),
+          "conv_aux": ("mtd_conv_pack_fwd", "mtd_conv_pack_dgrad", "mtd_conv_wgrad_finish", "mtd_act_bwd"),
+          "fft": ("mtd_fft_rows_fwd", "mtd_fft_cols_mix", "mtd_fft_rows_inv", "mtd_fft_cols_mix_bwd"),
+          "spectral_norm": ("mtd_sn_power_iter",), "pcgrad": ("mtd_pcgrad_project",), "adamw": ("mtd_adamw_step",)}
+
+
+def run_own(args):
+    import mtdgan_b200
+    from mtdgan_b200 import _ext
+    from mtdgan_b200.data import synthetic_pair
+    from mtdgan_b200.optim import FusedAdamW
+    from mtdgan_b200 import distributed as mdist
+    from arch.Ours.networks import MTD_GAN_Method
+    from module.weight_methods import WeightMethods
+
+    rank, world, local = dist_env()
+    if args.gpus != world and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    mtdgan_b200.require_cuda_extension()
+    if world > 1:
+        mdist.init()
+    torch.manual_seed(2024)
+    random.seed(2024)
+    model = MTD_GAN_Method().to(dev).train()
+    D, G = model.Discriminator, model.Generator
+    opt_D = FusedAdamW([{"params": list(D.parameters())}, {"params": [], "lr": 0.025}], lr=1e-4, weight_decay=5e-4)
+    opt_G = FusedAdamW(G.parameters(), lr=1e-4, weight_decay=5e-4)
+    wm = WeightMethods("pcgrad", n_tasks=3, device=dev)
+    shared, ts, last = list(D.shared_parameters()), list(D.task_specific_parameters()), list(D.last_shared_parameters())
+    xh, yh = synthetic_pair(BATCH, PATCH, seed=1234, rank=rank, pin=True)
+    xd, yd = xh.to(dev), yh.to(dev)
+
+    def step(x, y):
+        opt_D.zero_grad(); D.zero_grad()
+        d_losses, d_det = model.d_loss(x, y)
+        wm.backward(losses=d_losses, shared_parameters=shared, task_specific_parameters=ts, last_shared_parameters=last)
+        opt_D.step()
+        opt_G.zero_grad(); G.zero_grad()
+        g_loss, g_det = model.g_loss(x, y)
+        g_loss.backward()
+        if world > 1:
+            mdist.allreduce_mean_grads(list(G.parameters()))
+        opt_G.step()
+        return d_losses, g_loss
+
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)      # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    def timed(n, e2e):
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n)]
+        sink = torch.empty(4, dtype=torch.float32).pin_memory()
+        for s, e in ev:
+            flush.zero_()
+            s.record()
+            if e2e:
+                x, y = xh.to(dev, non_blocking=True), yh.to(dev, non_blocking=True)
+                dl, gl = step(x, y)
+                sink[:3].copy_(dl.detach(), non_blocking=True)
+                sink[3:].copy_(gl.detach().reshape(1), non_blocking=True)
+            else:
+                step(xd, yd)
+            e.record()
+        torch.cuda.synchronize()
+        return [s.elapsed_time(e) for s, e in ev]
+
+    for _ in range(max(args.warmup, 3)):
+        step(xd, yd)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = _ext.kernel_launch_count()
+    ms = timed(args.steps, e2e=False)
+    launches = (_ext.kernel_launch_count() - l0) // args.steps
+    barrier()
+    ms_e2e = timed(args.steps, e2e=True)
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    t_dev, t_e2e = sum(ms), sum(ms_e2e)
+    if world > 1:
+        t = torch.tensor([t_dev, t_e2e], device=dev, dtype=torch.float64)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        t_dev, t_e2e = float(t[0]), float(t[1])
+
+    # ---- per-kernel-class times: one extra (untimed) step with CUDA events around every C-ABI call
+    breakdown, roof = None, None
+    if rank == 0:
+        torch.cuda.synchronize()
+        _ext.start_profile()
+        step(xd, yd)
+        rec = _ext.stop_profile()
+        total_ms = sum(r[2] for r in rec)
+        by = {}
+        for name, a, t in rec:
+            d = by.setdefault(name, {"ms": 0.0, "calls": 0, "flop": 0.0})
+            d["ms"] += t; d["calls"] += 1; d["flop"] += flops_of(name, a)
+        breakdown = {g: {"ms": round(sum(by[n]["ms"] for n in names if n in by), 3),
+                         "calls": sum(by[n]["calls"] for n in names if n in by)} for g, names in GROUPS.items()}
+        known = {n for names in GROUPS.values() for n in names}
+        breakdown["other"] = {"ms": round(sum(v["ms"] for k, v in by.items() if k not in known), 3),
+                              "calls": sum(v["calls"] for k, v in by.items() if k not in known)}
+        breakdown["sum_ms"] = round(total_ms, 3)
+        pk = peaks()
+        conv_ms = sum(by[n]["ms"] for n in GROUPS["conv"] if n in by)
+        conv_flop = sum(by[n]["flop"] for n in GROUPS["conv"] if n in by)
+        conv_calls = sum(by[n]["calls"] for n in GROUPS["conv"] if n in by)
+        ach = conv_flop / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
+        roof = {"kernel": "implicit-GEMM conv family (fwd + dgrad + wgrad)", "bound": "tensor", "achieved": round(ach, 3),
+                "peak": pk["tflops_sustained"], "unit": "TFLOP/s", "frac": round(ach / pk["tflops_sustained"], 5),
+                "traffic": None, "peak_source": pk["source"] + ", sustained bf16 dense (kernel timed inside a long step)",
+                "algorithmic_flop_per_launch": round(conv_flop / max(conv_calls, 1)), "launches_per_step": conv_calls,
+                "avg_launch_ms": round(conv_ms / max(conv_calls, 1), 5), "share_of_step": round(conv_ms / total_ms, 4),
+                "pcgrad": {"bound": "hbm", "achieved": round(7 * N_SHARED * 4 / (by["mtd_pcgrad_project"]["ms"] * 1e-3) / 1e9, 1),
+                           "peak": pk["hbm_gbs"], "unit": "GB/s",
+                           "frac": round(7 * N_SHARED * 4 / (by["mtd_pcgrad_project"]["ms"] * 1e-3) / 1e9 / pk["hbm_gbs"], 4)}
+                if "mtd_pcgrad_project" in by else None}
+
+    # ---- generator inference, 1 x 512 x 512 (configs[1]); slices are independent => ranks run replicas
+    infer = None
+    model.eval()
+    xs_h = synthetic_pair(1, 512, seed=4321, rank=rank, pin=True)[0]
+    xs = xs_h.to(dev)
+    with torch.no_grad():
+        for _ in range(3):
+            G(xs)
+        torch.cuda.synchronize()
+        n_inf = max(10, min(50, args.steps))
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_inf)]
+        for s, e in ev:
+            flush.zero_()
+            s.record(); G(xs); e.record()
+        torch.cuda.synchronize()
+        inf_ms = [s.elapsed_time(e) for s, e in ev]
+        out_h = torch.empty(1, 1, 512, 512).pin_memory()
+        ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_inf)]
+        for s, e in ev2:
+            flush.zero_()
+            s.record(); out_h.copy_(G(xs_h.to(dev, non_blocking=True)), non_blocking=True); e.record()
+        torch.cuda.synchronize()
+        inf_e2e = [s.elapsed_time(e) for s, e in ev2]
+    if rank == 0:
+        pk = peaks()
+        sl = 1e3 / statistics.mean(inf_ms)
+        infer = {"metric": "512x512 denoised slices/s (generator inference, batch 1)", "value": round(sl * world, 3),
+                 "ms_per_slice": round(statistics.mean(inf_ms), 4), "e2e_value": round(1e3 / statistics.mean(inf_e2e) * world, 3),
+                 "roofline": {"bound": "hbm", "achieved": round(B_ALG_INFER * sl / 1e9, 1), "peak": pk["hbm_gbs"], "unit": "GB/s",
+                              "frac": round(B_ALG_INFER * sl / 1e9 / pk["hbm_gbs"], 4), "traffic": None},
+                 "scaling": "replicas (slices are independent; no collective)"}
+
+    if rank != 0:
+        return None
+    patches = BATCH * world
+    line = {
+        "metric": "train patches/s (64x64, bs20/GPU)", "value": round(patches * args.steps / (t_dev * 1e-3), 3), "unit": "patches/s",
+        "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(t_dev / args.steps, 4),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "MTD_GAN_Method full train step (G + MTL-D + RC/NDS + PCGrad + AdamW), 20 synthetic 1x64x64 patches/GPU "
+                               "(BASELINE configs[2]/[3])", "global_batch": patches, "patch": PATCH,
+                   "parallelism": f"dp{world}", "l2": "256 MiB buffer written between timed steps (L2 flush)",
+                   "weights": "random init, seed 2024", "optimizer": "fused AdamW lr 1e-4 wd 5e-4"},
+        "e2e": {"value": round(patches * args.steps / (t_e2e * 1e-3), 3), "unit": "patches/s",
+                "h2d_bytes_per_step": 2 * BATCH * PATCH * PATCH * 4, "d2h_bytes_per_step": 16},
+        "gpu_launches": int(launches) * args.steps, "gpu_launches_per_step": int(launches),
+        "useful_tflops": round(F_ALG_TRAIN * patches * args.steps / (t_dev * 1e-3) / 1e12, 3),
+        "roofline": roof, "kernel_breakdown_ms": breakdown, "inference": infer, "clocks": clocks,
+    }
+    return line
+
+
+# ----------------------------------------------------------------------------------------------------
+# CPU legs (oracle port)
+# ----------------------------------------------------------------------------------------------------
+def oracle_state():
+    """Reference-identical initial weights (the drop-in modules reproduce the reference's init RNG order)."""
+    from arch.Ours.networks import MTD_GAN_Method
+    torch.manual_seed(2024)
+    random.seed(2024)
+    m = MTD_GAN_Method()
+    return {k: v.detach().clone() for k, v in m.state_dict().items()}
+
+
+def cpu_train_steps(batch, steps, warmup):
+    from oracle.train_step import OracleTrainer
+    from oracle.mtdgan_oracle import synthetic_pair
+    torch.set_num_threads(os.cpu_count())
+    tr = OracleTrainer(oracle_state())
+    x, y = synthetic_pair(batch, PATCH, seed=1234)
+    for _ in range(warmup):
+        tr.step(x, y)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        tr.step(x, y)
+    return (time.perf_counter() - t0) / max(steps, 1)
+
+
+def run_cpu_baseline():
+    """Bounded sample (~10-30 s of CPU work): 1 warm-up + 2 timed train steps of BASELINE configs[0] (B = 4)."""
+    code = ("import bench, json; t = bench.cpu_train_steps(4, 2, 1); "
+            "print(json.dumps({'s_per_step': t}))")
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+    r = subprocess.run([sys.executable, "-c", code], cwd=ROOT, env=env, capture_output=True, text=True, timeout=900)
+    t = json.loads(r.stdout.strip().splitlines()[-1])["s_per_step"]
+    return {"value": round(4 / t, 4), "unit": "patches/s", "cores": os.cpu_count(), "kind": "port",
+            "sample": "oracle port (torch-CPU, all host threads) of the full train step on 4 synthetic 64x64 patches "
+                      "(BASELINE configs[0]): 1 warm-up + 2 timed steps", "s_per_step": round(t, 3)}
+
+
+def run_reference(args):
+    rank, world, local = dist_env()
+    if rank != 0:
+        return None
+    os.environ["CUDA_VISIBLE_DEVICES"] = ""
+    from oracle.train_step import OracleTrainer
+    from oracle.mtdgan_oracle import synthetic_pair
+    torch.set_num_threads(os.cpu_count())
+    tr = OracleTrainer(oracle_state())
+    # size the per-step sample so that (steps + warmup) steps stay within ~4 minutes
+    x2, y2 = synthetic_pair(2, PATCH, seed=1234)
+    t0 = time.perf_counter(); tr.step(x2, y2); t_cal = time.perf_counter() - t0
+    budget = 240.0 / (args.steps + args.warmup)
+    batch = BATCH
+    for b in (20, 8, 4, 2, 1):
+        batch = b
+        if t_cal * (0.55 + 0.45 * b / 2) <= budget:       # ~55 % of the CPU step is batch-independent (spectral norm, PCGrad)
+            break
+    x, y = synthetic_pair(batch, PATCH, seed=1234)
+    for _ in range(args.warmup):
+        tr.step(x, y)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        tr.step(x, y)
+    dt = time.perf_counter() - t0
+    v = round(batch * args.steps / dt, 4)
+    return {"impl": "reference", "metric": "train patches/s (64x64, bs20/GPU)", "value": v, "unit": "patches/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt / args.steps * 1e3, 2), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "MTD_GAN_Method full train step, CPU oracle port of the reference (torch-CPU, all host threads)",
+                       "sample_batch": batch, "patch": PATCH},
+            "cpu_baseline": {"value": v, "unit": "patches/s", "cores": os.cpu_count(), "kind": "port",
+                             "sample": f"{args.steps} timed steps of {batch} synthetic 64x64 patches each"},
+            "e2e": {"value": v, "unit": "patches/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        line = run_reference(args)
+        if line is not None:
+            print(json.dumps(line), flush=True)
+        return
+    line = run_own(args)
+    rank, world, _ = dist_env()
+    if rank == 0:
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                line["cpu_baseline"] = run_cpu_baseline()
+            except Exception as ex:      # the baseline leg must never take the measurement down with it
+                line["cpu_baseline"] = {"value": None, "unit": "patches/s", "cores": os.cpu_count(), "kind": "port",
+                                        "sample": f"failed: {type(ex).__name__}: {ex}"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -31,6 +31,8 @@ extern "C" {
 int mtd_abi_version(void);
 /* 1 if the running device is compute capability 10.x (B200), else 0; <0 on CUDA error */
 int mtd_device_ok(void);
+/* number of CUDA kernels this library has launched in this process (host-side counter) */
+long long mtd_kernel_launch_count(void);
 
 /* ---- convolution (conv_simt.cu, conv_tc.cu) ----------------------------------------------------
  * Replaces nn.Conv2d / nn.ConvTranspose2d / nn.Linear forward and ATen convolution_backward:
@@ -128,6 +130,9 @@ int mtd_loss_finalize(const double* acc, int k, float s0, float s1, float s2, fl
 /* ---- PCGrad (pcgrad.cu) -----------------------------------------------------------------------------
  * Replaces PCGrad._project_conflicting of module/weight_methods.py:449-464 and module/pcgrad.py:50-70. */
 int mtd_pcgrad_chunk_elems(void);
+int mtd_pcgrad_gram(const void* seg_tab, const void* chunk_tab, int n_chunks, int T, double* gram_ws, void* stream);
+int mtd_pcgrad_solve_combine(const void* seg_tab, const void* chunk_tab, int n_chunks, int T, const int* orders, int mean,
+                             double* gram_ws, float* coef_out, float* cmat_out, double* gram_out, void* stream);
 int mtd_pcgrad_project(const void* seg_tab, const void* chunk_tab, int n_chunks, int T, const int* orders, int mean,
                        double* gram_ws, float* coef_out, float* cmat_out, double* gram_out, void* stream);
 

@@ -86,15 +86,39 @@ class MtdError(RuntimeError):
     pass
 
 
-launch_count = 0          # number of C-ABI compute calls made (bench.py's `gpu_launches` evidence)
+_profile = None           # when a list: (entry point, args, start event, end event) per call (bench.py)
+
+
+def kernel_launch_count() -> int:
+    """CUDA kernels launched by the library so far in this process."""
+    return int((_lib if _lib is not None else load()).mtd_kernel_launch_count())
+
+
+def start_profile():
+    """Bracket every C-ABI call with CUDA events on the launching stream (for bench.py's per-kernel times;
+    adds two event records per call, so never enabled inside a timed region)."""
+    global _profile
+    _profile = []
+
+
+def stop_profile():
+    global _profile
+    rec, _profile = _profile, None
+    torch.cuda.synchronize()
+    return [(n, a, s.elapsed_time(e)) for n, a, s, e in rec]
 
 
 def call(name: str, *args):
     """Invoke an int-returning entry point; raise on a non-zero status."""
-    global launch_count
     lib = _lib if _lib is not None else load()
-    rc = getattr(lib, name)(*args)
-    launch_count += 1
+    if _profile is not None:
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        rc = getattr(lib, name)(*args)
+        e.record()
+        _profile.append((name, args, s, e))
+    else:
+        rc = getattr(lib, name)(*args)
     if rc != 0:
         if rc < 0:
             raise MtdError(f"{name}: invalid argument / unsupported shape (status {rc})")

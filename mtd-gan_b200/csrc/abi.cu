@@ -2,7 +2,11 @@
 #include "common.cuh"
 #include "mtdgan_b200.h"
 
+long long g_mtd_kernel_launches = 0;
+
 extern "C" {
+
+long long mtd_kernel_launch_count(void) { return g_mtd_kernel_launches; }
 
 int mtd_abi_version(void) { return 1; }
 

@@ -10,8 +10,12 @@
 
 // Return convention of every extern "C" entry point: 0 ok, <0 argument error,
 // >0 a cudaError_t.  Nothing throws across the ABI.
+// every kernel launch in the library is followed by MTD_CHECK_LAUNCH(): it also counts launches
+// (mtd_kernel_launch_count) — bench.py reports that number as `gpu_launches`.
+extern long long g_mtd_kernel_launches;
 #define MTD_CHECK_LAUNCH()                               \
   do {                                                   \
+    ++g_mtd_kernel_launches;                             \
     cudaError_t e__ = cudaGetLastError();                \
     if (e__ != cudaSuccess) return (int)e__;             \
   } while (0)

@@ -123,22 +123,36 @@ extern "C" {
 
 int mtd_pcgrad_chunk_elems(void) { return kChunk; }
 
-// gram_ws: 16 doubles (zeroed here).  coef_out: T floats.  cmat_out (T*T floats) / gram_out (T*T
-// doubles) may be null.
-int mtd_pcgrad_project(const void* seg_tab, const void* chunk_tab, int n_chunks, int T, const int* orders, int mean,
-                       double* gram_ws, float* coef_out, float* cmat_out, double* gram_out, void* stream) {
-  MTD_REQUIRE(seg_tab && chunk_tab && orders && gram_ws && coef_out && n_chunks > 0 && T >= 1 && T <= kMaxTasks);
+// gram_ws: 16 doubles (zeroed here); entry [a*4+b], a <= b.  Split form for multi-GPU use: the caller
+// all-reduces gram_ws between the two calls (each rank holds a shard of the gradients).
+int mtd_pcgrad_gram(const void* seg_tab, const void* chunk_tab, int n_chunks, int T, double* gram_ws, void* stream) {
+  MTD_REQUIRE(seg_tab && chunk_tab && gram_ws && n_chunks > 0 && T >= 1 && T <= kMaxTasks);
   cudaStream_t st = (cudaStream_t)stream;
   MTD_CUDA(cudaMemsetAsync(gram_ws, 0, 16 * sizeof(double), st));
   pcgrad_gram_kernel<<<n_chunks, 256, 0, st>>>(reinterpret_cast<const Seg*>(seg_tab),
                                                reinterpret_cast<const int2*>(chunk_tab), T, gram_ws);
   MTD_CHECK_LAUNCH();
+  return MTD_OK;
+}
+
+// coef_out: T floats.  cmat_out (T*T floats) / gram_out (T*T doubles) may be null.
+int mtd_pcgrad_solve_combine(const void* seg_tab, const void* chunk_tab, int n_chunks, int T, const int* orders, int mean,
+                             double* gram_ws, float* coef_out, float* cmat_out, double* gram_out, void* stream) {
+  MTD_REQUIRE(seg_tab && chunk_tab && orders && gram_ws && coef_out && n_chunks > 0 && T >= 1 && T <= kMaxTasks);
+  cudaStream_t st = (cudaStream_t)stream;
   pcgrad_solve_kernel<<<1, 32, 0, st>>>(gram_ws, orders, T, mean, coef_out, cmat_out, gram_out);
   MTD_CHECK_LAUNCH();
   pcgrad_combine_kernel<<<n_chunks, 256, 0, st>>>(reinterpret_cast<const Seg*>(seg_tab),
                                                   reinterpret_cast<const int2*>(chunk_tab), T, coef_out);
   MTD_CHECK_LAUNCH();
   return MTD_OK;
+}
+
+int mtd_pcgrad_project(const void* seg_tab, const void* chunk_tab, int n_chunks, int T, const int* orders, int mean,
+                       double* gram_ws, float* coef_out, float* cmat_out, double* gram_out, void* stream) {
+  int rc = mtd_pcgrad_gram(seg_tab, chunk_tab, n_chunks, T, gram_ws, stream);
+  if (rc) return rc;
+  return mtd_pcgrad_solve_combine(seg_tab, chunk_tab, n_chunks, T, orders, mean, gram_ws, coef_out, cmat_out, gram_out, stream);
 }
 
 }  // extern "C"

@@ -129,8 +129,8 @@ class UpsampleBlock(nn.Module):
         cv = self.upsample[0]
         if self._scale != 2:
             raise _ext.MtdError("UpsampleBlock on the B200 path supports scale=2 (the only value the reference uses)")
-        w, b = (cv.weight.detach(), cv.bias.detach()) if freeze else (cv.weight, cv.bias)
-        t = conv(x, w, b, ConvCfg(cin=cv.in_channels, cout=cv.out_channels, kh=1, kw=1, stride=1, pad=0))
+        t = conv(x, cv.weight, cv.bias,
+                 ConvCfg(cin=cv.in_channels, cout=cv.out_channels, kh=1, kw=1, stride=1, pad=0, freeze=freeze))
         return PixelShuffle2Fn.apply(t)
 
     def forward(self, input):
@@ -267,7 +267,6 @@ class Multi_Task_Discriminator_Skip(nn.Module):
         if x.dim() != 4 or x.shape[2] != 64 or x.shape[3] != 64:
             raise RuntimeError(f"Multi_Task_Discriminator_Skip expects (B, C, 64, 64) inputs, got {tuple(x.shape)}")
         sn = self._spectral_norm_step(x.device)
-        frz = (lambda t: t.detach()) if not weight_grads else (lambda t: t)
 
         def layer(name, x1, x2=None, act=ACT_LEAKY):
             m = getattr(self, name)
@@ -281,8 +280,8 @@ class Multi_Task_Discriminator_Skip(nn.Module):
                 kh = kw = 1; stride, pad = 1, 0; cin, cout = m.in_features, m.out_features
             else:
                 kh, kw = m.kernel_size; stride, pad = m.stride[0], m.padding[0]; cin, cout = m.in_channels, m.out_channels
-            cfg = ConvCfg(cin=cin, cout=cout, kh=kh, kw=kw, stride=stride, pad=pad, pre_act=act)
-            return conv(x1, frz(w), frz(m.bias), cfg, x2=x2, inv_sigma=inv, u=u, v=v)
+            cfg = ConvCfg(cin=cin, cout=cout, kh=kh, kw=kw, stride=stride, pad=pad, pre_act=act, freeze=not weight_grads)
+            return conv(x1, w, m.bias, cfg, x2=x2, inv_sigma=inv, u=u, v=v)
 
         t = to_nhwc(x)
         skips = []

@@ -5,6 +5,7 @@ calls into libmtdgan_sm100a.so — PyTorch supplies memory, streams and the auto
 from __future__ import annotations
 
 import os
+import weakref
 from dataclasses import dataclass
 from typing import Optional
 
@@ -26,14 +27,28 @@ def _empty(shape, like):
 # packed-weight cache: reference-layout Parameters stay the masters (state_dict / optimizer
 # compatible); K-major packed copies are rebuilt when the parameter's version counter or storage moves.
 # ------------------------------------------------------------------------------------------------
-_pack_cache: dict = {}
+_pack_cache: dict = {}        # id(weight object) -> {(kind, transposed, stride): (tag, packed)}
+
+
+def _cache_slot(weight) -> dict:
+    k = id(weight)
+    slot = _pack_cache.get(k)
+    if slot is None:
+        slot = {}
+        _pack_cache[k] = slot
+        weakref.finalize(weight, _pack_cache.pop, k, None)     # entry dies with the tensor object
+    return slot
 
 
 def _packed(weight: torch.Tensor, kind: str, cfg: "ConvCfg") -> torch.Tensor:
-    """K-major packed copy of a reference-layout weight, cached on (storage pointer, version)."""
-    key = (weight.data_ptr(), weight.numel(), kind, cfg.transposed, cfg.stride)
-    ent = _pack_cache.get(key)
-    if ent is not None and ent[0] == weight._version:
+    """K-major packed copy of a reference-layout weight.  Cached per weight OBJECT (weakly: entries die
+    with the parameter, so a recycled allocation can never alias a stale entry) and invalidated by the
+    tensor's version counter / storage pointer."""
+    slot = _cache_slot(weight)
+    key = (kind, cfg.transposed, cfg.stride)
+    tag = (weight._version, weight.data_ptr())
+    ent = slot.get(key)
+    if ent is not None and ent[0] == tag:
         return ent[1]
     w = weight.detach()
     out = _empty((w.numel(),), w)
@@ -42,7 +57,7 @@ def _packed(weight: torch.Tensor, kind: str, cfg: "ConvCfg") -> torch.Tensor:
     else:
         call("mtd_conv_pack_dgrad", fptr(w), cfg.transposed, cfg.cout, cfg.cin, cfg.kh, cfg.kw, cfg.stride, fptr(out),
              stream())
-    _pack_cache[key] = (weight._version, out)
+    slot[key] = (tag, out)
     return out
 
 
@@ -84,6 +99,7 @@ class ConvCfg:
     post_act: int = ACT_NONE
     slope: float = LEAK
     fuse_add1_is_input: bool = False   # add1 is x1 itself (block residual): its gradient is fused into dgrad
+    freeze: bool = False               # treat weight / bias as constants (no wgrad, no dbias)
 
 
 _USE_TC = os.environ.get("MTDGAN_CONV", "auto")      # "simt" forces the exact-fp32 kernel everywhere
@@ -124,6 +140,7 @@ class ConvFn(Function):
         _conv_forward_launch(x1, x2, wp, bias, inv_sigma, y, aux, add1, add2, cfg)
         ctx.cfg = cfg
         ctx.has_add = has_add
+        ctx.weight_obj = weight          # identity key of the packed-weight cache
         ctx.shapes = (B, H, W, C1, C2)
         ctx.save_for_backward(x1, x2, weight, inv_sigma, u, v, y, aux)
         return y
@@ -132,8 +149,11 @@ class ConvFn(Function):
     def backward(ctx, dy):
         cfg: ConvCfg = ctx.cfg
         x1, x2, weight, inv_sigma, u, v, y, aux = ctx.saved_tensors
+        weight = ctx.weight_obj
         B, H, W, C1, C2 = ctx.shapes
-        need = ctx.needs_input_grad
+        need = list(ctx.needs_input_grad)
+        if cfg.freeze:
+            need[2] = need[3] = False
         dy = dy.contiguous()
         M = dy.numel() // cfg.cout
         st = stream()
@@ -222,12 +242,14 @@ class FFTConvBlockFn(Function):
         out = _empty(x.shape, x)
         call("mtd_fft_rows_inv", fptr(spec2), fptr(x), fptr(img), fptr(out), B, H, W, C, st)
         if need_graph:
+            ctx.img_w_obj = img_w
             ctx.save_for_backward(x, img_w, fft_w, fft_b, spec, img)
         return out
 
     @staticmethod
     def backward(ctx, dout):
         x, img_w, fft_w, fft_b, spec, img = ctx.saved_tensors
+        img_w = ctx.img_w_obj
         B, H, W, C = x.shape
         st = stream()
         cfg = _img_cfg(C)

