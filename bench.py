@@ -211,6 +211,10 @@ def run_own(args):
         step(xd, yd)
         rec = _ext.stop_profile()
         total_ms = sum(r[2] for r in rec)
+        if os.environ.get("MTD_BENCH_DUMP"):       # per-call records (entry point, integer args, ms) for offline analysis
+            with open(os.environ["MTD_BENCH_DUMP"], "w") as fh:
+                for name, a, t in rec:
+                    fh.write(json.dumps([name, [v for v in a if isinstance(v, int) and abs(v) < 1 << 31], round(t, 5)]) + "\n")
         by = {}
         for name, a, t in rec:
             d = by.setdefault(name, {"ms": 0.0, "calls": 0, "flop": 0.0})

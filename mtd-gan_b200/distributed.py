@@ -1,0 +1,117 @@
+"""Data-parallel MTD-GAN training: one process per GPU, NCCL over NVLink.
+
+The reference has no working multi-GPU path for PCGrad (nn.DataParallel hides `shared_parameters()`,
+SURVEY §2.1), so the semantics are defined here: R ranks x B patches == one process on the concatenated
+R*B batch.  Losses are batch means, so every gradient is averaged over ranks; because PCGrad is non-linear,
+the per-task shared gradients are reduced BEFORE the projection:
+
+    reduce-scatter g_0, g_1, g_2 (each rank keeps a 1/R shard)  ->  partial 3x3 Gram on the shard
+    -> all-reduce 16 doubles -> identical coefficient solve on every rank (same `random.shuffle` stream)
+    -> combine on the shard -> all-gather the merged gradient
+
+which moves 2 x 114 MB less than three all-reduces.  Task-specific and generator gradients are plain
+all-reduce(mean).  The collective choreography is independent of the arithmetic back-end (`ops` argument),
+so world_size-2 gloo tests on CPU exercise it with torch stand-ins.
+"""
+from __future__ import annotations
+
+import os
+from typing import List, Optional, Sequence
+
+import torch
+import torch.distributed as dist
+
+
+def init(backend: Optional[str] = None):
+    """Initialise the default process group from the torchrun environment (idempotent)."""
+    if dist.is_initialized():
+        return
+    backend = backend or ("nccl" if torch.cuda.is_available() else "gloo")
+    dist.init_process_group(backend=backend, init_method="env://")
+
+
+def active() -> bool:
+    return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+
+
+def world() -> int:
+    return dist.get_world_size() if active() else 1
+
+
+def rank() -> int:
+    return dist.get_rank() if active() else 0
+
+
+def shard_bounds(n: int, world_size: int, r: int):
+    """Element range of rank r's shard of a length-n vector padded to a multiple of world_size."""
+    per = (n + world_size - 1) // world_size
+    return per, min(n, r * per), min(n, (r + 1) * per)
+
+
+def flatten(tensors: Sequence[torch.Tensor], pad_to: int = 1) -> torch.Tensor:
+    n = sum(t.numel() for t in tensors)
+    total = (n + pad_to - 1) // pad_to * pad_to
+    flat = torch.zeros(total, dtype=tensors[0].dtype, device=tensors[0].device)
+    off = 0
+    for t in tensors:
+        flat[off:off + t.numel()].copy_(t.reshape(-1))
+        off += t.numel()
+    return flat
+
+
+def unflatten(flat: torch.Tensor, like: Sequence[torch.Tensor]) -> List[torch.Tensor]:
+    out, off = [], 0
+    for t in like:
+        out.append(flat[off:off + t.numel()].view(t.shape))
+        off += t.numel()
+    return out
+
+
+def allreduce_mean_grads(params: Sequence[torch.Tensor]):
+    """p.grad <- mean over ranks, for every parameter that has a gradient (one flat all-reduce)."""
+    if not active():
+        return
+    ps = [p for p in params if p.grad is not None]
+    if not ps:
+        return
+    flat = flatten([p.grad for p in ps])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+    flat.div_(dist.get_world_size())
+    for p, g in zip(ps, unflatten(flat, [p.grad for p in ps])):
+        p.grad = g
+
+
+def allreduce_mean_list(tensors: Sequence[torch.Tensor]) -> List[torch.Tensor]:
+    if not active():
+        return list(tensors)
+    flat = flatten(tensors)
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+    flat.div_(dist.get_world_size())
+    return unflatten(flat, tensors)
+
+
+def pcgrad_sharded(task_grads: Sequence[Sequence[torch.Tensor]], orders, mean: bool, gram_fn, solve_combine_fn):
+    """Distributed PCGrad on per-task gradient lists (all tasks have a gradient for every parameter).
+
+    gram_fn(shards: List[Tensor]) -> float64 tensor [16] with entry [a*4+b] (a <= b) = <shard_a, shard_b>
+    solve_combine_fn(shards, gram16, orders, mean, scale) -> merged shard (Tensor)
+    Returns the merged gradients as views of one flat buffer, identical on every rank.
+    """
+    R, r = dist.get_world_size(), dist.get_rank()
+    T = len(task_grads)
+    n = sum(g.numel() for g in task_grads[0])
+    per, lo, hi = shard_bounds(n, R, r)
+    shards = []
+    for k in range(T):
+        flat = flatten(task_grads[k], pad_to=R)                    # zero padded to R * per
+        shard = torch.empty(per, dtype=flat.dtype, device=flat.device)
+        dist.reduce_scatter_tensor(shard, flat, op=dist.ReduceOp.SUM)
+        shards.append(shard)
+    gram = gram_fn(shards)
+    dist.all_reduce(gram, op=dist.ReduceOp.SUM)
+    # sums (not means) were reduced: the projection coefficients are invariant to a common scale, the 1/R of the
+    # batch mean is applied in the combine
+    merged_shard = solve_combine_fn(shards, gram, orders, mean, 1.0 / R)
+    full = torch.empty(R * per, dtype=merged_shard.dtype, device=merged_shard.device)
+    dist.all_gather_into_tensor(full, merged_shard)
+    return unflatten(full[:n], task_grads[0])

@@ -16,6 +16,7 @@ from typing import Dict, List, Optional, Sequence, Tuple, Union
 import torch
 
 from . import _ext
+from . import distributed as mdist
 from ._ext import call, fptr, ptr, stream
 from .ops import wgrad_only_for
 
@@ -103,6 +104,30 @@ def pcgrad_merge(task_grads: Sequence[Sequence[Optional[torch.Tensor]]], orders:
     return merged
 
 
+def _cuda_gram(shards):
+    """<shard_a, shard_b> for a <= b on the device (fp64), for distributed.pcgrad_sharded."""
+    T, dev = len(shards), shards[0].device
+    row = [fptr(s) for s in shards] + [0] * (4 - T) + [0, shards[0].numel(), _float_bits(1.0), 0]
+    seg = torch.tensor([row], dtype=torch.int64).to(dev, non_blocking=True)
+    chunks, n_chunks = _chunk_table([shards[0].numel()], dev)
+    gram = torch.empty(16, dtype=torch.float64, device=dev)
+    call("mtd_pcgrad_gram", ptr(seg), ptr(chunks), n_chunks, T, ptr(gram), stream())
+    return gram
+
+
+def _cuda_solve_combine(shards, gram, orders, mean, scale):
+    T, dev = len(shards), shards[0].device
+    out = torch.empty_like(shards[0])
+    row = [fptr(s) for s in shards] + [0] * (4 - T) + [fptr(out), out.numel(), _float_bits(scale), 0]
+    seg = torch.tensor([row], dtype=torch.int64).to(dev, non_blocking=True)
+    chunks, n_chunks = _chunk_table([out.numel()], dev)
+    ords = torch.tensor(orders, dtype=torch.int32).to(dev, non_blocking=True)
+    coef = torch.empty(4, dtype=torch.float32, device=dev)
+    call("mtd_pcgrad_solve_combine", ptr(seg), ptr(chunks), n_chunks, T, ptr(ords), 1 if mean else 0, ptr(gram), fptr(coef),
+         None, None, stream())
+    return out
+
+
 class WeightMethod:
     def __init__(self, n_tasks: int, device: torch.device):
         super().__init__()
@@ -156,11 +181,15 @@ class PCGrad(WeightMethod):
             task_specific_parameters = list(task_specific_parameters)
             with wgrad_only_for(task_specific_parameters):
                 ts_grads = torch.autograd.grad(losses.sum(), task_specific_parameters)
+            if mdist.active():
+                ts_grads = mdist.allreduce_mean_list(ts_grads)
             for p, g in zip(task_specific_parameters, ts_grads):
                 p.grad = g
 
     def _project_conflicting(self, grads: List[Tuple[torch.Tensor]]):
-        orders = draw_visit_orders(len(grads))
+        orders = draw_visit_orders(len(grads))          # every rank draws the same orders (same `random` seed)
+        if mdist.active():
+            return mdist.pcgrad_sharded(grads, orders, self.reduction == "mean", _cuda_gram, _cuda_solve_combine)
         return pcgrad_merge(grads, orders, mean=(self.reduction == "mean"))
 
     def backward(self, losses, parameters=None, shared_parameters=None, task_specific_parameters=None, **kwargs):
