@@ -102,7 +102,7 @@ def flops_of(name, a):
         B, H, W, C1, C2, N, kh, kw, s, p = a[9:19]
         Ho, Wo = (H + 2 * p - kh) // s + 1, (W + 2 * p - kw) // s + 1
         return 2.0 * B * Ho * Wo * N * (C1 + C2) * kh * kw
-    if name == "mtd_conv_dgrad":
+    if name in ("mtd_conv_dgrad", "mtd_conv_dgrad_tc"):
         B, H, W, Cin, Cout, kh, kw, s, p = a[9:18]
         Ho, Wo = (H + 2 * p - kh) // s + 1, (W + 2 * p - kw) // s + 1
         return 2.0 * B * Ho * Wo * Cout * Cin * kh * kw
@@ -113,8 +113,9 @@ def flops_of(name, a):
     return 0.0
 
 
-GROUPS = {"conv": ("mtd_conv_fwd", "mtd_conv_fwd_tc", "mtd_conv_dgrad", "mtd_conv_wgrad"),
-          "conv_aux": ("mtd_conv_pack_fwd", "mtd_conv_pack_dgrad", "mtd_conv_wgrad_finish", "mtd_act_bwd"),
+GROUPS = {"conv": ("mtd_conv_fwd", "mtd_conv_fwd_tc", "mtd_conv_dgrad", "mtd_conv_dgrad_tc", "mtd_conv_wgrad", "mtd_conv_wgrad_tc"),
+          "conv_aux": ("mtd_conv_pack_fwd", "mtd_conv_pack_dgrad", "mtd_conv_wgrad_finish", "mtd_act_bwd", "mtd_split_tf32",
+                       "mtd_round_tf32"),
           "fft": ("mtd_fft_rows_fwd", "mtd_fft_cols_mix", "mtd_fft_rows_inv", "mtd_fft_cols_mix_bwd"),
           "spectral_norm": ("mtd_sn_power_iter",), "pcgrad": ("mtd_pcgrad_project",), "adamw": ("mtd_adamw_step",)}
 

@@ -69,13 +69,24 @@ int mtd_act_bwd(const float* dy, const float* y, float* dz, float* dbias, long l
                 void* stream);
 
 /* tcgen05 / TMEM TF32 implicit-GEMM forward for C % 32 == 0 layers (conv_tc.cu).  Same contract as
- * mtd_conv_fwd restricted to one or two sources with C1 % 32 == 0 && C2 % 32 == 0, N % 16 == 0,
- * stride 1, and TMA-tileable spatial dims; returns MTD_EINVAL for anything else (the caller then
- * uses mtd_conv_fwd).  Numerics: TF32 operands, fp32 accumulate (rel. error <= 2e-3).             */
+ * mtd_conv_fwd restricted to one or two sources with C1 % 32 == 0 && C2 % 32 == 0, N % 32 == 0,
+ * stride 1, power-of-two spatial dims; skinny-M layers are split-K; returns MTD_EINVAL for anything else (the caller then
+ * uses mtd_conv_fwd).  passes = 1: TF32 operands, fp32 accumulate (rel. error <= 2e-3), wp tf32-rounded;
+ * passes = 3: error-compensated 3xTF32 (fp32-grade, <= 1e-5), wp = [hi | lo] from mtd_split_tf32.  */
 int mtd_conv_fwd_tc_supported(int B, int H, int W, int C1, int C2, int N, int kh, int kw, int stride, int pad);
+/* in-place round-to-nearest fp32 -> tf32 of a packed weight buffer (tcgen05 truncates its operands)  */
+int mtd_round_tf32(float* p, long long n, void* stream);
 int mtd_conv_fwd_tc(const float* x1, const float* x2, const float* wp, const float* bias, const float* scale, float* y,
                     float* aux, const float* add1, const float* add2, int B, int H, int W, int C1, int C2, int N, int kh,
-                    int kw, int stride, int pad, int pre_act, int post_act, float slope, void* stream);
+                    int kw, int stride, int pad, int pre_act, int post_act, float slope, int passes, void* stream);
+/* dgrad on the tensor cores (stride 1, or stride 2 with 4x4/pad 1); same contract as mtd_conv_dgrad.
+ * passes = 1: wpd tf32-rounded (mtd_round_tf32); passes = 3: wpd = [hi | lo] halves of the full dgrad pack
+ * (mtd_split_tf32); for stride 1 wpd may point at a row slice of the hi half of [cin_total][T][Cout].  */
+int mtd_conv_dgrad_tc(const float* dz, const float* wpd, float* dx, const float* scale, const float* add1, const float* add2,
+                      const float* mask_src, int mask_act, float slope, int B, int H, int W, int Cin, int Cout, int kh, int kw,
+                      int stride, int pad, int passes, int cin_total, void* stream);
+/* in place hi <- rna_tf32(w), lo <- rna_tf32(w - hi): operand split for the 3xTF32 mode               */
+int mtd_split_tf32(float* hi, float* lo, long long n, void* stream);
 
 /* ---- Res-FFT-Conv frequency branch (fft_block.cu) ------------------------------------------------
  * Replaces torch.fft.rfft2 / cat / fft_conv 1x1 + ReLU / chunk / complex / torch.fft.irfft2 at

@@ -1,13 +1,713 @@
-// tcgen05 / TMEM implicit-GEMM convolution (TF32) — under construction in this commit: the entry
-// points exist so the ABI is stable; until the kernel lands they report "unsupported" and the host
-// mirror routes every layer to the exact-fp32 kernel in conv_simt.cu.
+// tcgen05 / TMEM implicit-GEMM convolution for sm_100a (TF32 operands, fp32 accumulate in TMEM).
+//
+//   out[b,h,w,n] = epilogue( sum_t sum_c  in[b, h+dy[t], w+dx[t], c] * wp[n][t][c] )          (stride 1)
+//
+// GEMM view: M = B*H*W output pixels (128 per tile = one TMEM lane each), N = output channels
+// (BN = 32/64/128 per tile), K = taps x channels, consumed 32 channels (128 B, one SWIZZLE_128B row) at a
+// time.  No im2col buffer exists anywhere: for tap t the A tile is the TMA box
+// (32 ch, TW, TH, TB) of the NHWC input at coordinates (c0, w0+dx, h0+dy, b0); the convolution halo / zero
+// padding is TMA's out-of-bounds zero fill.  Two inputs (torch.cat skip connections) are two tensor maps.
+//
+// Persistent, warp-specialised CTA (one per SM), 10 warps:
+//   warp 0      TMA producer  (one elected lane): A box + B box per k-step into a 4..6 stage smem ring
+//   warp 1      MMA issuer    (one elected lane): 4 x tcgen05.mma.kind::tf32 (128 x BN x 8) per k-step,
+//               tcgen05.commit frees the smem stage / publishes the accumulator; owns TMEM alloc/dealloc
+//   warps 2-5   operand rounding: cvt.rna.tf32.f32 of the landed A tile in place (tcgen05 TRUNCATES fp32 to
+//               tf32, a systematic bias; weights are pre-rounded by the pack kernel), fence.proxy.async
+//   warps 6-9   epilogue: tcgen05.ld 32x32b of the finished accumulator (double-buffered in TMEM so it
+//               overlaps the next tile's MMAs), scale(1/sigma)+bias+activation+residual adds, float4 stores
+//
+// Numerics, selectable per call (`passes`):
+//   1  TF32 (10-bit mantissa, round-to-nearest operands), fp32 accumulation: <= 2e-3 relative.
+//   3  error-compensated "3xTF32": a = a_hi + a_lo, w = w_hi + w_lo (each part TF32-exact), D += a_hi*w_hi
+//      + a_lo*w_hi + a_hi*w_lo — the dropped a_lo*w_lo term is ~2^-22 relative, so the result is fp32-grade
+//      (<= 1e-5 relative) at 3 MMAs per k-step.  The rounding warps produce a_lo on the fly; w_lo is
+//      pre-split by mtd_split_tf32.  This is the default for training (gradient parity <= 1e-4).
+// Used for forward convs and stride-1 dgrad with C % 32 == 0, N % 32 == 0 and >= 2048 output pixels;
+// everything else runs on conv_simt.cu (exact fp32).
+#include <cuda.h>
+#include <mutex>
+#include <unordered_map>
+#include <string>
+#include <string.h>
 #include "common.cuh"
 #include "mtdgan_b200.h"
 
+namespace {
+
+constexpr int kMaxTaps = 16;
+constexpr int kBM = 128;
+constexpr int kABytes = kBM * 128;        // 128 rows x 32 tf32
+constexpr int kThreads = 320;
+
+struct TcArgs {
+  int B, H, W, C1, C2, N;
+  int T;
+  int dy[kMaxTaps], dx[kMaxTaps];
+  int TW, TH, TB, n_wt, n_ht, n_bt, n_nt, n_tiles;
+  int kc1, kc2;                 // 32-channel chunks per source
+  int stages;
+  int wrows_total;              // rows of the full packed weight buffer (offset of the lo half, passes == 3)
+  int ksplit, kper;             // split-K: tile = mn_tile * ksplit + ks, k-steps [ks*kper, (ks+1)*kper)
+  int outH, outW, omy, omx, ooy, oox;   // output pixel = (h*omy+ooy, w*omx+oox) in a (B,outH,outW,N) tensor
+  float* out;
+  const float* scale;
+  const float* bias;
+  int pre_act;
+  const float* add1;
+  const float* add2;
+  int post_act;
+  const float* mask_src;
+  int mask_act;
+  float slope;
+  float* aux;
+};
+
+// ---------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  int spins = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) break;
+    if (++spins > (1 << 22)) __trap();      // a lost arrival must fail the launch, never hang the GPU
+  }
+}
+__device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint32_t dst, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint32_t dst, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
+//   [0,14) start address >> 4 | [16,30) LBO >> 4 (=1, unused for swizzled K-major) | [32,46) SBO >> 4
+//   (8 rows x 128 B = 1024 B) | [46,48) version = 1 | [61,64) layout = 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): c=F32 [4,6), a=b=TF32 [7,10)/[10,13), K-major both,
+// N>>3 at [17,23), M>>4 at [24,29)
+__host__ __device__ constexpr uint32_t make_idesc(int bn) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
+}
+
+struct PipeState {
+  int stage = 0;
+  uint32_t phase = 0;
+  __device__ __forceinline__ void advance(int n) {
+    if (++stage == n) { stage = 0; phase ^= 1u; }
+  }
+};
+
+template <int BN, int NPASS>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUtensorMap mapA2,
+               const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapBlo,
+               const __grid_constant__ TcArgs a) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  constexpr int kBBytes = BN * 128;
+  constexpr int kNA = NPASS == 3 ? 2 : 1;                           // A_hi (+ A_lo), B_hi (+ B_lo)
+  constexpr int kStageBytes = kNA * (kABytes + kBBytes);
+  constexpr int kTxBytes = kABytes + kNA * kBBytes;                 // bytes TMA writes per stage (A_lo is produced on chip)
+  constexpr int kOffAlo = kABytes, kOffB = kNA * kABytes, kOffBlo = kNA * kABytes + kBBytes;
+  constexpr uint32_t kTmemCols = (2 * BN) < 32 ? 32 : 2 * BN;      // two accumulators; power of two >= 32
+
+  // 1024-byte alignment for SWIZZLE_128B
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int S = a.stages;
+  const uint32_t bar_base = base + (uint32_t)S * kStageBytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (S + s); };
+  auto conv_bar = [&](int s) { return bar_base + 8u * (2 * S + s); };
+  auto tfull_bar = [&](int i) { return bar_base + 8u * (3 * S + i); };
+  auto tempty_bar = [&](int i) { return bar_base + 8u * (3 * S + 2 + i); };
+  const uint32_t tmem_slot = bar_base + 8u * (3 * S + 4);
+  unsigned char* gen_base = smem_raw + (base - smem_u32(smem_raw));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kchunks = a.kc1 + a.kc2;
+  const int kiters = a.T * kchunks;
+  const int Ctot = (a.kc1 + a.kc2) * 32;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&mapA1);
+    if (a.kc2) prefetch_tmap(&mapA2);
+    prefetch_tmap(&mapB);
+    if (NPASS == 3) prefetch_tmap(&mapBlo);
+    for (int s = 0; s < S; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+      mbar_init(conv_bar(s), 128);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(tfull_bar(i), 1);
+      mbar_init(tempty_bar(i), 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(kTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gen_base + (tmem_slot - base));
+
+  auto decode_tile = [&](int tile, int& b0, int& h0, int& w0, int& n0, int& k_begin, int& k_end) {
+    const int ks = tile % a.ksplit;
+    tile /= a.ksplit;
+    k_begin = ks * a.kper;
+    k_end = min(kiters, k_begin + a.kper);
+    int nt = tile % a.n_nt, m = tile / a.n_nt;
+    int mw = m % a.n_wt;
+    m /= a.n_wt;
+    int mh = m % a.n_ht, mb = m / a.n_ht;
+    b0 = mb * a.TB; h0 = mh * a.TH; w0 = mw * a.TW; n0 = nt * BN;
+  };
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      PipeState st;
+      for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+        int b0, h0, w0, n0, k_begin, k_end;
+        decode_tile(tile, b0, h0, w0, n0, k_begin, k_end);
+        for (int it = k_begin; it < k_end; ++it) {
+          mbar_wait(empty_bar(st.stage), st.phase ^ 1u);
+          mbar_expect_tx(full_bar(st.stage), kTxBytes);
+          const int t = it / kchunks, cc = it - t * kchunks;
+          const uint32_t sa = base + (uint32_t)st.stage * kStageBytes, sb = sa + kOffB;
+          if (cc < a.kc1) tma_load_4d(&mapA1, sa, full_bar(st.stage), cc * 32, w0 + a.dx[t], h0 + a.dy[t], b0);
+          else tma_load_4d(&mapA2, sa, full_bar(st.stage), (cc - a.kc1) * 32, w0 + a.dx[t], h0 + a.dy[t], b0);
+          tma_load_2d(&mapB, sb, full_bar(st.stage), t * Ctot + cc * 32, n0);
+          if (NPASS == 3) tma_load_2d(&mapBlo, sa + kOffBlo, full_bar(st.stage), t * Ctot + cc * 32, n0);
+          st.advance(S);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      PipeState st;
+      constexpr uint32_t idesc = make_idesc(BN);
+      int lt = 0;
+      for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++lt) {
+        const int acc = lt & 1;
+        const uint32_t acc_phase = (uint32_t)(lt >> 1) & 1u;
+        int b0, h0, w0, n0, k_begin, k_end;
+        decode_tile(tile, b0, h0, w0, n0, k_begin, k_end);
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+        for (int it = k_begin; it < k_end; ++it) {
+          mbar_wait(conv_bar(st.stage), st.phase);
+          tc_fence_after();
+          const uint32_t sa = base + (uint32_t)st.stage * kStageBytes;
+          const uint64_t da = make_sw128_desc(sa), db = make_sw128_desc(sa + kOffB);
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {      // 4 x (K = 8 tf32 = 32 B): +2 in 16-byte address units
+            if (NPASS == 3) {                   // small cross terms first, then the main product
+              const uint64_t dal = make_sw128_desc(sa + kOffAlo), dbl = make_sw128_desc(sa + kOffBlo);
+              umma_tf32(tmem_d, dal + 2u * kk, db + 2u * kk, idesc, (it > k_begin || kk > 0) ? 1u : 0u);
+              umma_tf32(tmem_d, da + 2u * kk, dbl + 2u * kk, idesc, 1u);
+              umma_tf32(tmem_d, da + 2u * kk, db + 2u * kk, idesc, 1u);
+            } else {
+              umma_tf32(tmem_d, da + 2u * kk, db + 2u * kk, idesc, (it > k_begin || kk > 0) ? 1u : 0u);
+            }
+          }
+          umma_commit(empty_bar(st.stage));       // implies tcgen05.fence::before_thread_sync
+          st.advance(S);
+        }
+        umma_commit(tfull_bar(acc));
+      }
+    }
+  } else if (warp < 6) {
+    // ===== operand rounding (fp32 -> tf32, round to nearest) =====
+    const int ct = threadIdx.x - 64;               // 0..127
+    PipeState st;
+    for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+      int b0, h0, w0, n0, k_begin, k_end;
+      decode_tile(tile, b0, h0, w0, n0, k_begin, k_end);
+      for (int it = k_begin; it < k_end; ++it) {
+        mbar_wait(full_bar(st.stage), st.phase);
+        float4* tileA = reinterpret_cast<float4*>(gen_base + (size_t)st.stage * kStageBytes);
+#pragma unroll 8
+        for (int j = 0; j < kABytes / 16 / 128; ++j) {
+          float4 v = tileA[ct + 128 * j];
+          uint32_t r0, r1, r2, r3;
+          asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r0) : "f"(v.x));
+          asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r1) : "f"(v.y));
+          asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r2) : "f"(v.z));
+          asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r3) : "f"(v.w));
+          const float4 hi = make_float4(__uint_as_float(r0), __uint_as_float(r1), __uint_as_float(r2), __uint_as_float(r3));
+          tileA[ct + 128 * j] = hi;
+          if (NPASS == 3) {                      // residual a - a_hi is exact in fp32; round it to tf32 as well
+            uint32_t l0, l1, l2, l3;
+            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l0) : "f"(v.x - hi.x));
+            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l1) : "f"(v.y - hi.y));
+            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l2) : "f"(v.z - hi.z));
+            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l3) : "f"(v.w - hi.w));
+            tileA[kOffAlo / 16 + ct + 128 * j] =
+                make_float4(__uint_as_float(l0), __uint_as_float(l1), __uint_as_float(l2), __uint_as_float(l3));
+          }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> tensor-core (async proxy) reads
+        mbar_arrive(conv_bar(st.stage));
+        st.advance(S);
+      }
+    }
+  } else {
+    // ===== epilogue =====
+    const int q = warp & 3;                        // TMEM lane group this warp may access
+    const int r = q * 32 + lane;                   // accumulator row == pixel within the tile
+    const int bl = r / (a.TH * a.TW), rem = r - bl * (a.TH * a.TW);
+    const int hl = rem / a.TW, wl = rem - hl * a.TW;
+    const float scale = a.scale ? __ldg(a.scale) : 1.f;
+    int lt = 0;
+    for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++lt) {
+      int b0, h0, w0, n0, k_begin, k_end;
+      decode_tile(tile, b0, h0, w0, n0, k_begin, k_end);
+      const int acc = lt & 1;
+      const uint32_t acc_phase = (uint32_t)(lt >> 1) & 1u;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const int b = b0 + bl;
+      const bool valid = b < a.B;
+      const size_t rowoff =
+          (((size_t)b * a.outH + ((h0 + hl) * a.omy + a.ooy)) * a.outW + ((w0 + wl) * a.omx + a.oox)) * a.N + n0;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0), v);
+        if (valid && a.ksplit > 1) {
+          // split-K: raw partial sums; scale / bias / activation / adds run in tc_finish_kernel
+#pragma unroll
+          for (int j = 0; j < 32; ++j) atomicAdd(a.out + rowoff + c0 + j, __uint_as_float(v[j]));
+        } else if (valid) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const size_t idx = rowoff + c0 + j;
+            float o[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              float x = __uint_as_float(v[j + e]) * scale;
+              if (a.bias) x += __ldg(a.bias + n0 + c0 + j + e);
+              o[e] = mtd_act(x, a.pre_act, a.slope);
+            }
+            if (a.aux) *reinterpret_cast<float4*>(a.aux + idx) = make_float4(o[0], o[1], o[2], o[3]);
+            if (a.add1) { float4 t = __ldg(reinterpret_cast<const float4*>(a.add1 + idx)); o[0] += t.x; o[1] += t.y; o[2] += t.z; o[3] += t.w; }
+            if (a.add2) { float4 t = __ldg(reinterpret_cast<const float4*>(a.add2 + idx)); o[0] += t.x; o[1] += t.y; o[2] += t.z; o[3] += t.w; }
+#pragma unroll
+            for (int e = 0; e < 4; ++e) o[e] = mtd_act(o[e], a.post_act, a.slope);
+            if (a.mask_src) {
+              float4 t = __ldg(reinterpret_cast<const float4*>(a.mask_src + idx));
+              o[0] *= mtd_act_grad(t.x, a.mask_act, a.slope); o[1] *= mtd_act_grad(t.y, a.mask_act, a.slope);
+              o[2] *= mtd_act_grad(t.z, a.mask_act, a.slope); o[3] *= mtd_act_grad(t.w, a.mask_act, a.slope);
+            }
+            *reinterpret_cast<float4*>(a.out + idx) = make_float4(o[0], o[1], o[2], o[3]);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+  }
+}
+
+// second phase of a split-K launch: `out` holds raw sums over a dense (B,outH,outW,N) tensor
+__global__ void tc_finish_kernel(const __grid_constant__ TcArgs a, size_t total) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
+  const float scale = a.scale ? __ldg(a.scale) : 1.f;
+  for (; i < total; i += stride) {
+    int n = (int)(i % a.N);
+    float x = a.out[i] * scale;
+    if (a.bias) x += __ldg(a.bias + n);
+    x = mtd_act(x, a.pre_act, a.slope);
+    if (a.aux) a.aux[i] = x;
+    if (a.add1) x += __ldg(a.add1 + i);
+    if (a.add2) x += __ldg(a.add2 + i);
+    x = mtd_act(x, a.post_act, a.slope);
+    if (a.mask_src) x *= mtd_act_grad(__ldg(a.mask_src + i), a.mask_act, a.slope);
+    a.out[i] = x;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host side: tensor maps
+// ---------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+std::mutex g_map_mutex;
+std::unordered_map<std::string, CUtensorMap> g_map_cache;
+
+// activations: rank-4 (C, W, H, B) fp32, box (32, TW, TH, TB), SWIZZLE_128B, OOB -> zeros
+int make_act_map(CUtensorMap* out, const float* ptr, int C, int W, int H, int B, int TW, int TH, int TB) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return MTD_EINVAL;
+  char keybuf[128];
+  snprintf(keybuf, sizeof(keybuf), "A%p:%d:%d:%d:%d:%d:%d:%d", (const void*)ptr, C, W, H, B, TW, TH, TB);
+  std::string key(keybuf);
+  {
+    std::lock_guard<std::mutex> lk(g_map_mutex);
+    auto it = g_map_cache.find(key);
+    if (it != g_map_cache.end()) { *out = it->second; return MTD_OK; }
+  }
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4};
+  cuuint32_t box[4] = {32, (cuuint32_t)TW, (cuuint32_t)TH, (cuuint32_t)TB};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return MTD_EINVAL;
+  std::lock_guard<std::mutex> lk(g_map_mutex);
+  if (g_map_cache.size() > 8192) g_map_cache.clear();
+  g_map_cache[key] = *out;
+  return MTD_OK;
+}
+
+// packed weights: rank-2 (K = T*Ctot, rows) fp32, box (32, BN)
+int make_w_map(CUtensorMap* out, const float* ptr, long long K, int rows, int BN) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return MTD_EINVAL;
+  char keybuf[128];
+  snprintf(keybuf, sizeof(keybuf), "W%p:%lld:%d:%d", (const void*)ptr, K, rows, BN);
+  std::string key(keybuf);
+  {
+    std::lock_guard<std::mutex> lk(g_map_mutex);
+    auto it = g_map_cache.find(key);
+    if (it != g_map_cache.end()) { *out = it->second; return MTD_OK; }
+  }
+  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)K * 4};
+  cuuint32_t box[2] = {32, (cuuint32_t)BN};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return MTD_EINVAL;
+  std::lock_guard<std::mutex> lk(g_map_mutex);
+  if (g_map_cache.size() > 8192) g_map_cache.clear();
+  g_map_cache[key] = *out;
+  return MTD_OK;
+}
+
+bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
+
+bool tc_geometry(int B, int H, int W, int C1, int C2, int N, int kh, int kw, int stride, int pad, int* TW, int* TH, int* TB) {
+  if (stride != 1 || kh != kw || 2 * pad != kh - 1 || kh * kw > kMaxTaps) return false;
+  if (C1 <= 0 || C1 % 32 || C2 < 0 || C2 % 32 || N <= 0 || N % 32) return false;
+  if (!is_pow2(W) || !is_pow2(H)) return false;
+  if ((long long)B * H * W < 16) return false;
+  int tw = W < kBM ? W : kBM;
+  int th = kBM / tw;
+  if (th > H) th = H;
+  int tb = kBM / (tw * th);
+  if (tw * th * tb != kBM || tb > 256) return false;
+  *TW = tw; *TH = th; *TB = tb;
+  return true;
+}
+
+template <int BN, int NPASS>
+int launch_bn(const CUtensorMap& mA1, const CUtensorMap& mA2, const CUtensorMap& mB, const CUtensorMap& mBlo, TcArgs& a,
+              cudaStream_t st) {
+  const int stage_bytes = (NPASS == 3 ? 2 : 1) * (kABytes + BN * 128);
+  const int kiters = a.kper;
+  int stages = (200 * 1024) / stage_bytes;
+  if (stages > 6) stages = 6;
+  if (stages > kiters) stages = kiters < 2 ? 2 : kiters;
+  a.stages = stages;
+  size_t smem = 1024 + (size_t)stages * stage_bytes + 8 * (3 * stages + 4) + 16;
+  static bool attr_set = false;
+  if (!attr_set) {
+    MTD_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, NPASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  int grid = a.n_tiles < mtd_sm_count() ? a.n_tiles : mtd_sm_count();
+  conv_tc_kernel<BN, NPASS><<<grid, kThreads, smem, st>>>(mA1, mA2, mB, mBlo, a);
+  MTD_CHECK_LAUNCH();
+  return MTD_OK;
+}
+
+// wp: packed weights [N][T][C]; for passes == 3 the buffer holds [hi | lo] (2 x N*T*C floats, mtd_split_tf32).
+// `finish`: run the split-K finishing pass here (false when the caller batches several launches into one
+// output, e.g. the four parity classes of a stride-2 dgrad).  Returns the chosen ksplit through a.ksplit.
+int launch_tc(const float* x1, const float* x2, const float* wp, int passes, TcArgs& a, cudaStream_t st, int force_split = 0,
+              bool finish = true) {
+  if (passes != 1 && passes != 3) return MTD_EINVAL;
+  if (!tc_geometry(a.B, a.H, a.W, a.C1, a.C2, a.N, 1, 1, 1, 0, &a.TW, &a.TH, &a.TB)) return MTD_EINVAL;
+  if (!mtd_aligned16(x1) || !mtd_aligned16(wp) || !mtd_aligned16(a.out) || (x2 && !mtd_aligned16(x2))) return MTD_EALIGN;
+  a.n_wt = a.W / a.TW; a.n_ht = a.H / a.TH; a.n_bt = (a.B + a.TB - 1) / a.TB;
+  const int m_tiles = a.n_wt * a.n_ht * a.n_bt;
+  a.kc1 = a.C1 / 32; a.kc2 = a.C2 / 32;
+  const int kiters = a.T * (a.kc1 + a.kc2);
+  const int sms = mtd_sm_count();
+  // Cout tile: as wide as possible while the grid still fills the machine (skinny-M layers stream the
+  // weights: narrower tiles + split-K spread that stream over all SMs)
+  int BN = a.N >= 128 ? 128 : (a.N >= 64 ? 64 : 32);
+  while (BN > 32 && m_tiles * (a.N / BN) < sms) BN >>= 1;
+  if (a.N % BN) return MTD_EINVAL;
+  a.n_nt = a.N / BN;
+  int mn_tiles = m_tiles * a.n_nt;
+  int ksplit = 1;
+  if (force_split > 0) ksplit = force_split;
+  else if (mn_tiles < sms && kiters >= 8) {
+    ksplit = (sms + mn_tiles - 1) / mn_tiles;
+    if (ksplit > kiters / 4) ksplit = kiters / 4;
+    if (ksplit < 1) ksplit = 1;
+  }
+  a.kper = (kiters + ksplit - 1) / ksplit;
+  ksplit = (kiters + a.kper - 1) / a.kper;          // no empty splits
+  a.ksplit = ksplit;
+  a.n_tiles = mn_tiles * ksplit;
+  const size_t total = (size_t)a.B * a.outH * a.outW * a.N;
+  if (ksplit > 1 && finish) MTD_CUDA(cudaMemsetAsync(a.out, 0, total * sizeof(float), st));
+  CUtensorMap mA1, mA2, mB;
+  int rc = make_act_map(&mA1, x1, a.C1, a.W, a.H, a.B, a.TW, a.TH, a.TB);
+  if (rc) return rc;
+  if (a.C2) { rc = make_act_map(&mA2, x2, a.C2, a.W, a.H, a.B, a.TW, a.TH, a.TB); if (rc) return rc; }
+  else mA2 = mA1;
+  const long long K = (long long)a.T * (a.C1 + a.C2);
+  rc = make_w_map(&mB, wp, K, a.N, BN);
+  if (rc) return rc;
+  CUtensorMap mBlo = mB;
+  if (passes == 3) {
+    // the lo half follows the hi half of the FULL packed weight (a.wrows_total rows), not of this row slice
+    rc = make_w_map(&mBlo, wp + (size_t)a.wrows_total * K, K, a.N, BN);
+    if (rc) return rc;
+  }
+#define TC_DISPATCH(BN_)                                                           \
+  rc = passes == 3 ? launch_bn<BN_, 3>(mA1, mA2, mB, mBlo, a, st) : launch_bn<BN_, 1>(mA1, mA2, mB, mBlo, a, st)
+  if (BN == 128) { TC_DISPATCH(128); }
+  else if (BN == 64) { TC_DISPATCH(64); }
+  else { TC_DISPATCH(32); }
+#undef TC_DISPATCH
+  if (rc) return rc;
+  if (ksplit > 1 && finish) {
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > sms * 8) blocks = sms * 8;
+    tc_finish_kernel<<<blocks, 256, 0, st>>>(a, total);
+    MTD_CHECK_LAUNCH();
+  }
+  return MTD_OK;
+}
+
+__global__ void split_tf32_kernel(float* __restrict__ hi, float* __restrict__ lo, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    float w = hi[i];
+    uint32_t h, l;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(w));
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(w - __uint_as_float(h)));
+    hi[i] = __uint_as_float(h);
+    lo[i] = __uint_as_float(l);
+  }
+}
+
+__global__ void round_tf32_kernel(float* __restrict__ p, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(p[i]));
+    p[i] = __uint_as_float(r);
+  }
+}
+
+}  // namespace
+
 extern "C" {
-int mtd_conv_fwd_tc_supported(int, int, int, int, int, int, int, int, int, int) { return 0; }
-int mtd_conv_fwd_tc(const float*, const float*, const float*, const float*, const float*, float*, float*, const float*,
-                    const float*, int, int, int, int, int, int, int, int, int, int, int, int, float, void*) {
-  return MTD_EINVAL;
+
+int mtd_conv_fwd_tc_supported(int B, int H, int W, int C1, int C2, int N, int kh, int kw, int stride, int pad) {
+  int tw, th, tb;
+  return tc_geometry(B, H, W, C1, C2, N, kh, kw, stride, pad, &tw, &th, &tb) && get_encode() != nullptr ? 1 : 0;
 }
+
+// Rounds a packed weight buffer to TF32 (round to nearest, ties away) in place — the B operand of the
+// tensor-core kernels must be pre-rounded because tcgen05 truncates.
+int mtd_round_tf32(float* p, long long n, void* stream) {
+  MTD_REQUIRE(p && n > 0);
+  int blocks = (int)(((size_t)n + 255) / 256);
+  if (blocks > mtd_sm_count() * 16) blocks = mtd_sm_count() * 16;
+  round_tf32_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(p, (size_t)n);
+  MTD_CHECK_LAUNCH();
+  return MTD_OK;
 }
+
+// In place: hi <- rna_tf32(w), lo <- rna_tf32(w - hi).  `lo` normally points n floats past `hi`.
+int mtd_split_tf32(float* hi, float* lo, long long n, void* stream) {
+  MTD_REQUIRE(hi && lo && n > 0);
+  int blocks = (int)(((size_t)n + 255) / 256);
+  if (blocks > mtd_sm_count() * 16) blocks = mtd_sm_count() * 16;
+  split_tf32_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(hi, lo, (size_t)n);
+  MTD_CHECK_LAUNCH();
+  return MTD_OK;
+}
+
+int mtd_conv_fwd_tc(const float* x1, const float* x2, const float* wp, const float* bias, const float* scale, float* y,
+                    float* aux, const float* add1, const float* add2, int B, int H, int W, int C1, int C2, int N, int kh,
+                    int kw, int stride, int pad, int pre_act, int post_act, float slope, int passes, void* stream) {
+  MTD_REQUIRE(x1 && wp && y && ((C2 == 0) == (x2 == nullptr)));
+  int tw, th, tb;
+  if (!tc_geometry(B, H, W, C1, C2, N, kh, kw, stride, pad, &tw, &th, &tb)) return MTD_EINVAL;
+  TcArgs a{};
+  a.B = B; a.H = H; a.W = W; a.C1 = C1; a.C2 = C2; a.N = N; a.T = kh * kw;
+  for (int ky = 0; ky < kh; ++ky)
+    for (int kx = 0; kx < kw; ++kx) { a.dy[ky * kw + kx] = ky - pad; a.dx[ky * kw + kx] = kx - pad; }
+  a.out = y; a.scale = scale; a.bias = bias; a.pre_act = pre_act; a.add1 = add1; a.add2 = add2; a.post_act = post_act;
+  a.mask_src = nullptr; a.mask_act = 0; a.slope = slope; a.aux = aux;
+  a.wrows_total = N;
+  a.outH = H; a.outW = W; a.omy = a.omx = 1; a.ooy = a.oox = 0;
+  return launch_tc(x1, x2, wp, passes, a, (cudaStream_t)stream);
+}
+
+// Data gradient on the tensor cores: dx = (scale * dgrad(dz) + add1 + add2) * act'(mask_src).
+// stride 1: dz (B,H,W,Cout), wpd[Cin][kh*kw][Cout].  stride 2 (4x4, pad 1): dz (B,H/2,W/2,Cout),
+// wpd[4][Cin][4][Cout]: four output-parity classes, each a 2x2-tap stride-1 conv over dz scattered to
+// (2i+py, 2j+px).  (H, W) are the conv INPUT dims = dx dims.
+int mtd_conv_dgrad_tc(const float* dz, const float* wpd, float* dx, const float* scale, const float* add1, const float* add2,
+                      const float* mask_src, int mask_act, float slope, int B, int H, int W, int Cin, int Cout, int kh, int kw,
+                      int stride, int pad, int passes, int cin_total, void* stream) {
+  MTD_REQUIRE(dz && wpd && dx);
+  cudaStream_t st = (cudaStream_t)stream;
+  int tw, th, tb;
+  TcArgs a{};
+  a.B = B; a.C1 = Cout; a.C2 = 0; a.N = Cin;
+  a.out = dx; a.scale = scale; a.bias = nullptr; a.pre_act = 0; a.add1 = add1; a.add2 = add2; a.post_act = 0;
+  a.mask_src = mask_src; a.mask_act = mask_act; a.slope = slope; a.aux = nullptr;
+  a.outH = H; a.outW = W;
+  if (stride == 1) {
+    if (!tc_geometry(B, H, W, Cout, 0, Cin, kh, kw, 1, pad, &tw, &th, &tb)) return MTD_EINVAL;
+    a.H = H; a.W = W; a.T = kh * kw;
+    for (int ky = 0; ky < kh; ++ky)
+      for (int kx = 0; kx < kw; ++kx) { a.dy[ky * kw + kx] = pad - ky; a.dx[ky * kw + kx] = pad - kx; }
+    a.omy = a.omx = 1; a.ooy = a.oox = 0;
+    a.wrows_total = cin_total;    // wpd may point at a row slice [cin_off, cin_off + Cin) of the [cin_total][T][Cout] pack
+    return launch_tc(dz, nullptr, wpd, passes, a, st);
+  }
+  MTD_REQUIRE(stride == 2 && kh == 4 && kw == 4 && pad == 1 && H % 2 == 0 && W % 2 == 0 && cin_total == Cin);
+  if (!tc_geometry(B, H / 2, W / 2, Cout, 0, Cin, 1, 1, 1, 0, &tw, &th, &tb)) return MTD_EINVAL;
+  a.H = H / 2; a.W = W / 2; a.T = 4; a.omy = a.omx = 2;
+  const size_t total = (size_t)B * H * W * Cin;
+  const size_t cls_elems = (size_t)Cin * 4 * Cout;
+  int ksplit = 0;
+  for (int py = 0; py < 2; ++py)
+    for (int px = 0; px < 2; ++px) {
+      TcArgs c = a;
+      for (int aa = 0; aa < 2; ++aa)
+        for (int bb = 0; bb < 2; ++bb) {
+          int ky = (1 - py) + 2 * aa, kx = (1 - px) + 2 * bb;
+          c.dy[aa * 2 + bb] = (py + 1 - ky) / 2;
+          c.dx[aa * 2 + bb] = (px + 1 - kx) / 2;
+        }
+      c.ooy = py; c.oox = px;
+      // packed layout [4 classes][Cin][4][Cout]; for passes == 3 the lo half starts after all four classes
+      c.wrows_total = 4 * Cin;                            // rows from this class's base to the lo copy of the same class
+      if (py == 0 && px == 0) {
+        // decide the split once so all classes agree; zero dx up front when partial sums will be accumulated
+        TcArgs probe = c;
+        probe.n_wt = probe.W / tw; probe.n_ht = probe.H / th; probe.n_bt = (B + tb - 1) / tb;
+        int m_tiles = probe.n_wt * probe.n_ht * probe.n_bt, kiters = 4 * (Cout / 32), sms = mtd_sm_count();
+        int BN = Cin >= 128 ? 128 : (Cin >= 64 ? 64 : 32);
+        while (BN > 32 && m_tiles * (Cin / BN) < sms) BN >>= 1;
+        int mn = m_tiles * (Cin / BN);
+        ksplit = 1;
+        if (mn < sms && kiters >= 8) {
+          ksplit = (sms + mn - 1) / mn;
+          if (ksplit > kiters / 4) ksplit = kiters / 4;
+          if (ksplit < 1) ksplit = 1;
+        }
+        const int kper = (kiters + ksplit - 1) / ksplit;
+        ksplit = (kiters + kper - 1) / kper;
+        if (ksplit > 1) MTD_CUDA(cudaMemsetAsync(dx, 0, total * sizeof(float), st));
+      }
+      int rc = launch_tc(dz, nullptr, wpd + (size_t)(py * 2 + px) * cls_elems, passes, c, st, ksplit, false);
+      if (rc) return rc;
+      if (c.ksplit != ksplit) return MTD_EINVAL;
+    }
+  if (ksplit > 1) {
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > mtd_sm_count() * 8) blocks = mtd_sm_count() * 8;
+    tc_finish_kernel<<<blocks, 256, 0, st>>>(a, total);
+    MTD_CHECK_LAUNCH();
+  }
+  // ksplit == 1: the per-class epilogues already applied scale / adds / mask (each output pixel belongs to one class)
+  return MTD_OK;
+}
+
+}  // extern "C"

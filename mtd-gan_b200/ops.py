@@ -51,12 +51,17 @@ def _packed(weight: torch.Tensor, kind: str, cfg: "ConvCfg") -> torch.Tensor:
     if ent is not None and ent[0] == tag:
         return ent[1]
     w = weight.detach()
-    out = _empty((w.numel(),), w)
-    if kind == "fwd":
+    out = _empty((w.numel() * (2 if kind.endswith("_tf32x3") else 1),), w)
+    if kind.startswith("fwd"):
         call("mtd_conv_pack_fwd", fptr(w), cfg.transposed, cfg.cout, cfg.cin, cfg.kh, cfg.kw, fptr(out), stream())
     else:
         call("mtd_conv_pack_dgrad", fptr(w), cfg.transposed, cfg.cout, cfg.cin, cfg.kh, cfg.kw, cfg.stride, fptr(out),
              stream())
+    if kind.endswith("_tf32"):          # B operand of the tcgen05 kernels: round to nearest (the MMA truncates)
+        call("mtd_round_tf32", fptr(out), out.numel(), stream())
+    elif kind.endswith("_tf32x3"):      # [hi | lo] halves for the error-compensated 3xTF32 mode
+        n = w.numel()
+        call("mtd_split_tf32", fptr(out), out.data_ptr() + 4 * n, n, stream())
     slot[key] = (tag, out)
     return out
 
@@ -103,18 +108,70 @@ class ConvCfg:
 
 
 _USE_TC = os.environ.get("MTDGAN_CONV", "auto")      # "simt" forces the exact-fp32 kernel everywhere
+tc_launches = 0                                       # tcgen05 conv launches so far (tests / bench evidence)
 
 
-def _conv_forward_launch(x1, x2, wp, bias, scale, y, aux, add1, add2, cfg: ConvCfg):
+_TC_PASSES = 1 if os.environ.get("MTDGAN_TF32", "x3") == "x1" else 3
+
+
+def set_conv_mode(mode: str, passes: int | None = None):
+    """"auto": tcgen05 kernels where they apply, exact fp32 SIMT elsewhere; "simt": exact fp32 only.
+    passes: 3 = error-compensated 3xTF32 (fp32-grade, default), 1 = plain TF32 (<= 2e-3)."""
+    global _USE_TC, _TC_PASSES
+    assert mode in ("auto", "simt")
+    _USE_TC = mode
+    if passes is not None:
+        assert passes in (1, 3)
+        _TC_PASSES = passes
+
+
+def _tc_kind(base: str) -> str:
+    return base + ("_tf32x3" if _TC_PASSES == 3 else "_tf32")
+
+
+def _tc_ok(B, H, W, C1, C2, N, kh, kw, stride, pad) -> bool:
+    """Kernel selection: the tcgen05 TF32 kernel takes stride-1 layers with C % 32 == 0, N % 32 == 0 and
+    >= 2048 output pixels; skinny-M / thin / strided layers stay on the exact-fp32 SIMT kernel."""
+    return _USE_TC != "simt" and _ext.load().mtd_conv_fwd_tc_supported(B, H, W, C1, C2, N, kh, kw, stride, pad) == 1
+
+
+def _conv_forward_launch(x1, x2, weight, bias, scale, y, aux, add1, add2, cfg: ConvCfg):
     B, H, W, C1 = x1.shape
     C2 = 0 if x2 is None else x2.shape[3]
-    args = (fptr(x1), fptr(x2), fptr(wp), fptr(bias), fptr(scale), fptr(y), fptr(aux), fptr(add1), fptr(add2), B, H, W, C1,
-            C2, cfg.cout, cfg.kh, cfg.kw, cfg.stride, cfg.pad, cfg.pre_act, cfg.post_act, cfg.slope, stream())
-    if _USE_TC != "simt" and _ext.load().mtd_conv_fwd_tc_supported(B, H, W, C1, C2, cfg.cout, cfg.kh, cfg.kw, cfg.stride,
-                                                                    cfg.pad) == 1:
-        call("mtd_conv_fwd_tc", *args)
+    tc = _tc_ok(B, H, W, C1, C2, cfg.cout, cfg.kh, cfg.kw, cfg.stride, cfg.pad)
+    if tc:
+        wp = _packed(weight, _tc_kind("fwd"), cfg)
     else:
-        call("mtd_conv_fwd", *args)
+        wp = _packed(weight, "fwd", cfg) if cfg.kh * cfg.kw > 1 or cfg.transposed else weight.detach()
+    args = (fptr(x1), fptr(x2), fptr(wp), fptr(bias), fptr(scale), fptr(y), fptr(aux), fptr(add1), fptr(add2), B, H, W, C1,
+            C2, cfg.cout, cfg.kh, cfg.kw, cfg.stride, cfg.pad, cfg.pre_act, cfg.post_act, cfg.slope)
+    if tc:
+        global tc_launches
+        tc_launches += 1
+        call("mtd_conv_fwd_tc", *args, _TC_PASSES, stream())
+    else:
+        call("mtd_conv_fwd", *args, stream())
+
+
+def _conv_dgrad_launch(dz, weight, dx, scale, add1, B, H, W, cin_sub, cin_off, cfg: ConvCfg):
+    """dx (B,H,W,cin_sub) = scale * dgrad(dz) (+ add1) for input channels [cin_off, cin_off + cin_sub)."""
+    T = cfg.kh * cfg.kw
+    st = stream()
+    if cfg.stride == 1:
+        tc = _tc_ok(B, H, W, cfg.cout, 0, cin_sub, cfg.kh, cfg.kw, 1, cfg.pad)
+    else:   # 4x4 stride-2: four parity classes of 2x2-tap stride-1 convs over dz (B,H/2,W/2,Cout)
+        tc = (cfg.stride == 2 and cfg.kh == 4 and cfg.kw == 4 and cfg.pad == 1 and cin_off == 0 and cin_sub == cfg.cin
+              and H % 2 == 0 and W % 2 == 0 and _tc_ok(B, H // 2, W // 2, cfg.cout, 0, cin_sub, 1, 1, 1, 0))
+    if tc:
+        global tc_launches
+        tc_launches += 1
+        wpd = _packed(weight, _tc_kind("dgrad"), cfg)
+        call("mtd_conv_dgrad_tc", fptr(dz), wpd.data_ptr() + 4 * cin_off * T * cfg.cout, fptr(dx), fptr(scale), fptr(add1), None,
+             None, 0, cfg.slope, B, H, W, cin_sub, cfg.cout, cfg.kh, cfg.kw, cfg.stride, cfg.pad, _TC_PASSES, cfg.cin, st)
+    else:
+        wpd = _packed(weight, "dgrad", cfg)
+        call("mtd_conv_dgrad", fptr(dz), wpd.data_ptr() + 4 * cin_off * T * cfg.cout, fptr(dx), fptr(scale), fptr(add1), None,
+             None, 0, cfg.slope, B, H, W, cin_sub, cfg.cout, cfg.kh, cfg.kw, cfg.stride, cfg.pad, st)
 
 
 class ConvFn(Function):
@@ -132,12 +189,11 @@ class ConvFn(Function):
         assert C1 + C2 == cfg.cin, (C1, C2, cfg)
         Ho = (H + 2 * cfg.pad - cfg.kh) // cfg.stride + 1
         Wo = (W + 2 * cfg.pad - cfg.kw) // cfg.stride + 1
-        wp = _packed(weight, "fwd", cfg) if cfg.kh * cfg.kw > 1 or cfg.transposed else weight.detach()
         y = _empty((B, Ho, Wo, cfg.cout), x1)
         has_add = add1 is not None or add2 is not None
         need_graph = any(ctx.needs_input_grad)
         aux = _empty(y.shape, x1) if (need_graph and cfg.pre_act != ACT_NONE and has_add) else None
-        _conv_forward_launch(x1, x2, wp, bias, inv_sigma, y, aux, add1, add2, cfg)
+        _conv_forward_launch(x1, x2, weight, bias, inv_sigma, y, aux, add1, add2, cfg)
         ctx.cfg = cfg
         ctx.has_add = has_add
         ctx.weight_obj = weight          # identity key of the packed-weight cache
@@ -174,24 +230,13 @@ class ConvFn(Function):
                 call("mtd_act_bwd", fptr(g1), None, None, fptr(dbias), M, cfg.cout, ACT_NONE, cfg.slope, st)
         # 2) data gradients
         dx1 = dx2 = None
-        if need[0] or need[1]:
-            wpd = _packed(weight, "dgrad", cfg)
-            T = cfg.kh * cfg.kw
-            fuse = g1 if (cfg.fuse_add1_is_input and need[0]) else None
-            if cfg.stride == 1:
-                if need[0]:
-                    dx1 = _empty((B, H, W, C1), dy)
-                    call("mtd_conv_dgrad", fptr(dz), fptr(wpd), fptr(dx1), fptr(inv_sigma), fptr(fuse), None, None, 0,
-                         cfg.slope, B, H, W, C1, cfg.cout, cfg.kh, cfg.kw, 1, cfg.pad, st)
-                if C2 and need[1]:
-                    dx2 = _empty((B, H, W, C2), dy)
-                    call("mtd_conv_dgrad", fptr(dz), wpd.data_ptr() + 4 * C1 * T * cfg.cout, fptr(dx2), fptr(inv_sigma),
-                         None, None, None, 0, cfg.slope, B, H, W, C2, cfg.cout, cfg.kh, cfg.kw, 1, cfg.pad, st)
-            else:
-                assert C2 == 0
-                dx1 = _empty((B, H, W, C1), dy)
-                call("mtd_conv_dgrad", fptr(dz), fptr(wpd), fptr(dx1), fptr(inv_sigma), None, None, None, 0, cfg.slope, B,
-                     H, W, C1, cfg.cout, cfg.kh, cfg.kw, cfg.stride, cfg.pad, st)
+        if need[0]:
+            dx1 = _empty((B, H, W, C1), dy)
+            fuse = g1 if cfg.fuse_add1_is_input else None
+            _conv_dgrad_launch(dz, weight, dx1, inv_sigma, fuse, B, H, W, C1, 0, cfg)
+        if C2 and need[1]:
+            dx2 = _empty((B, H, W, C2), dy)
+            _conv_dgrad_launch(dz, weight, dx2, inv_sigma, None, B, H, W, C2, C1, cfg)
         # 3) weight gradient (packed), then to reference layout (+ spectral-norm correction)
         dw = None
         if need[2] and _wgrad_wanted(weight):
@@ -238,7 +283,7 @@ class FFTConvBlockFn(Function):
         spec2 = _empty(spec.shape, x) if need_graph else spec          # in place when nothing is saved
         call("mtd_fft_cols_mix", fptr(spec), fptr(spec2), fptr(fft_w.detach()), fptr(fft_b.detach()), B, H, W, C, st)
         img = _empty(x.shape, x)
-        _conv_forward_launch(x, None, _packed(img_w, "fwd", cfg), img_b.detach(), None, img, None, None, None, cfg)
+        _conv_forward_launch(x, None, img_w, img_b.detach(), None, img, None, None, None, cfg)
         out = _empty(x.shape, x)
         call("mtd_fft_rows_inv", fptr(spec2), fptr(x), fptr(img), fptr(out), B, H, W, C, st)
         if need_graph:
@@ -272,8 +317,7 @@ class FFTConvBlockFn(Function):
         dx = None
         if need[0]:
             dxc = _empty(x.shape, x)      # dgrad(dz) + dout   (residual path fused)
-            call("mtd_conv_dgrad", fptr(dz), fptr(_packed(img_w, "dgrad", cfg)), fptr(dxc), None, fptr(dout), None, None, 0,
-                 LEAK, B, H, W, C, C, 3, 3, 1, 1, st)
+            _conv_dgrad_launch(dz, img_w, dxc, None, dout, B, H, W, C, 0, cfg)
             dx = _empty(x.shape, x)       # + frequency-branch gradient, fused into the inverse row pass
             call("mtd_fft_rows_inv", fptr(gspec), fptr(dxc), None, fptr(dx), B, H, W, C, st)
         diw = None

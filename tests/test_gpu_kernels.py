@@ -86,6 +86,101 @@ def test_conv_forward_backward(case):
         assert rel_err(nchw(sc.grad), sr.grad) <= TOL
 
 
+TC_CASES = [
+    # B, H, W, C1, C2, N, k, p, transposed, pre, post, add     (all stride 1, >= 2048 output pixels)
+    (2, 64, 64, 32, 0, 32, 3, 1, 0, 1, 0, False),        # generator encoder / img_conv
+    (2, 64, 64, 32, 0, 32, 3, 1, 1, 0, 1, True),         # generator decoder (ConvTranspose + skip + relu)
+    (2, 32, 32, 64, 64, 128, 3, 1, 0, 2, 0, False),      # decoder conv on cat[up, skip]
+    (4, 32, 32, 128, 0, 64, 1, 0, 0, 2, 0, False),       # 1x1
+    (8, 16, 16, 256, 0, 256, 3, 1, 0, 2, 0, False),      # TW=16, TH=8
+    (33, 8, 8, 256, 0, 512, 3, 1, 0, 2, 0, False),       # TW=8, TH=8, TB=2 with a ragged last batch tile
+    (1, 32, 128, 32, 0, 32, 3, 1, 0, 1, 0, False),       # TW=128, TH=1
+    (1, 8, 512, 32, 0, 64, 3, 1, 0, 1, 0, False),        # 512-wide rows (inference geometry)
+    (20, 4, 4, 512, 0, 512, 3, 1, 0, 2, 0, False),       # skinny M = 320: split-K weight streaming
+    (20, 2, 2, 512, 512, 512, 3, 1, 0, 2, 0, False),     # M = 80, two sources, split-K
+    (20, 1, 1, 512, 0, 512, 1, 0, 0, 2, 0, False),       # bottleneck 1x1 at 1x1 spatial (TB = 128)
+    (3, 4, 4, 512, 0, 2048, 1, 0, 0, 0, 0, False),       # UpsampleBlock 1x1 conv C -> 4C
+]
+
+
+@pytest.mark.parametrize("passes,tol", [(1, 2e-3), (3, 5e-5)], ids=["tf32", "tf32x3"])
+@pytest.mark.parametrize("B,H,C", [(2, 64, 64), (20, 8, 512), (20, 2, 512), (3, 16, 256)])
+def test_conv_tcgen05_stride2_dgrad(B, H, C, passes, tol):
+    """down* layers (4x4, stride 2, pad 1): data gradient as four parity classes on the tcgen05 kernel."""
+    from mtdgan_b200 import ops
+    x = _rand(B, C, H, H, seed=1)
+    w = _rand(C, C, 4, 4, seed=2, scale=1.0 / math.sqrt(C * 16))
+    gout = _rand(B, C, H // 2, H // 2, seed=5)
+    xr = x.clone().requires_grad_(True)
+    F.conv2d(xr, w, None, stride=2, padding=1).backward(gout)
+    xc = nhwc(x.float()).to(DEV).requires_grad_(True)
+    wc = w.float().to(DEV)
+    bc = torch.zeros(C, device=DEV)
+    cfg = ops.ConvCfg(cin=C, cout=C, kh=4, kw=4, stride=2, pad=1)
+    ops.set_conv_mode("auto", passes)
+    try:
+        n0 = ops.tc_launches
+        y = ops.conv(xc, wc, bc, cfg)
+        y.backward(nhwc(gout.float()).to(DEV))
+        torch.cuda.synchronize()
+        assert ops.tc_launches - n0 == 1, "tcgen05 dgrad was not selected"
+    finally:
+        ops.set_conv_mode("auto", 3)
+    assert rel_err(nchw(xc.grad), xr.grad) <= tol
+
+
+@pytest.mark.parametrize("passes,tol", [(1, 2e-3), (3, 5e-5)], ids=["tf32", "tf32x3"])
+@pytest.mark.parametrize("case", TC_CASES, ids=lambda c: "x".join(map(str, c)))
+def test_conv_tcgen05_forward_backward(case, passes, tol):
+    """tcgen05/TMEM kernel (forward + dgrad) vs fp64 torch: plain TF32 <= 2e-3, error-compensated 3xTF32 <= 2e-5;
+    and it must really be the kernel that ran.  The backward reference uses the activation mask of the CUDA
+    forward (a ReLU sign flip at |z| ~ 1e-3 is not a kernel error; the mask kernels are tested on their own)."""
+    from mtdgan_b200 import ops
+    B, H, W, C1, C2, N, k, p, tr, pre, post, add = case
+    C = C1 + C2
+    x = _rand(B, C, H, W, seed=1)
+    w = _rand(*((C, N, k, k) if tr else (N, C, k, k)), seed=2, scale=1.0 / math.sqrt(C * k * k))
+    b = _rand(N, seed=3, scale=0.1)
+    skip = _rand(B, N, H, W, seed=4) if add else None
+    gout = _rand(B, N, H, W, seed=5)
+    act = {0: lambda t: t, 1: F.relu, 2: lambda t: F.leaky_relu(t, 0.2)}
+    dact = {0: lambda y: torch.ones_like(y), 1: lambda y: (y > 0).double(), 2: lambda y: torch.where(y > 0, 1.0, 0.2).double()}
+    xr, wr, br = x.clone().requires_grad_(True), w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    z = F.conv_transpose2d(xr, wr, br, padding=p) if tr else F.conv2d(xr, wr, br, padding=p)
+    yr = act[pre](z)
+    if add:
+        yr = yr + skip
+    yr = act[post](yr)
+    xc = nhwc(x.float()).to(DEV)
+    x1 = xc[..., :C1].contiguous().requires_grad_(True)
+    x2 = xc[..., C1:].contiguous().requires_grad_(True) if C2 else None
+    wc, bc = w.float().to(DEV).requires_grad_(True), b.float().to(DEV).requires_grad_(True)
+    sc = nhwc(skip.float()).to(DEV).requires_grad_(True) if add else None
+    cfg = ops.ConvCfg(cin=C, cout=N, kh=k, kw=k, stride=1, pad=p, transposed=tr, pre_act=pre, post_act=post)
+    ops.set_conv_mode("auto", passes)
+    try:
+        n0 = ops.tc_launches
+        y = ops.conv(x1, wc, bc, cfg, x2=x2, add1=sc)
+        y.backward(nhwc(gout.float()).to(DEV))
+        torch.cuda.synchronize()
+        assert ops.tc_launches - n0 == (3 if C2 else 2), "tcgen05 kernel was not selected"
+    finally:
+        ops.set_conv_mode("auto", 3)
+    assert rel_err(nchw(y), yr) <= tol
+    # backward reference through the CUDA forward's own activation pattern
+    yc = nchw(y).detach().double().cpu()
+    g1 = gout * dact[post](yc)
+    pre_out = yc if not add else act[pre](z.detach())           # pre_act is NONE whenever a skip is added here
+    dz = g1 * dact[pre](pre_out)
+    z.backward(dz)
+    dx = nchw(x1.grad) if not C2 else torch.cat([nchw(x1.grad), nchw(x2.grad)], 1)
+    assert rel_err(dx, xr.grad) <= tol
+    assert rel_err(wc.grad, wr.grad) <= 2e-5                    # wgrad runs on the exact kernel
+    assert rel_err(bc.grad, br.grad) <= 2e-5
+    if add:
+        assert rel_err(nchw(sc.grad), g1) <= 1e-6
+
+
 def test_conv_weight_grad_filter_and_frozen_weights():
     from mtdgan_b200 import ops
     x = nhwc(_rand(2, 8, 8, 8, seed=1).float()).to(DEV).requires_grad_(True)
@@ -193,6 +288,7 @@ def test_fft_block_vs_golden_and_oracle():
     assert rel_err(x.grad, fix["dx"]) <= 1e-4
     for k, p in blk.named_parameters():
         assert rel_err(p.grad, fix["grads"][k]) <= 1e-4, k
+    # B = 1 x 64 x 64 has 4096 pixels: the img_conv ran on the tcgen05 3xTF32 kernel (default mode)
 
 
 @pytest.mark.parametrize("H,W", [(64, 64), (128, 64), (64, 256), (512, 512)])
