@@ -148,18 +148,25 @@ def run_own(args):
     xh, yh = synthetic_pair(BATCH, PATCH, seed=1234, rank=rank, pin=True)
     xd, yd = xh.to(dev), yh.to(dev)
 
+    from mtdgan_b200.graphs import GraphedTrainStep
+    gparams = list(G.parameters())
+    runner = GraphedTrainStep(model, opt_D, opt_G, wm,
+                              post_g_backward=(lambda: mdist.allreduce_mean_grads(gparams)) if world > 1 else None)
+
+    def eager_step(x, y):
+        dl, _, gl, _ = runner.eager_step(x, y)
+        return dl, gl
+
+    use_graph = not args.no_graph and world == 1      # NCCL collectives are left out of graph capture for now
+    l0 = _ext.kernel_launch_count()
+    eager_step(xd, yd)
+    launches = _ext.kernel_launch_count() - l0          # kernels of this library per step (replays run the same ones)
+    if use_graph:
+        runner.capture(xd, yd, warmup=2)
+
     def step(x, y):
-        opt_D.zero_grad(); D.zero_grad()
-        d_losses, d_det = model.d_loss(x, y)
-        wm.backward(losses=d_losses, shared_parameters=shared, task_specific_parameters=ts, last_shared_parameters=last)
-        opt_D.step()
-        opt_G.zero_grad(); G.zero_grad()
-        g_loss, g_det = model.g_loss(x, y)
-        g_loss.backward()
-        if world > 1:
-            mdist.allreduce_mean_grads(list(G.parameters()))
-        opt_G.step()
-        return d_losses, g_loss
+        dl, _, gl, _ = runner(x, y)
+        return dl, gl
 
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)      # > 126 MB L2
 
@@ -191,9 +198,7 @@ def run_own(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    l0 = _ext.kernel_launch_count()
     ms = timed(args.steps, e2e=False)
-    launches = (_ext.kernel_launch_count() - l0) // args.steps
     barrier()
     ms_e2e = timed(args.steps, e2e=True)
     barrier()
@@ -209,7 +214,7 @@ def run_own(args):
     if rank == 0:
         torch.cuda.synchronize()
         _ext.start_profile()
-        step(xd, yd)
+        eager_step(xd, yd)
         rec = _ext.stop_profile()
         total_ms = sum(r[2] for r in rec)
         if os.environ.get("MTD_BENCH_DUMP"):       # per-call records (entry point, integer args, ms) for offline analysis
@@ -283,7 +288,9 @@ def run_own(args):
         "config": {"workload": "MTD_GAN_Method full train step (G + MTL-D + RC/NDS + PCGrad + AdamW), 20 synthetic 1x64x64 patches/GPU "
                                "(BASELINE configs[2]/[3])", "global_batch": patches, "patch": PATCH,
                    "parallelism": f"dp{world}", "l2": "256 MiB buffer written between timed steps (L2 flush)",
-                   "weights": "random init, seed 2024", "optimizer": "fused AdamW lr 1e-4 wd 5e-4"},
+                   "weights": "random init, seed 2024", "optimizer": "fused AdamW lr 1e-4 wd 5e-4",
+                   "execution": "whole step replayed as one CUDA graph" if use_graph else "eager launches",
+                   "conv_precision": "tcgen05 3xTF32 (fp32-grade) + exact fp32 SIMT for thin/strided layers"},
         "e2e": {"value": round(patches * args.steps / (t_e2e * 1e-3), 3), "unit": "patches/s",
                 "h2d_bytes_per_step": 2 * BATCH * PATCH * PATCH * 4, "d2h_bytes_per_step": 16},
         "gpu_launches": int(launches) * args.steps, "gpu_launches_per_step": int(launches),
@@ -374,6 +381,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of the captured CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":
         line = run_reference(args)

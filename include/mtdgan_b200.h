@@ -85,6 +85,12 @@ int mtd_conv_fwd_tc(const float* x1, const float* x2, const float* wp, const flo
 int mtd_conv_dgrad_tc(const float* dz, const float* wpd, float* dx, const float* scale, const float* add1, const float* add2,
                       const float* mask_src, int mask_act, float slope, int B, int H, int W, int Cin, int Cout, int kh, int kw,
                       int stride, int pad, int passes, int cin_total, void* stream);
+/* weight gradient on the tensor cores (stride-1 same convs, C % 32 == 0, N % 32 == 0): both operands are
+ * MN-major TMA boxes, split-K over pixels, fp32 atomics into gp (zeroed here).  Same gp layout as
+ * mtd_conv_wgrad.                                                                                    */
+int mtd_conv_wgrad_tc_supported(int B, int H, int W, int C1, int C2, int N, int kh, int kw, int stride, int pad);
+int mtd_conv_wgrad_tc(const float* x1, const float* x2, const float* dz, float* gp, int B, int H, int W, int C1, int C2, int N,
+                      int kh, int kw, int stride, int pad, int passes, void* stream);
 /* in place hi <- rna_tf32(w), lo <- rna_tf32(w - hi): operand split for the 3xTF32 mode               */
 int mtd_split_tf32(float* hi, float* lo, long long n, void* stream);
 
@@ -148,10 +154,11 @@ int mtd_pcgrad_project(const void* seg_tab, const void* chunk_tab, int n_chunks,
                        double* gram_ws, float* coef_out, float* cmat_out, double* gram_out, void* stream);
 
 /* ---- AdamW (adamw.cu) — "next" row: torch.optim.AdamW step of optimizers.py:9 / engine.py:44,52 ------
- * seg table int64[nseg][8]: { param, grad, exp_avg, exp_avg_sq, numel, bits(1-b1^t), bits(1-b2^t), 0 };
+ * seg table int64[nseg][8]: { param, grad, exp_avg, exp_avg_sq, numel, step counter (device float*), 0, 0 };
+ * the step counters are incremented on the device, bias corrections derived in-kernel (graph-capturable).
  * chunk table as PCGrad.                                                                             */
-int mtd_adamw_step(const void* seg_tab, const void* chunk_tab, int n_chunks, float lr, float beta1, float beta2,
-                   float eps, float weight_decay, void* stream);
+int mtd_adamw_step(const void* seg_tab, int n_segs, const void* chunk_tab, int n_chunks, float lr, float beta1,
+                   float beta2, float eps, float weight_decay, void* stream);
 
 #ifdef __cplusplus
 }

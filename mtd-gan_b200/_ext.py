@@ -145,3 +145,18 @@ def fptr(t):
 
 def stream():
     return torch.cuda.current_stream().cuda_stream
+
+
+_capture_keepalive = []       # pinned staging buffers referenced by memcpy nodes of captured CUDA graphs
+
+
+def device_table(rows, dtype, device):
+    """Small host-built table -> device through PINNED staging (a pageable H2D copy is illegal during CUDA-graph
+    capture).  While capturing, the staging buffer is kept alive for the life of the process: the graph's memcpy
+    node re-reads it on every replay."""
+    host = torch.tensor(rows, dtype=dtype).pin_memory()
+    dev = torch.empty(host.shape, dtype=dtype, device=device)
+    dev.copy_(host, non_blocking=True)
+    if torch.cuda.is_current_stream_capturing():
+        _capture_keepalive.append(host)
+    return dev

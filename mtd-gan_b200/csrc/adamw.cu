@@ -16,17 +16,23 @@ struct Seg {
   float* m;
   float* v;
   long long numel;
-  long long bc1_bits, bc2_bits;   // float bits of the per-parameter bias corrections 1-b1^t, 1-b2^t
-  long long pad;
+  float* step;                    // device step counter of this parameter (incremented by adamw_inc_kernel)
+  long long pad0, pad1;
 };
 static_assert(sizeof(Seg) == 64, "segment entry must be 8 x int64");
+
+__global__ void adamw_inc_kernel(const Seg* __restrict__ segs, int nseg) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < nseg) *segs[i].step += 1.f;
+}
 
 __global__ void __launch_bounds__(256) adamw_kernel(const Seg* __restrict__ segs, const int2* __restrict__ chunks, float lr,
                                                     float b1, float b2, float eps, float wd) {
   const int2 ck = chunks[blockIdx.x];
   const Seg s = segs[ck.x];
   const long long end = min(s.numel, (long long)ck.y + kChunk);
-  const float bc1 = __int_as_float((int)s.bc1_bits), bc2 = __int_as_float((int)s.bc2_bits);
+  const float t = __ldg(s.step);
+  const float bc1 = 1.f - powf(b1, t), bc2 = 1.f - powf(b2, t);
   const float step = lr / bc1, inv_sq_bc2 = rsqrtf(bc2), decay = 1.f - lr * wd;
   for (long long i = ck.y + threadIdx.x; i < end; i += blockDim.x) {
     float g = __ldg(s.g + i);
@@ -40,9 +46,11 @@ __global__ void __launch_bounds__(256) adamw_kernel(const Seg* __restrict__ segs
 }
 }  // namespace
 
-extern "C" int mtd_adamw_step(const void* seg_tab, const void* chunk_tab, int n_chunks, float lr, float beta1, float beta2,
-                              float eps, float weight_decay, void* stream) {
-  MTD_REQUIRE(seg_tab && chunk_tab && n_chunks > 0);
+extern "C" int mtd_adamw_step(const void* seg_tab, int n_segs, const void* chunk_tab, int n_chunks, float lr, float beta1,
+                              float beta2, float eps, float weight_decay, void* stream) {
+  MTD_REQUIRE(seg_tab && chunk_tab && n_chunks > 0 && n_segs > 0);
+  adamw_inc_kernel<<<(n_segs + 127) / 128, 128, 0, (cudaStream_t)stream>>>(reinterpret_cast<const Seg*>(seg_tab), n_segs);
+  MTD_CHECK_LAUNCH();
   adamw_kernel<<<n_chunks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const Seg*>(seg_tab),
                                                            reinterpret_cast<const int2*>(chunk_tab), lr, beta1, beta2, eps,
                                                            weight_decay);

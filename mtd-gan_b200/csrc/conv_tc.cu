@@ -191,7 +191,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
     for (int s = 0; s < S; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
-      mbar_init(conv_bar(s), 128);
+      mbar_init(conv_bar(s), 4);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(tfull_bar(i), 1);
@@ -307,7 +307,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
           }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> tensor-core (async proxy) reads
-        mbar_arrive(conv_bar(st.stage));
+        __syncwarp();
+        if (lane == 0) mbar_arrive(conv_bar(st.stage));                // one arrival per rounding warp (count 4)
         st.advance(S);
       }
     }
@@ -418,12 +419,14 @@ EncodeTiledFn get_encode() {
 std::mutex g_map_mutex;
 std::unordered_map<std::string, CUtensorMap> g_map_cache;
 
-// activations: rank-4 (C, W, H, B) fp32, box (32, TW, TH, TB), SWIZZLE_128B, OOB -> zeros
-int make_act_map(CUtensorMap* out, const float* ptr, int C, int W, int H, int B, int TW, int TH, int TB) {
+// activations: rank-4 (C, W, H, B) fp32, box (32, TW, TH, TB), OOB -> zeros.  atom32 = false: SWIZZLE_128B
+// (K-major operands of the forward / dgrad kernels); atom32 = true: SWIZZLE_128B_ATOM_32B (MN-major tf32
+// operands of the wgrad kernel)
+int make_act_map(CUtensorMap* out, const float* ptr, int C, int W, int H, int B, int TW, int TH, int TB, bool atom32 = false) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return MTD_EINVAL;
   char keybuf[128];
-  snprintf(keybuf, sizeof(keybuf), "A%p:%d:%d:%d:%d:%d:%d:%d", (const void*)ptr, C, W, H, B, TW, TH, TB);
+  snprintf(keybuf, sizeof(keybuf), "A%d%p:%d:%d:%d:%d:%d:%d:%d", (int)atom32, (const void*)ptr, C, W, H, B, TW, TH, TB);
   std::string key(keybuf);
   {
     std::lock_guard<std::mutex> lk(g_map_mutex);
@@ -435,7 +438,8 @@ int make_act_map(CUtensorMap* out, const float* ptr, int C, int W, int H, int B,
   cuuint32_t box[4] = {32, (cuuint32_t)TW, (cuuint32_t)TH, (cuuint32_t)TB};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return MTD_EINVAL;
   std::lock_guard<std::mutex> lk(g_map_mutex);
   if (g_map_cache.size() > 8192) g_map_cache.clear();
@@ -580,6 +584,284 @@ __global__ void split_tf32_kernel(float* __restrict__ hi, float* __restrict__ lo
   }
 }
 
+
+// =====================================================================================================
+// Weight gradient on the tensor cores.
+//
+//   gp[n][t][c] = sum_p dz[p][n] * x[p@t][c]          (p = output pixel, x[p@t] = input pixel of tap t)
+//
+// GEMM with K = pixels.  Both operands have the reduction (pixel) dimension as their SLOW memory dimension
+// (NHWC), i.e. they are MN-major: a TMA box (32 channels, Kp pixels) lands as Kp rows of 128 B, which (with the
+// 128B_ATOM_32B swizzle) is the canonical MN-major SW128_32B atom stack (4 pixel rows = one 512 B k-atom;
+// 32 channels = one mn-block).
+//   A (M side, 128 rows) = 4 mn-blocks: "units" u = t*kchunks + cc (tap t, 32-channel chunk cc) 4j..4j+3,
+//                          each the tap-shifted box of x — for C = 32 layers one MMA covers 4 taps at once
+//   B (N side, BN cols)  = BN/32 mn-blocks of the dz box (unshifted)
+// so D[row = (unit, ch)][col = n] accumulates in TMEM over the CTA's share of the pixel tiles (split-K over
+// pixels), and the epilogue atomically adds the fp32 partials into the packed gradient.  Both operands are
+// activations, so the rounding warps split BOTH into tf32 hi/lo for the 3xTF32 mode.
+// =====================================================================================================
+constexpr int kKp = 32;                         // pixels per k-step
+constexpr int kBlkBytes = kKp * 128;            // one (32 ch x 32 px) block = 4 KB
+
+struct WgArgs {
+  int B, H, W, C1, C2, N, T;
+  int dy[kMaxTaps], dx[kMaxTaps];
+  int TW, TH, TB, n_wt, n_ht, n_bt;            // pixel-tile geometry (TW*TH*TB == kKp)
+  int kc1, kc2, units, m_tiles, n_nt;
+  int ksplit, kper, ptiles, n_tiles, stages;
+  float* gp;
+};
+
+__host__ __device__ constexpr uint32_t make_idesc_mn(int bn) {      // both operands MN-major
+  return (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(bn >> 3) << 17) |
+         ((uint32_t)(kBM >> 4) << 24);
+}
+// MN-major descriptor.  For 32-bit (tf32) MN-major operands the ONLY layout the tensor core accepts is
+// SWIZZLE_128B_BASE32B (layout type 1; cutlass sm100_common.inl: "for mn-major tf32 operands, SW128_32B is the
+// only available smem layout"): Swizzle<2,5,2>, atom = 32 channels (128 B) x 4 pixel rows, produced by TMA's
+// CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B.  LBO = byte stride between 32-channel mn-blocks, SBO = 512 B between
+// 4-pixel k-atoms (one K = 8 MMA spans two of them).
+__device__ __forceinline__ uint64_t make_sw128_desc_mn(uint32_t smem_addr, uint32_t lbo_bytes) {
+  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | (32ull << 32) | (1ull << 46) | (1ull << 61);
+}
+
+template <int BN, int NPASS>
+__global__ void __launch_bounds__(kThreads, 1)
+wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapX1, const __grid_constant__ CUtensorMap mapX2,
+                const __grid_constant__ CUtensorMap mapDz, const __grid_constant__ WgArgs a) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  constexpr int kNB = BN / 32;                                  // dz blocks
+  constexpr int kBlocks = 4 + kNB;                              // fp32 blocks landed by TMA per stage
+  constexpr int kHalf = kBlocks * kBlkBytes;                    // hi tiles (in place); lo tiles follow
+  constexpr int kStageBytes = (NPASS == 3 ? 2 : 1) * kHalf;
+  constexpr uint32_t kTmemCols = (2 * BN) < 32 ? 32 : 2 * BN;
+
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int S = a.stages;
+  const uint32_t bar_base = base + (uint32_t)S * kStageBytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (S + s); };
+  auto conv_bar = [&](int s) { return bar_base + 8u * (2 * S + s); };
+  auto tfull_bar = [&](int i) { return bar_base + 8u * (3 * S + i); };
+  auto tempty_bar = [&](int i) { return bar_base + 8u * (3 * S + 2 + i); };
+  const uint32_t tmem_slot = bar_base + 8u * (3 * S + 4);
+  unsigned char* gen_base = smem_raw + (base - smem_u32(smem_raw));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kchunks = a.kc1 + a.kc2;
+  const int Ctot = kchunks * 32;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&mapX1);
+    if (a.kc2) prefetch_tmap(&mapX2);
+    prefetch_tmap(&mapDz);
+    for (int s = 0; s < S; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+      mbar_init(conv_bar(s), 4);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(tfull_bar(i), 1);
+      mbar_init(tempty_bar(i), 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(kTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gen_base + (tmem_slot - base));
+
+  // tile = ((mt * n_nt) + nt) * ksplit + ks
+  auto decode_tile = [&](int tile, int& mt, int& n0, int& k_begin, int& k_end) {
+    const int ks = tile % a.ksplit;
+    tile /= a.ksplit;
+    k_begin = ks * a.kper;
+    k_end = min(a.ptiles, k_begin + a.kper);
+    n0 = (tile % a.n_nt) * BN;
+    mt = tile / a.n_nt;
+  };
+  auto decode_ptile = [&](int pt, int& b0, int& h0, int& w0) {
+    int mw = pt % a.n_wt;
+    pt /= a.n_wt;
+    int mh = pt % a.n_ht, mb = pt / a.n_ht;
+    b0 = mb * a.TB; h0 = mh * a.TH; w0 = mw * a.TW;
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      PipeState st;
+      for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+        int mt, n0, k_begin, k_end;
+        decode_tile(tile, mt, n0, k_begin, k_end);
+        int nvalid = min(4, a.units - mt * 4);
+        for (int it = k_begin; it < k_end; ++it) {
+          int b0, h0, w0;
+          decode_ptile(it, b0, h0, w0);
+          mbar_wait(empty_bar(st.stage), st.phase ^ 1u);
+          mbar_expect_tx(full_bar(st.stage), (uint32_t)(nvalid + kNB) * kBlkBytes);
+          const uint32_t sa = base + (uint32_t)st.stage * kStageBytes;
+          for (int i = 0; i < nvalid; ++i) {
+            const int u = mt * 4 + i, t = u / kchunks, cc = u - t * kchunks;
+            if (cc < a.kc1) tma_load_4d(&mapX1, sa + i * kBlkBytes, full_bar(st.stage), cc * 32, w0 + a.dx[t], h0 + a.dy[t], b0);
+            else tma_load_4d(&mapX2, sa + i * kBlkBytes, full_bar(st.stage), (cc - a.kc1) * 32, w0 + a.dx[t], h0 + a.dy[t], b0);
+          }
+#pragma unroll
+          for (int j = 0; j < kNB; ++j)
+            tma_load_4d(&mapDz, sa + (4 + j) * kBlkBytes, full_bar(st.stage), n0 + j * 32, w0, h0, b0);
+          st.advance(S);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      PipeState st;
+      constexpr uint32_t idesc = make_idesc_mn(BN);
+      int lt = 0;
+      for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++lt) {
+        int mt, n0, k_begin, k_end;
+        decode_tile(tile, mt, n0, k_begin, k_end);
+        const int acc = lt & 1;
+        const uint32_t acc_phase = (uint32_t)(lt >> 1) & 1u;
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+        for (int it = k_begin; it < k_end; ++it) {
+          mbar_wait(conv_bar(st.stage), st.phase);
+          tc_fence_after();
+          const uint32_t sa = base + (uint32_t)st.stage * kStageBytes;
+          const uint64_t da = make_sw128_desc_mn(sa, kBlkBytes), db = make_sw128_desc_mn(sa + 4 * kBlkBytes, kBlkBytes);
+#pragma unroll
+          for (int kk = 0; kk < kKp / 8; ++kk) {       // one 8-pixel k-atom (1024 B) per MMA: +64 in 16-byte units
+            const uint32_t accum = (it > k_begin || kk > 0) ? 1u : 0u;
+            if (NPASS == 3) {
+              const uint64_t dal = make_sw128_desc_mn(sa + kHalf, kBlkBytes), dbl = make_sw128_desc_mn(sa + kHalf + 4 * kBlkBytes, kBlkBytes);
+              umma_tf32(tmem_d, dal + 64u * kk, db + 64u * kk, idesc, accum);
+              umma_tf32(tmem_d, da + 64u * kk, dbl + 64u * kk, idesc, 1u);
+              umma_tf32(tmem_d, da + 64u * kk, db + 64u * kk, idesc, 1u);
+            } else {
+              umma_tf32(tmem_d, da + 64u * kk, db + 64u * kk, idesc, accum);
+            }
+          }
+          umma_commit(empty_bar(st.stage));
+          st.advance(S);
+        }
+        umma_commit(tfull_bar(acc));
+      }
+    }
+  } else if (warp < 6) {
+    const int ct = threadIdx.x - 64;
+    PipeState st;
+    for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+      int mt, n0, k_begin, k_end;
+      decode_tile(tile, mt, n0, k_begin, k_end);
+      for (int it = k_begin; it < k_end; ++it) {
+        mbar_wait(full_bar(st.stage), st.phase);
+        float4* tileA = reinterpret_cast<float4*>(gen_base + (size_t)st.stage * kStageBytes);
+#pragma unroll 4
+        for (int j = 0; j < kHalf / 16 / 128; ++j) {
+          float4 v = tileA[ct + 128 * j];
+          uint32_t r0, r1, r2, r3;
+          asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r0) : "f"(v.x));
+          asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r1) : "f"(v.y));
+          asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r2) : "f"(v.z));
+          asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r3) : "f"(v.w));
+          const float4 hi = make_float4(__uint_as_float(r0), __uint_as_float(r1), __uint_as_float(r2), __uint_as_float(r3));
+          tileA[ct + 128 * j] = hi;
+          if (NPASS == 3) {
+            uint32_t l0, l1, l2, l3;
+            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l0) : "f"(v.x - hi.x));
+            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l1) : "f"(v.y - hi.y));
+            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l2) : "f"(v.z - hi.z));
+            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l3) : "f"(v.w - hi.w));
+            tileA[kHalf / 16 + ct + 128 * j] =
+                make_float4(__uint_as_float(l0), __uint_as_float(l1), __uint_as_float(l2), __uint_as_float(l3));
+          }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(conv_bar(st.stage));
+        st.advance(S);
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    int lt = 0;
+    for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++lt) {
+      int mt, n0, k_begin, k_end;
+      decode_tile(tile, mt, n0, k_begin, k_end);
+      const int acc = lt & 1;
+      const uint32_t acc_phase = (uint32_t)(lt >> 1) & 1u;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const int u = mt * 4 + (r >> 5);
+      const bool valid = u < a.units;
+      const int t = valid ? u / kchunks : 0, cc = valid ? u - t * kchunks : 0;
+      const int c = cc * 32 + (r & 31);
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0), v);
+        if (valid) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float* dst = a.gp + ((size_t)(n0 + c0 + j) * a.T + t) * Ctot + c;
+            if (a.ksplit > 1) atomicAdd(dst, __uint_as_float(v[j]));
+            else *dst = __uint_as_float(v[j]);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+  }
+}
+
+template <int BN, int NPASS>
+int launch_wg(const CUtensorMap& mX1, const CUtensorMap& mX2, const CUtensorMap& mDz, WgArgs& a, cudaStream_t st) {
+  const int stage_bytes = (NPASS == 3 ? 2 : 1) * (4 + BN / 32) * kBlkBytes;
+  int stages = (200 * 1024) / stage_bytes;
+  if (stages > 8) stages = 8;
+  if (stages > a.kper) stages = a.kper < 2 ? 2 : a.kper;
+  a.stages = stages;
+  size_t smem = 1024 + (size_t)stages * stage_bytes + 8 * (3 * stages + 4) + 16;
+  static bool attr_set = false;
+  if (!attr_set) {
+    MTD_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<BN, NPASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  int grid = a.n_tiles < mtd_sm_count() ? a.n_tiles : mtd_sm_count();
+  wgrad_tc_kernel<BN, NPASS><<<grid, kThreads, smem, st>>>(mX1, mX2, mDz, a);
+  MTD_CHECK_LAUNCH();
+  return MTD_OK;
+}
+
+bool wg_geometry(int B, int H, int W, int C1, int C2, int N, int kh, int kw, int stride, int pad, int* TW, int* TH, int* TB) {
+  if (stride != 1 || kh != kw || 2 * pad != kh - 1 || kh * kw > kMaxTaps) return false;
+  if (C1 <= 0 || C1 % 32 || C2 < 0 || C2 % 32 || N <= 0 || N % 32) return false;
+  if (!is_pow2(W) || !is_pow2(H)) return false;
+  int tw = W < kKp ? W : kKp;
+  int th = kKp / tw;
+  if (th > H) th = H;
+  int tb = kKp / (tw * th);
+  if (tw * th * tb != kKp) return false;
+  *TW = tw; *TH = th; *TB = tb;
+  return true;
+}
+
 __global__ void round_tf32_kernel(float* __restrict__ p, size_t n) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
   for (; i < n; i += stride) {
@@ -708,6 +990,60 @@ int mtd_conv_dgrad_tc(const float* dz, const float* wpd, float* dx, const float*
   }
   // ksplit == 1: the per-class epilogues already applied scale / adds / mask (each output pixel belongs to one class)
   return MTD_OK;
+}
+
+int mtd_conv_wgrad_tc_supported(int B, int H, int W, int C1, int C2, int N, int kh, int kw, int stride, int pad) {
+  int tw, th, tb;
+  return wg_geometry(B, H, W, C1, C2, N, kh, kw, stride, pad, &tw, &th, &tb) && get_encode() != nullptr ? 1 : 0;
+}
+
+// gp[N][kh*kw][C1+C2] = sum over pixels of dz (x) x on the tensor cores (stride-1 "same" convs).
+int mtd_conv_wgrad_tc(const float* x1, const float* x2, const float* dz, float* gp, int B, int H, int W, int C1, int C2, int N,
+                      int kh, int kw, int stride, int pad, int passes, void* stream) {
+  MTD_REQUIRE(x1 && dz && gp && ((C2 == 0) == (x2 == nullptr)) && (passes == 1 || passes == 3));
+  cudaStream_t st = (cudaStream_t)stream;
+  WgArgs a{};
+  if (!wg_geometry(B, H, W, C1, C2, N, kh, kw, stride, pad, &a.TW, &a.TH, &a.TB)) return MTD_EINVAL;
+  if (!mtd_aligned16(x1) || !mtd_aligned16(dz) || (x2 && !mtd_aligned16(x2))) return MTD_EALIGN;
+  a.B = B; a.H = H; a.W = W; a.C1 = C1; a.C2 = C2; a.N = N; a.T = kh * kw;
+  for (int ky = 0; ky < kh; ++ky)
+    for (int kx = 0; kx < kw; ++kx) { a.dy[ky * kw + kx] = ky - pad; a.dx[ky * kw + kx] = kx - pad; }
+  a.n_wt = W / a.TW; a.n_ht = H / a.TH; a.n_bt = (B + a.TB - 1) / a.TB;
+  a.ptiles = a.n_wt * a.n_ht * a.n_bt;
+  a.kc1 = C1 / 32; a.kc2 = C2 / 32;
+  a.units = a.T * (a.kc1 + a.kc2);
+  a.m_tiles = (a.units + 3) / 4;
+  const int sms = mtd_sm_count();
+  int BN = N >= 128 ? 128 : (N >= 64 ? 64 : 32);
+  while (BN > 32 && a.m_tiles * (N / BN) < sms) BN >>= 1;
+  if (N % BN) return MTD_EINVAL;
+  a.n_nt = N / BN;
+  const int mn = a.m_tiles * a.n_nt;
+  int ksplit = 1;
+  if (mn < 2 * sms) {
+    ksplit = (2 * sms + mn - 1) / mn;
+    if (ksplit > a.ptiles / 4) ksplit = a.ptiles / 4;
+    if (ksplit < 1) ksplit = 1;
+  }
+  a.kper = (a.ptiles + ksplit - 1) / ksplit;
+  ksplit = (a.ptiles + a.kper - 1) / a.kper;
+  a.ksplit = ksplit;
+  a.n_tiles = mn * ksplit;
+  a.gp = gp;
+  if (ksplit > 1) MTD_CUDA(cudaMemsetAsync(gp, 0, (size_t)N * a.T * (C1 + C2) * sizeof(float), st));
+  CUtensorMap mX1, mX2, mDz;
+  int rc = make_act_map(&mX1, x1, C1, W, H, B, a.TW, a.TH, a.TB, true);
+  if (rc) return rc;
+  if (C2) { rc = make_act_map(&mX2, x2, C2, W, H, B, a.TW, a.TH, a.TB, true); if (rc) return rc; }
+  else mX2 = mX1;
+  rc = make_act_map(&mDz, dz, N, W, H, B, a.TW, a.TH, a.TB, true);
+  if (rc) return rc;
+#define WG_DISPATCH(BN_) rc = passes == 3 ? launch_wg<BN_, 3>(mX1, mX2, mDz, a, st) : launch_wg<BN_, 1>(mX1, mX2, mDz, a, st)
+  if (BN == 128) { WG_DISPATCH(128); }
+  else if (BN == 64) { WG_DISPATCH(64); }
+  else { WG_DISPATCH(32); }
+#undef WG_DISPATCH
+  return rc;
 }
 
 }  // extern "C"

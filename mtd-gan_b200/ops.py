@@ -30,6 +30,12 @@ def _empty(shape, like):
 _pack_cache: dict = {}        # id(weight object) -> {(kind, transposed, stride): (tag, packed)}
 
 
+def clear_pack_cache():
+    """Drop every packed copy (used before CUDA-graph capture so the packing kernels are captured too)."""
+    for slot in _pack_cache.values():
+        slot.clear()
+
+
 def _cache_slot(weight) -> dict:
     k = id(weight)
     slot = _pack_cache.get(k)
@@ -153,6 +159,20 @@ def _conv_forward_launch(x1, x2, weight, bias, scale, y, aux, add1, add2, cfg: C
         call("mtd_conv_fwd", *args, stream())
 
 
+def _conv_wgrad_launch(x1, x2, dz, gp, B, H, W, C1, C2, cfg: ConvCfg):
+    """gp[N][T][C1+C2] (packed, forward orientation) = sum over pixels of dz (x) x."""
+    st = stream()
+    if _USE_TC != "simt" and _ext.load().mtd_conv_wgrad_tc_supported(B, H, W, C1, C2, cfg.cout, cfg.kh, cfg.kw, cfg.stride,
+                                                                      cfg.pad) == 1:
+        global tc_launches
+        tc_launches += 1
+        call("mtd_conv_wgrad_tc", fptr(x1), fptr(x2), fptr(dz), fptr(gp), B, H, W, C1, C2, cfg.cout, cfg.kh, cfg.kw, cfg.stride,
+             cfg.pad, _TC_PASSES, st)
+    else:
+        call("mtd_conv_wgrad", fptr(x1), fptr(x2), fptr(dz), fptr(gp), B, H, W, C1, C2, cfg.cout, cfg.kh, cfg.kw, cfg.stride,
+             cfg.pad, st)
+
+
 def _conv_dgrad_launch(dz, weight, dx, scale, add1, B, H, W, cin_sub, cin_off, cfg: ConvCfg):
     """dx (B,H,W,cin_sub) = scale * dgrad(dz) (+ add1) for input channels [cin_off, cin_off + cin_sub)."""
     T = cfg.kh * cfg.kw
@@ -241,8 +261,7 @@ class ConvFn(Function):
         dw = None
         if need[2] and _wgrad_wanted(weight):
             gp = _empty((weight.numel(),), dy)
-            call("mtd_conv_wgrad", fptr(x1), fptr(x2), fptr(dz), fptr(gp), B, H, W, C1, C2, cfg.cout, cfg.kh, cfg.kw,
-                 cfg.stride, cfg.pad, st)
+            _conv_wgrad_launch(x1, x2, dz, gp, B, H, W, C1, C2, cfg)
             dw = torch.empty_like(weight)
             scratch = torch.empty(4, dtype=torch.float32, device=dy.device) if inv_sigma is not None else None
             call("mtd_conv_wgrad_finish", fptr(gp), fptr(dw), cfg.transposed, cfg.cout, cfg.cin, cfg.kh, cfg.kw,
@@ -323,7 +342,7 @@ class FFTConvBlockFn(Function):
         diw = None
         if need[1] and _wgrad_wanted(img_w):
             gp = _empty((img_w.numel(),), x)
-            call("mtd_conv_wgrad", fptr(x), None, fptr(dz), fptr(gp), B, H, W, C, 0, C, 3, 3, 1, 1, st)
+            _conv_wgrad_launch(x, None, dz, gp, B, H, W, C, 0, cfg)
             diw = torch.empty_like(img_w)
             call("mtd_conv_wgrad_finish", fptr(gp), fptr(diw), 0, C, C, 3, 3, None, None, None, None, None, st)
         return dx, diw, dib, dfw, dfb

@@ -7,8 +7,9 @@ from __future__ import annotations
 
 import torch
 
+from . import _ext
 from ._ext import call, ptr, stream
-from .weight_methods import _chunk_table, _float_bits
+from .weight_methods import _chunk_table
 
 
 class FusedAdamW(torch.optim.Optimizer):
@@ -33,24 +34,26 @@ class FusedAdamW(torch.optim.Optimizer):
                     raise RuntimeError("FusedAdamW handles fp32 CUDA parameters only (no CPU fallback)")
                 st = self.state[p]
                 if len(st) == 0:
-                    st["step"] = torch.tensor(0.0, dtype=torch.float32)
+                    # the step counter lives on the device (like torch's capturable AdamW): the kernel increments it
+                    # and derives the bias corrections, so a captured CUDA graph needs no host-side update
+                    st["step"] = torch.zeros((), dtype=torch.float32, device=p.device)
                     st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
                     st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
-                st["step"] += 1
-                t = float(st["step"])
+                elif not st["step"].is_cuda:           # state loaded from a torch.optim.AdamW checkpoint
+                    st["step"] = st["step"].to(device=p.device, dtype=torch.float32)
                 g = p.grad.contiguous()
                 keep.append(g)
                 rows.append([p.data_ptr(), g.data_ptr(), st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr(), p.numel(),
-                             _float_bits(1.0 - b1 ** t), _float_bits(1.0 - b2 ** t), 0])
+                             st["step"].data_ptr(), 0, 0])
                 numels.append(p.numel())
                 device = p.device
             if not rows:
                 continue
-            seg = torch.tensor(rows, dtype=torch.int64).to(device, non_blocking=True)
+            seg = _ext.device_table(rows, torch.int64, device)
             chunks, n_chunks = _chunk_table(numels, device)
             lr = group["lr"]
-            call("mtd_adamw_step", ptr(seg), ptr(chunks), n_chunks, float(lr), float(b1), float(b2), float(group["eps"]),
-                 float(group["weight_decay"]), stream())
+            call("mtd_adamw_step", ptr(seg), len(rows), ptr(chunks), n_chunks, float(lr), float(b1), float(b2),
+                 float(group["eps"]), float(group["weight_decay"]), stream())
             for p in group["params"]:
                 if p.grad is not None:
                     torch.autograd.graph.increment_version(p)      # the kernel wrote p in place (pack caches key on it)

@@ -42,7 +42,7 @@ def _chunk_table(numels: Sequence[int], device) -> Tuple[torch.Tensor, int]:
     if ent is None:
         ck = _ext.load().mtd_pcgrad_chunk_elems()
         rows = [[s, off] for s, n in enumerate(numels) for off in range(0, n, ck)]
-        ent = (torch.tensor(rows, dtype=torch.int32).to(device), len(rows))
+        ent = (_ext.device_table(rows, torch.int32, device), len(rows))
         _chunk_cache[key] = ent
     return ent
 
@@ -51,7 +51,7 @@ def _float_bits(x: float) -> int:
     return int(torch.tensor(x, dtype=torch.float32).view(torch.int32).item())
 
 
-def pcgrad_merge(task_grads: Sequence[Sequence[Optional[torch.Tensor]]], orders: Sequence[Sequence[int]], mean: bool,
+def pcgrad_merge(task_grads: Sequence[Sequence[Optional[torch.Tensor]]], orders, mean: bool,
                  seg_scales: Optional[Sequence[float]] = None, return_debug: bool = False):
     """merged_p = scale_p * sum_k coef_k * g_k[p] for every parameter p.
 
@@ -86,9 +86,11 @@ def pcgrad_merge(task_grads: Sequence[Sequence[Optional[torch.Tensor]]], orders:
         row += [flat.data_ptr() + 4 * off, numels[p], _float_bits(scale), 0]
         rows.append(row)
         off += numels[p]
-    seg = torch.tensor(rows, dtype=torch.int64).to(device, non_blocking=True)
+    seg = _ext.device_table(rows, torch.int64, device)
     chunks, n_chunks = _chunk_table(numels, device)
-    ords = torch.tensor(orders, dtype=torch.int32).to(device, non_blocking=True)
+    # `orders` is either a host list (copied through pinned staging) or an int32 device tensor [T*T] the caller
+    # keeps refreshed (CUDA-graph replays)
+    ords = orders if isinstance(orders, torch.Tensor) else _ext.device_table(orders, torch.int32, device)
     gram_ws = torch.empty(16, dtype=torch.float64, device=device)
     coef = torch.empty(4, dtype=torch.float32, device=device)
     cmat = torch.empty(T * T, dtype=torch.float32, device=device) if return_debug else None
@@ -108,7 +110,7 @@ def _cuda_gram(shards):
     """<shard_a, shard_b> for a <= b on the device (fp64), for distributed.pcgrad_sharded."""
     T, dev = len(shards), shards[0].device
     row = [fptr(s) for s in shards] + [0] * (4 - T) + [0, shards[0].numel(), _float_bits(1.0), 0]
-    seg = torch.tensor([row], dtype=torch.int64).to(dev, non_blocking=True)
+    seg = _ext.device_table([row], torch.int64, dev)
     chunks, n_chunks = _chunk_table([shards[0].numel()], dev)
     gram = torch.empty(16, dtype=torch.float64, device=dev)
     call("mtd_pcgrad_gram", ptr(seg), ptr(chunks), n_chunks, T, ptr(gram), stream())
@@ -119,9 +121,9 @@ def _cuda_solve_combine(shards, gram, orders, mean, scale):
     T, dev = len(shards), shards[0].device
     out = torch.empty_like(shards[0])
     row = [fptr(s) for s in shards] + [0] * (4 - T) + [fptr(out), out.numel(), _float_bits(scale), 0]
-    seg = torch.tensor([row], dtype=torch.int64).to(dev, non_blocking=True)
+    seg = _ext.device_table([row], torch.int64, dev)
     chunks, n_chunks = _chunk_table([out.numel()], dev)
-    ords = torch.tensor(orders, dtype=torch.int32).to(dev, non_blocking=True)
+    ords = orders if isinstance(orders, torch.Tensor) else _ext.device_table(orders, torch.int32, dev)
     coef = torch.empty(4, dtype=torch.float32, device=dev)
     call("mtd_pcgrad_solve_combine", ptr(seg), ptr(chunks), n_chunks, T, ptr(ords), 1 if mean else 0, ptr(gram), fptr(coef),
          None, None, stream())
@@ -186,8 +188,26 @@ class PCGrad(WeightMethod):
             for p, g in zip(task_specific_parameters, ts_grads):
                 p.grad = g
 
+    def refresh_orders(self, device):
+        """Draw this step's task visit orders from Python's `random` (exactly like the reference) into a persistent
+        pinned buffer and enqueue its copy to a persistent device buffer.  A captured CUDA graph contains that copy
+        node, so the graph runner only calls `draw_orders_host()` before each replay."""
+        T = self.n_tasks
+        if getattr(self, "_orders_host", None) is None or self._orders_dev.device != torch.device(device):
+            self._orders_host = torch.zeros(T * T, dtype=torch.int32).pin_memory()
+            self._orders_dev = torch.zeros(T * T, dtype=torch.int32, device=device)
+        self.draw_orders_host()
+        self._orders_dev.copy_(self._orders_host, non_blocking=True)
+        return self._orders_dev
+
+    def draw_orders_host(self):
+        orders = draw_visit_orders(self.n_tasks)        # every rank draws the same orders (same `random` seed)
+        self._orders_host.copy_(torch.tensor(orders, dtype=torch.int32).reshape(-1))
+        return orders
+
     def _project_conflicting(self, grads: List[Tuple[torch.Tensor]]):
-        orders = draw_visit_orders(len(grads))          # every rank draws the same orders (same `random` seed)
+        assert len(grads) == self.n_tasks
+        orders = self.refresh_orders(grads[0][0].device)
         if mdist.active():
             return mdist.pcgrad_sharded(grads, orders, self.reduction == "mean", _cuda_gram, _cuda_solve_combine)
         return pcgrad_merge(grads, orders, mean=(self.reduction == "mean"))

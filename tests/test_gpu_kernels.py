@@ -163,7 +163,7 @@ def test_conv_tcgen05_forward_backward(case, passes, tol):
         y = ops.conv(x1, wc, bc, cfg, x2=x2, add1=sc)
         y.backward(nhwc(gout.float()).to(DEV))
         torch.cuda.synchronize()
-        assert ops.tc_launches - n0 == (3 if C2 else 2), "tcgen05 kernel was not selected"
+        assert ops.tc_launches - n0 == (4 if C2 else 3), "tcgen05 kernels (fwd, dgrad, wgrad) were not all selected"
     finally:
         ops.set_conv_mode("auto", 3)
     assert rel_err(nchw(y), yr) <= tol
@@ -175,7 +175,7 @@ def test_conv_tcgen05_forward_backward(case, passes, tol):
     z.backward(dz)
     dx = nchw(x1.grad) if not C2 else torch.cat([nchw(x1.grad), nchw(x2.grad)], 1)
     assert rel_err(dx, xr.grad) <= tol
-    assert rel_err(wc.grad, wr.grad) <= 2e-5                    # wgrad runs on the exact kernel
+    assert rel_err(wc.grad, wr.grad) <= tol                     # tcgen05 wgrad (MN-major operands, split-K over pixels)
     assert rel_err(bc.grad, br.grad) <= 2e-5
     if add:
         assert rel_err(nchw(sc.grad), g1) <= 1e-6

