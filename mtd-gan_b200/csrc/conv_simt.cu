@@ -301,7 +301,7 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, float* __restri
 struct UnpackArgs {
   PackArgs p;
   const float* inv_sigma;   // null => plain layer
-  const float* dotgw;       // device scalar <G, W_orig>
+  const double* dotgw;      // device scalar <G, W_orig> (fp64 accumulator of dot_packed_ref_kernel)
   const float* u;
   const float* v;
   int sn_rows;              // Cout of the reference weight; row = ref_index / sn_cols
@@ -316,7 +316,7 @@ __global__ void unpack_grad_kernel(const float* __restrict__ gp, float* __restri
   float alpha = 1.f, beta = 0.f;
   if (a.inv_sigma) {
     alpha = __ldg(a.inv_sigma);
-    beta = __ldg(a.dotgw) * alpha;
+    beta = (float)(*a.dotgw) * alpha;
   }
   for (; i < total; i += stride) {
     int c = (int)(i % p.C);
@@ -352,7 +352,6 @@ __global__ void dot_packed_ref_kernel(const float* __restrict__ gp, const float*
   s = block_sum(s, sh);
   if (threadIdx.x == 0) atomicAdd(acc, s);
 }
-__global__ void dot_finish_kernel(const double* acc, float* out) { *out = (float)(*acc); }
 
 // Fill the (sN, sC, toff) mapping for a reference weight tensor.
 //   transposed == 0: Conv2d / Linear layout (Cout, Cin, kh, kw)
@@ -740,13 +739,10 @@ int mtd_conv_wgrad_finish(const float* gp, float* dw_ref, int transposed, int Co
   if (inv_sigma) {
     MTD_REQUIRE(w_ref && u && v && scratch && !transposed);
     double* acc = (double*)scratch;
-    float* dotf = (float*)((char*)scratch + 8);
     MTD_CUDA(cudaMemsetAsync(acc, 0, 8, st));
     dot_packed_ref_kernel<<<blocks, 256, 0, st>>>(gp, w_ref, acc, a.p);
     MTD_CHECK_LAUNCH();
-    dot_finish_kernel<<<1, 1, 0, st>>>(acc, dotf);
-    MTD_CHECK_LAUNCH();
-    a.inv_sigma = inv_sigma; a.dotgw = dotf; a.u = u; a.v = v;
+    a.inv_sigma = inv_sigma; a.dotgw = acc; a.u = u; a.v = v;
     a.sn_rows = Cout; a.sn_cols = (long long)Cin * kh * kw;
   }
   unpack_grad_kernel<<<blocks, 256, 0, st>>>(gp, dw_ref, a);

@@ -509,6 +509,35 @@ int launch_bn(const CUtensorMap& mA1, const CUtensorMap& mA2, const CUtensorMap&
   return MTD_OK;
 }
 
+// Tile / split selection by a small cost model.  Every k-step costs roughly max(latency floor, bytes / per-SM
+// L2 bandwidth) and a CTA runs ceil(tiles / SMs) rounds of `kper` k-steps, so for skinny-M (weight-streaming)
+// layers the best choice is the WIDEST Cout tile whose (m-tiles x n-tiles x k-splits) still fits one wave.
+void choose_tiling(int m_tiles, int N, int kiters, int passes, int force_split, int* BN_out, int* ksplit_out) {
+  const int sms = mtd_sm_count();
+  double best = 1e30;
+  int BN = 32, ksplit = 1;
+  for (int bn = 128; bn >= 32; bn >>= 1) {
+    if (N % bn) continue;
+    const int mn = m_tiles * (N / bn);
+    const double kb = (passes == 3 ? 2.0 : 1.0) * (16.0 + bn * 0.125);          // smem KB landed / produced per k-step
+    const double t_step = kb < 28.0 ? 28.0 : kb;                                  // latency floor ~ a 28 KB step
+    int ks = 1;
+    if (force_split > 0) ks = force_split;
+    else if (mn < sms && kiters >= 8) {
+      ks = sms / mn;
+      if (ks > kiters / 2) ks = kiters / 2;
+      if (ks < 1) ks = 1;
+    }
+    const int kper = (kiters + ks - 1) / ks;
+    ks = (kiters + kper - 1) / kper;                                              // no empty splits
+    const int rounds = (mn * ks + sms - 1) / sms;
+    const double cost = (double)rounds * kper * t_step + (ks > 1 ? 6.0 * t_step : 0.0);   // + memset / finish pass
+    if (cost < best) { best = cost; BN = bn; ksplit = ks; }
+  }
+  *BN_out = BN;
+  *ksplit_out = ksplit;
+}
+
 // wp: packed weights [N][T][C]; for passes == 3 the buffer holds [hi | lo] (2 x N*T*C floats, mtd_split_tf32).
 // `finish`: run the split-K finishing pass here (false when the caller batches several launches into one
 // output, e.g. the four parity classes of a stride-2 dgrad).  Returns the chosen ksplit through a.ksplit.
@@ -522,20 +551,10 @@ int launch_tc(const float* x1, const float* x2, const float* wp, int passes, TcA
   a.kc1 = a.C1 / 32; a.kc2 = a.C2 / 32;
   const int kiters = a.T * (a.kc1 + a.kc2);
   const int sms = mtd_sm_count();
-  // Cout tile: as wide as possible while the grid still fills the machine (skinny-M layers stream the
-  // weights: narrower tiles + split-K spread that stream over all SMs)
-  int BN = a.N >= 128 ? 128 : (a.N >= 64 ? 64 : 32);
-  while (BN > 32 && m_tiles * (a.N / BN) < sms) BN >>= 1;
-  if (a.N % BN) return MTD_EINVAL;
+  int BN = 32, ksplit = 1;
+  choose_tiling(m_tiles, a.N, kiters, passes, force_split, &BN, &ksplit);
   a.n_nt = a.N / BN;
   int mn_tiles = m_tiles * a.n_nt;
-  int ksplit = 1;
-  if (force_split > 0) ksplit = force_split;
-  else if (mn_tiles < sms && kiters >= 8) {
-    ksplit = (sms + mn_tiles - 1) / mn_tiles;
-    if (ksplit > kiters / 4) ksplit = kiters / 4;
-    if (ksplit < 1) ksplit = 1;
-  }
   a.kper = (kiters + ksplit - 1) / ksplit;
   ksplit = (kiters + a.kper - 1) / a.kper;          // no empty splits
   a.ksplit = ksplit;
@@ -964,18 +983,8 @@ int mtd_conv_dgrad_tc(const float* dz, const float* wpd, float* dx, const float*
         // decide the split once so all classes agree; zero dx up front when partial sums will be accumulated
         TcArgs probe = c;
         probe.n_wt = probe.W / tw; probe.n_ht = probe.H / th; probe.n_bt = (B + tb - 1) / tb;
-        int m_tiles = probe.n_wt * probe.n_ht * probe.n_bt, kiters = 4 * (Cout / 32), sms = mtd_sm_count();
-        int BN = Cin >= 128 ? 128 : (Cin >= 64 ? 64 : 32);
-        while (BN > 32 && m_tiles * (Cin / BN) < sms) BN >>= 1;
-        int mn = m_tiles * (Cin / BN);
-        ksplit = 1;
-        if (mn < sms && kiters >= 8) {
-          ksplit = (sms + mn - 1) / mn;
-          if (ksplit > kiters / 4) ksplit = kiters / 4;
-          if (ksplit < 1) ksplit = 1;
-        }
-        const int kper = (kiters + ksplit - 1) / ksplit;
-        ksplit = (kiters + kper - 1) / kper;
+        int m_tiles = probe.n_wt * probe.n_ht * probe.n_bt, kiters = 4 * (Cout / 32), bn_unused = 32;
+        choose_tiling(m_tiles, Cin, kiters, passes, 0, &bn_unused, &ksplit);
         if (ksplit > 1) MTD_CUDA(cudaMemsetAsync(dx, 0, total * sizeof(float), st));
       }
       int rc = launch_tc(dz, nullptr, wpd + (size_t)(py * 2 + px) * cls_elems, passes, c, st, ksplit, false);
