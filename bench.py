@@ -211,11 +211,13 @@ def run_own(args):
 
     # ---- per-kernel-class times: one extra (untimed) step with CUDA events around every C-ABI call
     breakdown, roof = None, None
+    torch.cuda.synchronize()
     if rank == 0:
-        torch.cuda.synchronize()
         _ext.start_profile()
-        eager_step(xd, yd)
-        rec = _ext.stop_profile()
+    eager_step(xd, yd)                      # every rank runs it (the step contains collectives at N > 1)
+    rec = _ext.stop_profile() if rank == 0 else None
+    barrier()
+    if rank == 0:
         total_ms = sum(r[2] for r in rec)
         if os.environ.get("MTD_BENCH_DUMP"):       # per-call records (entry point, integer args, ms) for offline analysis
             with open(os.environ["MTD_BENCH_DUMP"], "w") as fh:

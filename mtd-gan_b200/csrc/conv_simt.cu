@@ -224,6 +224,158 @@ __global__ void __launch_bounds__(256) conv_igemm_kernel(const __grid_constant__
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------
+// Thin layers (bandwidth-bound, no GEMM shape): dedicated streaming kernels instead of padded tiles.
+//   conv_c1_kernel : source has ONE channel   out[p][n] = epi( sum_t in[p@t] * W[n][t] )
+//                    (conv11 1->64, generator encoder[0] 1->32, the 1->1 heads; dgrad of every Cout = 1 layer)
+//   conv_n1_kernel : N <= 4 outputs            out[p][n] = epi( sum_t sum_c in[p@t][c] * W[n][t][c] )
+//                    (s_/r_dconv61 128->1, generator decoder[0] 32->1; dgrad of every Cin = 1 layer)
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) conv_c1_kernel(const __grid_constant__ ConvArgs a) {
+  extern __shared__ float wsm[];                 // [T][N]
+  for (int i = threadIdx.x; i < a.T * a.N; i += blockDim.x) {
+    int t = i / a.N, n = i - t * a.N;
+    wsm[i] = __ldg(a.wp + (size_t)n * a.T + t);
+  }
+  __syncthreads();
+  const int NQ = (a.N + 3) >> 2;
+  const int HoWo = a.Ho * a.Wo;
+  const size_t total = (size_t)a.B * HoWo * NQ;
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < total; i += stride) {
+    const int nq = (int)(i % NQ);
+    const size_t m = i / NQ;
+    const int b = (int)(m / HoWo), r = (int)(m - (size_t)b * HoWo);
+    const int oy = r / a.Wo, ox = r - oy * a.Wo;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int t = 0; t < a.T; ++t) {
+      const int iy = oy * a.sy + a.dy[t], ix = ox * a.sx + a.dx[t];
+      if (iy < 0 || iy >= a.H || ix < 0 || ix >= a.W) continue;
+      const float v = __ldg(a.src1 + ((size_t)b * a.H + iy) * a.W + ix);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int n = nq * 4 + e;
+        if (n < a.N) acc[e] = fmaf(v, wsm[t * a.N + n], acc[e]);
+      }
+    }
+    const size_t pix = ((size_t)b * a.outH + (oy * a.omy + a.ooy)) * a.outW + (ox * a.omx + a.oox);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int n = nq * 4 + e;
+      if (n < a.N) {
+        const size_t idx = pix * a.N + n;
+        a.out[idx] = conv_epilogue_one(a, acc[e], idx, n);
+      }
+    }
+  }
+}
+
+// LPP lanes cooperate on one pixel (LPP = min(32, Ctot/4)); N <= 4 accumulators per lane, shuffle-reduced.
+__global__ void __launch_bounds__(256) conv_n1_kernel(const __grid_constant__ ConvArgs a, int lpp) {
+  extern __shared__ float wsm[];                 // [N][T][Ctot]
+  const int Ctot = a.C1 + a.C2;
+  for (int i = threadIdx.x; i < a.N * a.T * Ctot; i += blockDim.x) wsm[i] = __ldg(a.wp + i);
+  __syncthreads();
+  const int HoWo = a.Ho * a.Wo;
+  const size_t M = (size_t)a.B * HoWo;
+  const int ppw = 32 / lpp;                       // pixels per warp
+  const int lane = threadIdx.x & 31, sub = lane / lpp, l = lane - sub * lpp;
+  const size_t warp_global = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
+  for (size_t m0 = warp_global * ppw; m0 < M; m0 += nwarps * ppw) {
+    const size_t m = m0 + sub;
+    const bool valid = m < M;
+    const size_t mm = valid ? m : 0;
+    const int b = (int)(mm / HoWo), r = (int)(mm - (size_t)b * HoWo);
+    const int oy = r / a.Wo, ox = r - oy * a.Wo;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    if (valid) {
+      for (int t = 0; t < a.T; ++t) {
+        const int iy = oy * a.sy + a.dy[t], ix = ox * a.sx + a.dx[t];
+        if (iy < 0 || iy >= a.H || ix < 0 || ix >= a.W) continue;
+        const size_t pix = ((size_t)b * a.H + iy) * a.W + ix;
+        for (int c = l * 4; c < Ctot; c += lpp * 4) {
+          const float4 v = c < a.C1 ? __ldg(reinterpret_cast<const float4*>(a.src1 + pix * a.C1 + c))
+                                    : __ldg(reinterpret_cast<const float4*>(a.src2 + pix * a.C2 + (c - a.C1)));
+#pragma unroll
+          for (int n = 0; n < 4; ++n) {
+            if (n < a.N) {
+              const float4 w = *reinterpret_cast<const float4*>(wsm + ((size_t)n * a.T + t) * Ctot + c);
+              acc[n] = fmaf(v.x, w.x, fmaf(v.y, w.y, fmaf(v.z, w.z, fmaf(v.w, w.w, acc[n]))));
+            }
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int n = 0; n < 4; ++n)
+      for (int o = lpp >> 1; o > 0; o >>= 1) acc[n] += __shfl_xor_sync(0xffffffffu, acc[n], o);
+    if (valid && l == 0) {
+      const size_t pix = ((size_t)b * a.outH + (oy * a.omy + a.ooy)) * a.outW + (ox * a.omx + a.oox);
+#pragma unroll
+      for (int n = 0; n < 4; ++n) {
+        if (n < a.N) {
+          const size_t idx = pix * a.N + n;
+          a.out[idx] = conv_epilogue_one(a, acc[n], idx, n);
+        }
+      }
+    }
+  }
+}
+
+// Thin weight gradient: out[t*st_t + j*st_j] += sum_p V[p][j] * s[p + d_t]  (s: single-channel field of the same
+// spatial size as V's pixel grid, zero outside).  Covers wgrad of Cout = 1 layers (s = dz, V = x, d_t = -tap) and of
+// Cin = 1 layers (s = x, V = dz, d_t = +tap).  Each block reduces a pixel range; one atomicAdd per (t, j) per block.
+struct ThinWgArgs {
+  const float* V1;
+  const float* V2;
+  int J1, J2;              // vector channels per source
+  const float* s;
+  int B, H, W, T;
+  int dy[kMaxTaps], dx[kMaxTaps];
+  float* out;
+  long long st_t, st_j;
+  int pix_per_block;
+};
+
+__global__ void __launch_bounds__(256) thin_wgrad_kernel(const __grid_constant__ ThinWgArgs a) {
+  const int J = a.J1 + a.J2;
+  const int HW = a.H * a.W;
+  const long long M = (long long)a.B * HW;
+  const long long p0 = (long long)blockIdx.x * a.pix_per_block;
+  const long long p1 = min(M, p0 + a.pix_per_block);
+  // threads: j = tid % J (channel), lanes of equal j stride over pixels
+  const int jt = threadIdx.x % J, pl = threadIdx.x / J, npl = blockDim.x / J;
+  float acc[kMaxTaps];
+#pragma unroll
+  for (int t = 0; t < kMaxTaps; ++t) acc[t] = 0.f;
+  if (pl < npl) {
+    for (long long p = p0 + pl; p < p1; p += npl) {
+      const float v = jt < a.J1 ? __ldg(a.V1 + p * a.J1 + jt) : __ldg(a.V2 + p * a.J2 + (jt - a.J1));
+      const int b = (int)(p / HW), r = (int)(p - (long long)b * HW);
+      const int y = r / a.W, x = r - y * a.W;
+#pragma unroll
+      for (int t = 0; t < kMaxTaps; ++t) {
+        if (t < a.T) {
+          const int yy = y + a.dy[t], xx = x + a.dx[t];
+          if (yy >= 0 && yy < a.H && xx >= 0 && xx < a.W) acc[t] = fmaf(v, __ldg(a.s + ((size_t)b * a.H + yy) * a.W + xx), acc[t]);
+        }
+      }
+    }
+  }
+  __shared__ float red[kMaxTaps][256];
+  for (int t = 0; t < a.T; ++t) red[t][threadIdx.x] = (pl < npl) ? acc[t] : 0.f;
+  __syncthreads();
+  for (int i = threadIdx.x; i < a.T * J; i += blockDim.x) {
+    const int t = i / J, j = i - t * J;
+    float sum = 0.f;
+    for (int q = 0; q < npl; ++q) sum += red[t][q * J + j];
+    atomicAdd(a.out + t * a.st_t + j * a.st_j, sum);
+  }
+}
+
 // second phase of a split-K conv: out holds raw sums
 __global__ void conv_epilogue_kernel(const __grid_constant__ ConvArgs a, size_t total) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -240,6 +392,23 @@ int launch_conv(ConvArgs& a, cudaStream_t st) {
   if (M <= 0 || a.N <= 0 || Ctot <= 0 || a.T <= 0 || a.T > kMaxTaps) return MTD_EINVAL;
   bool vec = (a.C1 % 4 == 0) && (a.C2 % 4 == 0) && mtd_aligned16(a.src1) && mtd_aligned16(a.wp) &&
              (a.C2 == 0 || mtd_aligned16(a.src2));
+  a.splits = 1;
+  if (Ctot == 1 && a.T * a.N * sizeof(float) <= 40 * 1024) {                 // single-channel source: streaming kernel
+    size_t work = (size_t)M * ((a.N + 3) / 4);
+    int blocks = (int)std::min<size_t>((work + 255) / 256, (size_t)mtd_sm_count() * 16);
+    conv_c1_kernel<<<blocks, 256, a.T * a.N * sizeof(float), st>>>(a);
+    MTD_CHECK_LAUNCH();
+    return MTD_OK;
+  }
+  if (a.N <= 4 && vec && Ctot >= 8 && (size_t)a.N * a.T * Ctot * sizeof(float) <= 40 * 1024) {   // few outputs, many channels
+    int lpp = 1;
+    while (lpp < 32 && lpp * 2 * 4 <= Ctot) lpp <<= 1;
+    size_t warps = ((size_t)M + (32 / lpp) - 1) / (32 / lpp);
+    int blocks = (int)std::min<size_t>((warps + 7) / 8, (size_t)mtd_sm_count() * 16);
+    conv_n1_kernel<<<blocks, 256, (size_t)a.N * a.T * Ctot * sizeof(float), st>>>(a, lpp);
+    MTD_CHECK_LAUNCH();
+    return MTD_OK;
+  }
   bool thin_n = a.N <= 16;
   const int BM = thin_n ? 128 : 64, BN = thin_n ? 16 : 64;
   dim3 grid((M + BM - 1) / BM, (a.N + BN - 1) / BN, 1);
@@ -721,6 +890,32 @@ int mtd_conv_wgrad(const float* x1, const float* x2, const float* dz, float* gp,
   a.T = kh * kw; a.sy = a.sx = stride;
   tap_table_fwd(a.dy, a.dx, kh, kw, pad);
   a.gp = gp;
+  const int Ctot = C1 + C2;
+  if (stride == 1 && a.Ho == H && a.Wo == W && (N == 1 || Ctot == 1) && (N == 1 ? Ctot : N) <= 256) {
+    // thin layer: gp[n][t][c] with n == 0 (vector = x, scalar = dz, x pixel = p + tap  =>  s index = q - tap for q over x)
+    // or c == 0 (vector = dz, scalar = x at p + tap)
+    cudaStream_t st = (cudaStream_t)stream;
+    ThinWgArgs w{};
+    w.B = B; w.H = H; w.W = W; w.T = a.T; w.out = gp;
+    if (N == 1 && Ctot > 1) {
+      w.V1 = x1; w.V2 = x2; w.J1 = C1; w.J2 = C2; w.s = dz;
+      for (int t = 0; t < a.T; ++t) { w.dy[t] = -a.dy[t]; w.dx[t] = -a.dx[t]; }
+      w.st_t = Ctot; w.st_j = 1;
+    } else {
+      w.V1 = dz; w.V2 = nullptr; w.J1 = N; w.J2 = 0; w.s = x1;
+      for (int t = 0; t < a.T; ++t) { w.dy[t] = a.dy[t]; w.dx[t] = a.dx[t]; }
+      w.st_t = Ctot; w.st_j = (long long)a.T * Ctot;          // Ctot == 1
+    }
+    const long long M = (long long)B * H * W;
+    int blocks = mtd_sm_count() * 4;
+    if (blocks > M / 64 + 1) blocks = (int)(M / 64 + 1);
+    w.pix_per_block = (int)((M + blocks - 1) / blocks);
+    blocks = (int)((M + w.pix_per_block - 1) / w.pix_per_block);
+    MTD_CUDA(cudaMemsetAsync(gp, 0, (size_t)N * a.T * Ctot * sizeof(float), st));
+    thin_wgrad_kernel<<<blocks, 256, 0, st>>>(w);
+    MTD_CHECK_LAUNCH();
+    return MTD_OK;
+  }
   return launch_wgrad(a, (cudaStream_t)stream);
 }
 

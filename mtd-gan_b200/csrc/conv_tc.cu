@@ -49,6 +49,7 @@ struct TcArgs {
   int stages;
   int wrows_total;              // rows of the full packed weight buffer (offset of the lo half, passes == 3)
   int ksplit, kper;             // split-K: tile = mn_tile * ksplit + ks, k-steps [ks*kper, (ks+1)*kper)
+  int inH, inW, es;             // input tensor dims and conv stride (A tile = TMA box with elementStrides es)
   int outH, outW, omy, omx, ooy, oox;   // output pixel = (h*omy+ooy, w*omx+oox) in a (B,outH,outW,N) tensor
   float* out;
   const float* scale;
@@ -232,8 +233,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
           mbar_expect_tx(full_bar(st.stage), kTxBytes);
           const int t = it / kchunks, cc = it - t * kchunks;
           const uint32_t sa = base + (uint32_t)st.stage * kStageBytes, sb = sa + kOffB;
-          if (cc < a.kc1) tma_load_4d(&mapA1, sa, full_bar(st.stage), cc * 32, w0 + a.dx[t], h0 + a.dy[t], b0);
-          else tma_load_4d(&mapA2, sa, full_bar(st.stage), (cc - a.kc1) * 32, w0 + a.dx[t], h0 + a.dy[t], b0);
+          if (cc < a.kc1) tma_load_4d(&mapA1, sa, full_bar(st.stage), cc * 32, w0 * a.es + a.dx[t], h0 * a.es + a.dy[t], b0);
+          else tma_load_4d(&mapA2, sa, full_bar(st.stage), (cc - a.kc1) * 32, w0 * a.es + a.dx[t], h0 * a.es + a.dy[t], b0);
           tma_load_2d(&mapB, sb, full_bar(st.stage), t * Ctot + cc * 32, n0);
           if (NPASS == 3) tma_load_2d(&mapBlo, sa + kOffBlo, full_bar(st.stage), t * Ctot + cc * 32, n0);
           st.advance(S);
@@ -422,11 +423,14 @@ std::unordered_map<std::string, CUtensorMap> g_map_cache;
 // activations: rank-4 (C, W, H, B) fp32, box (32, TW, TH, TB), OOB -> zeros.  atom32 = false: SWIZZLE_128B
 // (K-major operands of the forward / dgrad kernels); atom32 = true: SWIZZLE_128B_ATOM_32B (MN-major tf32
 // operands of the wgrad kernel)
-int make_act_map(CUtensorMap* out, const float* ptr, int C, int W, int H, int B, int TW, int TH, int TB, bool atom32 = false) {
+// es = conv stride: the box traverses es*TW x es*TH input pixels with elementStrides (1, es, es, 1), i.e. it lands
+// exactly the TW x TH pixels a strided convolution tap needs.
+int make_act_map(CUtensorMap* out, const float* ptr, int C, int W, int H, int B, int TW, int TH, int TB, bool atom32 = false,
+                 int es = 1) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return MTD_EINVAL;
   char keybuf[128];
-  snprintf(keybuf, sizeof(keybuf), "A%d%p:%d:%d:%d:%d:%d:%d:%d", (int)atom32, (const void*)ptr, C, W, H, B, TW, TH, TB);
+  snprintf(keybuf, sizeof(keybuf), "A%d%d%p:%d:%d:%d:%d:%d:%d:%d", (int)atom32, es, (const void*)ptr, C, W, H, B, TW, TH, TB);
   std::string key(keybuf);
   {
     std::lock_guard<std::mutex> lk(g_map_mutex);
@@ -435,8 +439,9 @@ int make_act_map(CUtensorMap* out, const float* ptr, int C, int W, int H, int B,
   }
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
   cuuint64_t strides[3] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4};
-  cuuint32_t box[4] = {32, (cuuint32_t)TW, (cuuint32_t)TH, (cuuint32_t)TB};
-  cuuint32_t estr[4] = {1, 1, 1, 1};
+  cuuint32_t box[4] = {32, (cuuint32_t)(TW * es), (cuuint32_t)(TH * es), (cuuint32_t)TB};
+  cuuint32_t estr[4] = {1, (cuuint32_t)es, (cuuint32_t)es, 1};
+  if (box[1] > 256 || box[2] > 256) return MTD_EINVAL;
   CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -474,8 +479,15 @@ int make_w_map(CUtensorMap* out, const float* ptr, long long K, int rows, int BN
 
 bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 
+// (H, W) = conv INPUT dims.  stride 1: size-preserving convs; stride 2: output (H+2p-k)/2+1 (the 4x4/pad-1 down* layers).
+// The tile geometry is computed on the OUTPUT grid.
 bool tc_geometry(int B, int H, int W, int C1, int C2, int N, int kh, int kw, int stride, int pad, int* TW, int* TH, int* TB) {
-  if (stride != 1 || kh != kw || 2 * pad != kh - 1 || kh * kw > kMaxTaps) return false;
+  if (kh != kw || kh * kw > kMaxTaps) return false;
+  if (stride == 1) { if (2 * pad != kh - 1) return false; }
+  else if (stride == 2) {
+    if ((H + 2 * pad - kh) % 2 || (W + 2 * pad - kw) % 2 || H + 2 * pad < kh || W + 2 * pad < kw) return false;
+    H = (H + 2 * pad - kh) / 2 + 1; W = (W + 2 * pad - kw) / 2 + 1;
+  } else return false;
   if (C1 <= 0 || C1 % 32 || C2 < 0 || C2 % 32 || N <= 0 || N % 32) return false;
   if (!is_pow2(W) || !is_pow2(H)) return false;
   if ((long long)B * H * W < 16) return false;
@@ -562,9 +574,10 @@ int launch_tc(const float* x1, const float* x2, const float* wp, int passes, TcA
   const size_t total = (size_t)a.B * a.outH * a.outW * a.N;
   if (ksplit > 1 && finish) MTD_CUDA(cudaMemsetAsync(a.out, 0, total * sizeof(float), st));
   CUtensorMap mA1, mA2, mB;
-  int rc = make_act_map(&mA1, x1, a.C1, a.W, a.H, a.B, a.TW, a.TH, a.TB);
+  if (a.es < 1) { a.es = 1; a.inH = a.H; a.inW = a.W; }
+  int rc = make_act_map(&mA1, x1, a.C1, a.inW, a.inH, a.B, a.TW, a.TH, a.TB, false, a.es);
   if (rc) return rc;
-  if (a.C2) { rc = make_act_map(&mA2, x2, a.C2, a.W, a.H, a.B, a.TW, a.TH, a.TB); if (rc) return rc; }
+  if (a.C2) { rc = make_act_map(&mA2, x2, a.C2, a.inW, a.inH, a.B, a.TW, a.TH, a.TB, false, a.es); if (rc) return rc; }
   else mA2 = mA1;
   const long long K = (long long)a.T * (a.C1 + a.C2);
   rc = make_w_map(&mB, wp, K, a.N, BN);
@@ -620,13 +633,13 @@ __global__ void split_tf32_kernel(float* __restrict__ hi, float* __restrict__ lo
 // pixels), and the epilogue atomically adds the fp32 partials into the packed gradient.  Both operands are
 // activations, so the rounding warps split BOTH into tf32 hi/lo for the 3xTF32 mode.
 // =====================================================================================================
-constexpr int kKp = 32;                         // pixels per k-step
-constexpr int kBlkBytes = kKp * 128;            // one (32 ch x 32 px) block = 4 KB
+// KP = pixels per k-step (32 for the 3xTF32 mode, 64 for plain TF32); one (32 ch x KP px) block = KP * 128 bytes
 
 struct WgArgs {
   int B, H, W, C1, C2, N, T;
   int dy[kMaxTaps], dx[kMaxTaps];
-  int TW, TH, TB, n_wt, n_ht, n_bt;            // pixel-tile geometry (TW*TH*TB == kKp)
+  int TW, TH, TB, n_wt, n_ht, n_bt;            // pixel-tile geometry over the OUTPUT grid (TW*TH*TB == KP)
+  int es;                                       // conv stride: x boxes are loaded with elementStrides es
   int kc1, kc2, units, m_tiles, n_nt;
   int ksplit, kper, ptiles, n_tiles, stages;
   float* gp;
@@ -645,11 +658,12 @@ __device__ __forceinline__ uint64_t make_sw128_desc_mn(uint32_t smem_addr, uint3
   return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | (32ull << 32) | (1ull << 46) | (1ull << 61);
 }
 
-template <int BN, int NPASS>
+template <int BN, int NPASS, int KP>
 __global__ void __launch_bounds__(kThreads, 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapX1, const __grid_constant__ CUtensorMap mapX2,
                 const __grid_constant__ CUtensorMap mapDz, const __grid_constant__ WgArgs a) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
+  constexpr int kBlkBytes = KP * 128;
   constexpr int kNB = BN / 32;                                  // dz blocks
   constexpr int kBlocks = 4 + kNB;                              // fp32 blocks landed by TMA per stage
   constexpr int kHalf = kBlocks * kBlkBytes;                    // hi tiles (in place); lo tiles follow
@@ -726,8 +740,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapX1, const __grid_constant
           const uint32_t sa = base + (uint32_t)st.stage * kStageBytes;
           for (int i = 0; i < nvalid; ++i) {
             const int u = mt * 4 + i, t = u / kchunks, cc = u - t * kchunks;
-            if (cc < a.kc1) tma_load_4d(&mapX1, sa + i * kBlkBytes, full_bar(st.stage), cc * 32, w0 + a.dx[t], h0 + a.dy[t], b0);
-            else tma_load_4d(&mapX2, sa + i * kBlkBytes, full_bar(st.stage), (cc - a.kc1) * 32, w0 + a.dx[t], h0 + a.dy[t], b0);
+            if (cc < a.kc1) tma_load_4d(&mapX1, sa + i * kBlkBytes, full_bar(st.stage), cc * 32, w0 * a.es + a.dx[t], h0 * a.es + a.dy[t], b0);
+            else tma_load_4d(&mapX2, sa + i * kBlkBytes, full_bar(st.stage), (cc - a.kc1) * 32, w0 * a.es + a.dx[t], h0 * a.es + a.dy[t], b0);
           }
 #pragma unroll
           for (int j = 0; j < kNB; ++j)
@@ -755,7 +769,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapX1, const __grid_constant
           const uint32_t sa = base + (uint32_t)st.stage * kStageBytes;
           const uint64_t da = make_sw128_desc_mn(sa, kBlkBytes), db = make_sw128_desc_mn(sa + 4 * kBlkBytes, kBlkBytes);
 #pragma unroll
-          for (int kk = 0; kk < kKp / 8; ++kk) {       // one 8-pixel k-atom (1024 B) per MMA: +64 in 16-byte units
+          for (int kk = 0; kk < KP / 8; ++kk) {       // one 8-pixel k-atom (1024 B) per MMA: +64 in 16-byte units
             const uint32_t accum = (it > k_begin || kk > 0) ? 1u : 0u;
             if (NPASS == 3) {
               const uint64_t dal = make_sw128_desc_mn(sa + kHalf, kBlkBytes), dbl = make_sw128_desc_mn(sa + kHalf + 4 * kBlkBytes, kBlkBytes);
@@ -849,9 +863,9 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapX1, const __grid_constant
   }
 }
 
-template <int BN, int NPASS>
+template <int BN, int NPASS, int KP>
 int launch_wg(const CUtensorMap& mX1, const CUtensorMap& mX2, const CUtensorMap& mDz, WgArgs& a, cudaStream_t st) {
-  const int stage_bytes = (NPASS == 3 ? 2 : 1) * (4 + BN / 32) * kBlkBytes;
+  const int stage_bytes = (NPASS == 3 ? 2 : 1) * (4 + BN / 32) * KP * 128;
   int stages = (200 * 1024) / stage_bytes;
   if (stages > 8) stages = 8;
   if (stages > a.kper) stages = a.kper < 2 ? 2 : a.kper;
@@ -859,17 +873,22 @@ int launch_wg(const CUtensorMap& mX1, const CUtensorMap& mX2, const CUtensorMap&
   size_t smem = 1024 + (size_t)stages * stage_bytes + 8 * (3 * stages + 4) + 16;
   static bool attr_set = false;
   if (!attr_set) {
-    MTD_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<BN, NPASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    MTD_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<BN, NPASS, KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
   int grid = a.n_tiles < mtd_sm_count() ? a.n_tiles : mtd_sm_count();
-  wgrad_tc_kernel<BN, NPASS><<<grid, kThreads, smem, st>>>(mX1, mX2, mDz, a);
+  wgrad_tc_kernel<BN, NPASS, KP><<<grid, kThreads, smem, st>>>(mX1, mX2, mDz, a);
   MTD_CHECK_LAUNCH();
   return MTD_OK;
 }
 
-bool wg_geometry(int B, int H, int W, int C1, int C2, int N, int kh, int kw, int stride, int pad, int* TW, int* TH, int* TB) {
-  if (stride != 1 || kh != kw || 2 * pad != kh - 1 || kh * kw > kMaxTaps) return false;
+bool wg_geometry(int B, int H, int W, int C1, int C2, int N, int kh, int kw, int stride, int pad, int kKp, int* TW, int* TH, int* TB) {
+  if (kh != kw || kh * kw > kMaxTaps) return false;
+  if (stride == 1) { if (2 * pad != kh - 1) return false; }
+  else if (stride == 2) {
+    if ((H + 2 * pad - kh) % 2 || (W + 2 * pad - kw) % 2 || H + 2 * pad < kh || W + 2 * pad < kw) return false;
+    H = (H + 2 * pad - kh) / 2 + 1; W = (W + 2 * pad - kw) / 2 + 1;
+  } else return false;
   if (C1 <= 0 || C1 % 32 || C2 < 0 || C2 % 32 || N <= 0 || N % 32) return false;
   if (!is_pow2(W) || !is_pow2(H)) return false;
   int tw = W < kKp ? W : kKp;
@@ -927,13 +946,15 @@ int mtd_conv_fwd_tc(const float* x1, const float* x2, const float* wp, const flo
   int tw, th, tb;
   if (!tc_geometry(B, H, W, C1, C2, N, kh, kw, stride, pad, &tw, &th, &tb)) return MTD_EINVAL;
   TcArgs a{};
-  a.B = B; a.H = H; a.W = W; a.C1 = C1; a.C2 = C2; a.N = N; a.T = kh * kw;
+  const int Ho = (H + 2 * pad - kh) / stride + 1, Wo = (W + 2 * pad - kw) / stride + 1;
+  a.B = B; a.H = Ho; a.W = Wo; a.C1 = C1; a.C2 = C2; a.N = N; a.T = kh * kw;     // a.H / a.W: the output (tile) grid
+  a.inH = H; a.inW = W; a.es = stride;
   for (int ky = 0; ky < kh; ++ky)
     for (int kx = 0; kx < kw; ++kx) { a.dy[ky * kw + kx] = ky - pad; a.dx[ky * kw + kx] = kx - pad; }
   a.out = y; a.scale = scale; a.bias = bias; a.pre_act = pre_act; a.add1 = add1; a.add2 = add2; a.post_act = post_act;
   a.mask_src = nullptr; a.mask_act = 0; a.slope = slope; a.aux = aux;
   a.wrows_total = N;
-  a.outH = H; a.outW = W; a.omy = a.omx = 1; a.ooy = a.oox = 0;
+  a.outH = Ho; a.outW = Wo; a.omy = a.omx = 1; a.ooy = a.oox = 0;
   return launch_tc(x1, x2, wp, passes, a, (cudaStream_t)stream);
 }
 
@@ -1003,7 +1024,7 @@ int mtd_conv_dgrad_tc(const float* dz, const float* wpd, float* dx, const float*
 
 int mtd_conv_wgrad_tc_supported(int B, int H, int W, int C1, int C2, int N, int kh, int kw, int stride, int pad) {
   int tw, th, tb;
-  return wg_geometry(B, H, W, C1, C2, N, kh, kw, stride, pad, &tw, &th, &tb) && get_encode() != nullptr ? 1 : 0;
+  return wg_geometry(B, H, W, C1, C2, N, kh, kw, stride, pad, 64, &tw, &th, &tb) && get_encode() != nullptr ? 1 : 0;
 }
 
 // gp[N][kh*kw][C1+C2] = sum over pixels of dz (x) x on the tensor cores (stride-1 "same" convs).
@@ -1012,19 +1033,21 @@ int mtd_conv_wgrad_tc(const float* x1, const float* x2, const float* dz, float* 
   MTD_REQUIRE(x1 && dz && gp && ((C2 == 0) == (x2 == nullptr)) && (passes == 1 || passes == 3));
   cudaStream_t st = (cudaStream_t)stream;
   WgArgs a{};
-  if (!wg_geometry(B, H, W, C1, C2, N, kh, kw, stride, pad, &a.TW, &a.TH, &a.TB)) return MTD_EINVAL;
+  const int kp = passes == 3 ? 32 : 64;
+  if (!wg_geometry(B, H, W, C1, C2, N, kh, kw, stride, pad, kp, &a.TW, &a.TH, &a.TB)) return MTD_EINVAL;
   if (!mtd_aligned16(x1) || !mtd_aligned16(dz) || (x2 && !mtd_aligned16(x2))) return MTD_EALIGN;
-  a.B = B; a.H = H; a.W = W; a.C1 = C1; a.C2 = C2; a.N = N; a.T = kh * kw;
+  const int Ho = (H + 2 * pad - kh) / stride + 1, Wo = (W + 2 * pad - kw) / stride + 1;
+  a.B = B; a.H = Ho; a.W = Wo; a.C1 = C1; a.C2 = C2; a.N = N; a.T = kh * kw; a.es = stride;
   for (int ky = 0; ky < kh; ++ky)
     for (int kx = 0; kx < kw; ++kx) { a.dy[ky * kw + kx] = ky - pad; a.dx[ky * kw + kx] = kx - pad; }
-  a.n_wt = W / a.TW; a.n_ht = H / a.TH; a.n_bt = (B + a.TB - 1) / a.TB;
+  a.n_wt = Wo / a.TW; a.n_ht = Ho / a.TH; a.n_bt = (B + a.TB - 1) / a.TB;
   a.ptiles = a.n_wt * a.n_ht * a.n_bt;
   a.kc1 = C1 / 32; a.kc2 = C2 / 32;
   a.units = a.T * (a.kc1 + a.kc2);
   a.m_tiles = (a.units + 3) / 4;
   const int sms = mtd_sm_count();
+  // widest dz tile: x (the 9x re-read operand) is streamed once per n-tile; parallelism comes from split-K over pixels
   int BN = N >= 128 ? 128 : (N >= 64 ? 64 : 32);
-  while (BN > 32 && a.m_tiles * (N / BN) < sms) BN >>= 1;
   if (N % BN) return MTD_EINVAL;
   a.n_nt = N / BN;
   const int mn = a.m_tiles * a.n_nt;
@@ -1041,13 +1064,13 @@ int mtd_conv_wgrad_tc(const float* x1, const float* x2, const float* dz, float* 
   a.gp = gp;
   if (ksplit > 1) MTD_CUDA(cudaMemsetAsync(gp, 0, (size_t)N * a.T * (C1 + C2) * sizeof(float), st));
   CUtensorMap mX1, mX2, mDz;
-  int rc = make_act_map(&mX1, x1, C1, W, H, B, a.TW, a.TH, a.TB, true);
+  int rc = make_act_map(&mX1, x1, C1, W, H, B, a.TW, a.TH, a.TB, true, stride);
   if (rc) return rc;
-  if (C2) { rc = make_act_map(&mX2, x2, C2, W, H, B, a.TW, a.TH, a.TB, true); if (rc) return rc; }
+  if (C2) { rc = make_act_map(&mX2, x2, C2, W, H, B, a.TW, a.TH, a.TB, true, stride); if (rc) return rc; }
   else mX2 = mX1;
-  rc = make_act_map(&mDz, dz, N, W, H, B, a.TW, a.TH, a.TB, true);
+  rc = make_act_map(&mDz, dz, N, Wo, Ho, B, a.TW, a.TH, a.TB, true);
   if (rc) return rc;
-#define WG_DISPATCH(BN_) rc = passes == 3 ? launch_wg<BN_, 3>(mX1, mX2, mDz, a, st) : launch_wg<BN_, 1>(mX1, mX2, mDz, a, st)
+#define WG_DISPATCH(BN_) rc = passes == 3 ? launch_wg<BN_, 3, 32>(mX1, mX2, mDz, a, st) : launch_wg<BN_, 1, 64>(mX1, mX2, mDz, a, st)
   if (BN == 128) { WG_DISPATCH(128); }
   else if (BN == 64) { WG_DISPATCH(64); }
   else { WG_DISPATCH(32); }

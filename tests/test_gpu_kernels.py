@@ -46,8 +46,17 @@ CONV_CASES = [
 ]
 
 
+@pytest.fixture()
+def exact_kernels():
+    from mtdgan_b200 import ops
+    ops.set_conv_mode("simt")
+    yield
+    ops.set_conv_mode("auto", 3)
+
+
 @pytest.mark.parametrize("case", CONV_CASES, ids=lambda c: "x".join(map(str, c)))
-def test_conv_forward_backward(case):
+def test_conv_forward_backward(case, exact_kernels):
+    """Exact-fp32 CUDA-core kernels (generic implicit GEMM + the thin-layer streaming kernels)."""
     from mtdgan_b200 import ops
     B, H, W, C1, C2, N, k, s, p, tr, pre, post, add = case
     C = C1 + C2
@@ -105,28 +114,35 @@ TC_CASES = [
 
 @pytest.mark.parametrize("passes,tol", [(1, 2e-3), (3, 5e-5)], ids=["tf32", "tf32x3"])
 @pytest.mark.parametrize("B,H,C", [(2, 64, 64), (20, 8, 512), (20, 2, 512), (3, 16, 256)])
-def test_conv_tcgen05_stride2_dgrad(B, H, C, passes, tol):
-    """down* layers (4x4, stride 2, pad 1): data gradient as four parity classes on the tcgen05 kernel."""
+def test_conv_tcgen05_stride2(B, H, C, passes, tol):
+    """down* layers (4x4, stride 2, pad 1) on the tcgen05 kernels: forward and wgrad through TMA element strides,
+    data gradient as four output-parity classes."""
     from mtdgan_b200 import ops
     x = _rand(B, C, H, H, seed=1)
     w = _rand(C, C, 4, 4, seed=2, scale=1.0 / math.sqrt(C * 16))
+    b = _rand(C, seed=3, scale=0.1)
     gout = _rand(B, C, H // 2, H // 2, seed=5)
-    xr = x.clone().requires_grad_(True)
-    F.conv2d(xr, w, None, stride=2, padding=1).backward(gout)
+    xr, wr, br = x.clone().requires_grad_(True), w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    yr = F.conv2d(xr, wr, br, stride=2, padding=1)
+    yr.backward(gout)
     xc = nhwc(x.float()).to(DEV).requires_grad_(True)
-    wc = w.float().to(DEV)
-    bc = torch.zeros(C, device=DEV)
+    wc, bc = w.float().to(DEV).requires_grad_(True), b.float().to(DEV).requires_grad_(True)
     cfg = ops.ConvCfg(cin=C, cout=C, kh=4, kw=4, stride=2, pad=1)
     ops.set_conv_mode("auto", passes)
+    ops.set_wgrad_passes(passes)
     try:
         n0 = ops.tc_launches
         y = ops.conv(xc, wc, bc, cfg)
         y.backward(nhwc(gout.float()).to(DEV))
         torch.cuda.synchronize()
-        assert ops.tc_launches - n0 == 1, "tcgen05 dgrad was not selected"
+        assert ops.tc_launches - n0 == 3, "tcgen05 fwd / dgrad / wgrad were not all selected"
     finally:
         ops.set_conv_mode("auto", 3)
+        ops.set_wgrad_passes(1)
+    assert rel_err(nchw(y), yr) <= tol
     assert rel_err(nchw(xc.grad), xr.grad) <= tol
+    assert rel_err(wc.grad, wr.grad) <= tol
+    assert rel_err(bc.grad, br.grad) <= 2e-5
 
 
 @pytest.mark.parametrize("passes,tol", [(1, 2e-3), (3, 5e-5)], ids=["tf32", "tf32x3"])
@@ -158,6 +174,7 @@ def test_conv_tcgen05_forward_backward(case, passes, tol):
     sc = nhwc(skip.float()).to(DEV).requires_grad_(True) if add else None
     cfg = ops.ConvCfg(cin=C, cout=N, kh=k, kw=k, stride=1, pad=p, transposed=tr, pre_act=pre, post_act=post)
     ops.set_conv_mode("auto", passes)
+    ops.set_wgrad_passes(passes)
     try:
         n0 = ops.tc_launches
         y = ops.conv(x1, wc, bc, cfg, x2=x2, add1=sc)
@@ -166,6 +183,7 @@ def test_conv_tcgen05_forward_backward(case, passes, tol):
         assert ops.tc_launches - n0 == (4 if C2 else 3), "tcgen05 kernels (fwd, dgrad, wgrad) were not all selected"
     finally:
         ops.set_conv_mode("auto", 3)
+        ops.set_wgrad_passes(1)
     assert rel_err(nchw(y), yr) <= tol
     # backward reference through the CUDA forward's own activation pattern
     yc = nchw(y).detach().double().cpu()
