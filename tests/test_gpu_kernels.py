@@ -291,22 +291,30 @@ def test_pixel_shuffle_layout_clip_mul():
     assert c.tolist() == [0.0, 0.0, 0.25, 1.0, 1.0, 0.0] and v.grad.tolist() == [0, 1, 1, 1, 0, 1]
 
 
-def test_fft_block_vs_golden_and_oracle():
-    """FFT_ConvBlock forward + all gradients against the golden vectors from the live reference."""
+@pytest.mark.parametrize("mode", ["simt", "auto"])
+def test_fft_block_vs_golden_and_oracle(mode):
+    """FFT_ConvBlock forward + all gradients against the golden vectors from the live reference.  "simt": exact fp32
+    everywhere (1e-4 on everything); "auto" (default): the img_conv runs on tcgen05 (3xTF32 forward / dgrad: still
+    1e-4; plain-TF32 weight gradient: the north_star's tensor-core bound 2e-3)."""
     from arch.Ours.networks import FFT_ConvBlock
-    torch.manual_seed(5)
-    blk = FFT_ConvBlock(32).to(DEV)
-    g = torch.Generator().manual_seed(6)
-    x = (0.5 * torch.randn(1, 32, 64, 64, generator=g)).to(DEV).requires_grad_(True)
-    wgt = torch.randn(1, 32, 64, 64, generator=g).to(DEV)
-    out = blk(x)
-    (out * wgt).sum().backward()
+    from mtdgan_b200 import ops
+    ops.set_conv_mode(mode, 3 if mode == "auto" else None)
+    try:
+        torch.manual_seed(5)
+        blk = FFT_ConvBlock(32).to(DEV)
+        g = torch.Generator().manual_seed(6)
+        x = (0.5 * torch.randn(1, 32, 64, 64, generator=g)).to(DEV).requires_grad_(True)
+        wgt = torch.randn(1, 32, 64, 64, generator=g).to(DEV)
+        out = blk(x)
+        (out * wgt).sum().backward()
+    finally:
+        ops.set_conv_mode("auto", 3)
     fix = load("fftblock_64.pt")
     assert rel_err(out, fix["out"]) <= 1e-4          # north_star: fp32 rel. error <= 1e-4 on FFT/conv outputs
     assert rel_err(x.grad, fix["dx"]) <= 1e-4
     for k, p in blk.named_parameters():
-        assert rel_err(p.grad, fix["grads"][k]) <= 1e-4, k
-    # B = 1 x 64 x 64 has 4096 pixels: the img_conv ran on the tcgen05 3xTF32 kernel (default mode)
+        tol = 2e-3 if (mode == "auto" and k == "img_conv.weight") else 1e-4
+        assert rel_err(p.grad, fix["grads"][k]) <= tol, k
 
 
 @pytest.mark.parametrize("H,W", [(64, 64), (128, 64), (64, 256), (512, 512)])
