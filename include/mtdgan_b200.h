@@ -64,6 +64,14 @@ int mtd_conv_wgrad(const float* x1, const float* x2, const float* dz, float* gp,
 int mtd_conv_wgrad_finish(const float* gp, float* dw_ref, int transposed, int Cout, int Cin, int kh, int kw,
                           const float* w_ref, const float* u, const float* v, const float* inv_sigma, void* scratch,
                           void* stream);
+/* batched mtd_conv_wgrad_finish for every (layer, forward instance) of one backward pass; contributions of the
+ * instances that share a weight are summed into one dw.  Segment table int64[n][16] = { gp, dw, w_ref, u, v,
+ * inv_sigma, Cout, kh*kw, Cin, sN, sC, flip, sn_cols, dot slot, next segment of the same weight or -1, 0 }
+ * (Conv2d: sN = Cin*T, sC = T, flip 0; ConvTranspose2d: sN = T, sC = Cout*T, flip 1).  dot_chunks lists every
+ * spectral-normed segment, head_chunks only the first segment of each weight.                              */
+int mtd_wgrad_finish_chunk_elems(void);
+int mtd_wgrad_finish_batched(const void* seg_tab, int n_segs, const void* dot_chunks, int n_dot_chunks, const void* head_chunks,
+                             int n_head_chunks, double* dots, void* stream);
 /* dz = dy * act'(y) (F.relu / nn.LeakyReLU(0.2) backward); dbias[N] = column sums of dz (optional)  */
 int mtd_act_bwd(const float* dy, const float* y, float* dz, float* dbias, long long M, int N, int act, float slope,
                 void* stream);

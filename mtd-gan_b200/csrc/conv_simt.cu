@@ -233,13 +233,14 @@ __global__ void __launch_bounds__(256) conv_igemm_kernel(const __grid_constant__
 //                    (s_/r_dconv61 128->1, generator decoder[0] 32->1; dgrad of every Cin = 1 layer)
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) conv_c1_kernel(const __grid_constant__ ConvArgs a) {
-  extern __shared__ float wsm[];                 // [T][N]
-  for (int i = threadIdx.x; i < a.T * a.N; i += blockDim.x) {
-    int t = i / a.N, n = i - t * a.N;
-    wsm[i] = __ldg(a.wp + (size_t)n * a.T + t);
+  extern __shared__ __align__(16) float wsm[];   // [T][N4]  (N padded to a multiple of 4, zero filled)
+  const int N4 = (a.N + 3) & ~3;
+  for (int i = threadIdx.x; i < a.T * N4; i += blockDim.x) {
+    int t = i / N4, n = i - t * N4;
+    wsm[i] = n < a.N ? __ldg(a.wp + (size_t)n * a.T + t) : 0.f;
   }
   __syncthreads();
-  const int NQ = (a.N + 3) >> 2;
+  const int NQ = N4 >> 2;
   const int HoWo = a.Ho * a.Wo;
   const size_t total = (size_t)a.B * HoWo * NQ;
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -249,32 +250,42 @@ __global__ void __launch_bounds__(256) conv_c1_kernel(const __grid_constant__ Co
     const size_t m = i / NQ;
     const int b = (int)(m / HoWo), r = (int)(m - (size_t)b * HoWo);
     const int oy = r / a.Wo, ox = r - oy * a.Wo;
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int t = 0; t < a.T; ++t) {
-      const int iy = oy * a.sy + a.dy[t], ix = ox * a.sx + a.dx[t];
-      if (iy < 0 || iy >= a.H || ix < 0 || ix >= a.W) continue;
-      const float v = __ldg(a.src1 + ((size_t)b * a.H + iy) * a.W + ix);
+    const float* img = a.src1 + (size_t)b * a.H * a.W;
+    float v[kMaxTaps];
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int n = nq * 4 + e;
-        if (n < a.N) acc[e] = fmaf(v, wsm[t * a.N + n], acc[e]);
+    for (int t = 0; t < kMaxTaps; ++t) {           // all taps' loads in flight together
+      v[t] = 0.f;
+      if (t < a.T) {
+        const int iy = oy * a.sy + a.dy[t], ix = ox * a.sx + a.dx[t];
+        if (iy >= 0 && iy < a.H && ix >= 0 && ix < a.W) v[t] = __ldg(img + (size_t)iy * a.W + ix);
+      }
+    }
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int t = 0; t < kMaxTaps; ++t) {
+      if (t < a.T) {
+        const float4 w = *reinterpret_cast<const float4*>(wsm + t * N4 + nq * 4);
+        acc.x = fmaf(v[t], w.x, acc.x); acc.y = fmaf(v[t], w.y, acc.y);
+        acc.z = fmaf(v[t], w.z, acc.z); acc.w = fmaf(v[t], w.w, acc.w);
       }
     }
     const size_t pix = ((size_t)b * a.outH + (oy * a.omy + a.ooy)) * a.outW + (ox * a.omx + a.oox);
+    const float accv[4] = {acc.x, acc.y, acc.z, acc.w};
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       const int n = nq * 4 + e;
       if (n < a.N) {
         const size_t idx = pix * a.N + n;
-        a.out[idx] = conv_epilogue_one(a, acc[e], idx, n);
+        a.out[idx] = conv_epilogue_one(a, accv[e], idx, n);
       }
     }
   }
 }
 
 // LPP lanes cooperate on one pixel (LPP = min(32, Ctot/4)); N <= 4 accumulators per lane, shuffle-reduced.
+// Requires Ctot == 4 * LPP * k; the generic case loops over channel groups.
 __global__ void __launch_bounds__(256) conv_n1_kernel(const __grid_constant__ ConvArgs a, int lpp) {
-  extern __shared__ float wsm[];                 // [N][T][Ctot]
+  extern __shared__ __align__(16) float wsm[];   // [N][T][Ctot]
   const int Ctot = a.C1 + a.C2;
   for (int i = threadIdx.x; i < a.N * a.T * Ctot; i += blockDim.x) wsm[i] = __ldg(a.wp + i);
   __syncthreads();
@@ -291,19 +302,27 @@ __global__ void __launch_bounds__(256) conv_n1_kernel(const __grid_constant__ Co
     const int b = (int)(mm / HoWo), r = (int)(mm - (size_t)b * HoWo);
     const int oy = r / a.Wo, ox = r - oy * a.Wo;
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    if (valid) {
-      for (int t = 0; t < a.T; ++t) {
-        const int iy = oy * a.sy + a.dy[t], ix = ox * a.sx + a.dx[t];
-        if (iy < 0 || iy >= a.H || ix < 0 || ix >= a.W) continue;
-        const size_t pix = ((size_t)b * a.H + iy) * a.W + ix;
-        for (int c = l * 4; c < Ctot; c += lpp * 4) {
-          const float4 v = c < a.C1 ? __ldg(reinterpret_cast<const float4*>(a.src1 + pix * a.C1 + c))
-                                    : __ldg(reinterpret_cast<const float4*>(a.src2 + pix * a.C2 + (c - a.C1)));
+    for (int c = l * 4; c < Ctot; c += lpp * 4) {
+      const float* src = c < a.C1 ? a.src1 + c : a.src2 + (c - a.C1);
+      const int Cs = c < a.C1 ? a.C1 : a.C2;
+      float4 v[kMaxTaps];
+#pragma unroll
+      for (int t = 0; t < kMaxTaps; ++t) {         // all taps' loads in flight together
+        v[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (t < a.T && valid) {
+          const int iy = oy * a.sy + a.dy[t], ix = ox * a.sx + a.dx[t];
+          if (iy >= 0 && iy < a.H && ix >= 0 && ix < a.W)
+            v[t] = __ldg(reinterpret_cast<const float4*>(src + (((size_t)b * a.H + iy) * a.W + ix) * Cs));
+        }
+      }
+#pragma unroll
+      for (int t = 0; t < kMaxTaps; ++t) {
+        if (t < a.T) {
 #pragma unroll
           for (int n = 0; n < 4; ++n) {
             if (n < a.N) {
               const float4 w = *reinterpret_cast<const float4*>(wsm + ((size_t)n * a.T + t) * Ctot + c);
-              acc[n] = fmaf(v.x, w.x, fmaf(v.y, w.y, fmaf(v.z, w.z, fmaf(v.w, w.w, acc[n]))));
+              acc[n] = fmaf(v[t].x, w.x, fmaf(v[t].y, w.y, fmaf(v[t].z, w.z, fmaf(v[t].w, w.w, acc[n]))));
             }
           }
         }
@@ -327,7 +346,8 @@ __global__ void __launch_bounds__(256) conv_n1_kernel(const __grid_constant__ Co
 
 // Thin weight gradient: out[t*st_t + j*st_j] += sum_p V[p][j] * s[p + d_t]  (s: single-channel field of the same
 // spatial size as V's pixel grid, zero outside).  Covers wgrad of Cout = 1 layers (s = dz, V = x, d_t = -tap) and of
-// Cin = 1 layers (s = x, V = dz, d_t = +tap).  Each block reduces a pixel range; one atomicAdd per (t, j) per block.
+// Cin = 1 layers (s = x, V = dz, d_t = +tap).  L = J/4 lanes cover one pixel's J channels with float4 loads (32/L
+// pixels per warp per iteration); block-level reduction in shared memory, one atomicAdd per (t, j) per block.
 struct ThinWgArgs {
   const float* V1;
   const float* V2;
@@ -340,39 +360,59 @@ struct ThinWgArgs {
   int pix_per_block;
 };
 
+template <bool VEC4>
 __global__ void __launch_bounds__(256) thin_wgrad_kernel(const __grid_constant__ ThinWgArgs a) {
+  extern __shared__ float red[];                        // [T][J]
   const int J = a.J1 + a.J2;
   const int HW = a.H * a.W;
   const long long M = (long long)a.B * HW;
   const long long p0 = (long long)blockIdx.x * a.pix_per_block;
   const long long p1 = min(M, p0 + a.pix_per_block);
-  // threads: j = tid % J (channel), lanes of equal j stride over pixels
-  const int jt = threadIdx.x % J, pl = threadIdx.x / J, npl = blockDim.x / J;
-  float acc[kMaxTaps];
+  for (int i = threadIdx.x; i < a.T * J; i += blockDim.x) red[i] = 0.f;
+  __syncthreads();
+  constexpr int E = VEC4 ? 4 : 1;
+  const int L = VEC4 ? (J >> 2) : J;                    // threads per pixel
+  const int pl = threadIdx.x / L, jl = threadIdx.x - pl * L, npl = blockDim.x / L;
+  float acc[kMaxTaps][E];
 #pragma unroll
-  for (int t = 0; t < kMaxTaps; ++t) acc[t] = 0.f;
+  for (int t = 0; t < kMaxTaps; ++t)
+#pragma unroll
+    for (int e = 0; e < E; ++e) acc[t][e] = 0.f;
   if (pl < npl) {
+    const int j = jl * E;
     for (long long p = p0 + pl; p < p1; p += npl) {
-      const float v = jt < a.J1 ? __ldg(a.V1 + p * a.J1 + jt) : __ldg(a.V2 + p * a.J2 + (jt - a.J1));
+      float v[E];
+      if (VEC4) {
+        const float4 t4 = j < a.J1 ? __ldg(reinterpret_cast<const float4*>(a.V1 + p * a.J1 + j))
+                                   : __ldg(reinterpret_cast<const float4*>(a.V2 + p * a.J2 + (j - a.J1)));
+        v[0] = t4.x; if (E > 1) { v[E > 1 ? 1 : 0] = t4.y; v[E > 2 ? 2 : 0] = t4.z; v[E > 3 ? 3 : 0] = t4.w; }
+      } else {
+        v[0] = j < a.J1 ? __ldg(a.V1 + p * a.J1 + j) : __ldg(a.V2 + p * a.J2 + (j - a.J1));
+      }
       const int b = (int)(p / HW), r = (int)(p - (long long)b * HW);
       const int y = r / a.W, x = r - y * a.W;
+      float sv[kMaxTaps];
 #pragma unroll
       for (int t = 0; t < kMaxTaps; ++t) {
+        sv[t] = 0.f;
         if (t < a.T) {
           const int yy = y + a.dy[t], xx = x + a.dx[t];
-          if (yy >= 0 && yy < a.H && xx >= 0 && xx < a.W) acc[t] = fmaf(v, __ldg(a.s + ((size_t)b * a.H + yy) * a.W + xx), acc[t]);
+          if (yy >= 0 && yy < a.H && xx >= 0 && xx < a.W) sv[t] = __ldg(a.s + ((size_t)b * a.H + yy) * a.W + xx);
         }
       }
+#pragma unroll
+      for (int t = 0; t < kMaxTaps; ++t)
+#pragma unroll
+        for (int e = 0; e < E; ++e) acc[t][e] = fmaf(v[e], sv[t], acc[t][e]);
     }
+    for (int t = 0; t < a.T; ++t)
+#pragma unroll
+      for (int e = 0; e < E; ++e) atomicAdd(&red[t * J + j + e], acc[t][e]);
   }
-  __shared__ float red[kMaxTaps][256];
-  for (int t = 0; t < a.T; ++t) red[t][threadIdx.x] = (pl < npl) ? acc[t] : 0.f;
   __syncthreads();
   for (int i = threadIdx.x; i < a.T * J; i += blockDim.x) {
     const int t = i / J, j = i - t * J;
-    float sum = 0.f;
-    for (int q = 0; q < npl; ++q) sum += red[t][q * J + j];
-    atomicAdd(a.out + t * a.st_t + j * a.st_j, sum);
+    atomicAdd(a.out + t * a.st_t + j * a.st_j, red[i]);
   }
 }
 
@@ -396,7 +436,7 @@ int launch_conv(ConvArgs& a, cudaStream_t st) {
   if (Ctot == 1 && a.T * a.N * sizeof(float) <= 40 * 1024) {                 // single-channel source: streaming kernel
     size_t work = (size_t)M * ((a.N + 3) / 4);
     int blocks = (int)std::min<size_t>((work + 255) / 256, (size_t)mtd_sm_count() * 16);
-    conv_c1_kernel<<<blocks, 256, a.T * a.N * sizeof(float), st>>>(a);
+    conv_c1_kernel<<<blocks, 256, a.T * ((a.N + 3) & ~3) * sizeof(float), st>>>(a);
     MTD_CHECK_LAUNCH();
     return MTD_OK;
   }
@@ -520,6 +560,78 @@ __global__ void dot_packed_ref_kernel(const float* __restrict__ gp, const float*
   }
   s = block_sum(s, sh);
   if (threadIdx.x == 0) atomicAdd(acc, s);
+}
+
+
+// ---------------------------------------------------------------------------------------------------
+// Batched weight-gradient finishing: ONE dot launch + ONE unpack launch for all layers of a backward pass
+// (instead of two launches per layer), which also SUMS the contributions of the several forward instances that
+// used the same weight (the discriminator runs 2-4 times inside one d_loss graph) — replacing autograd's
+// per-instance add kernels.  Segment = one (layer, forward instance), 16 x int64: { gp, dw, w_ref, u, v, inv_sigma,
+// N, T, C, sN, sC, flip, sn_cols, dot slot index, next segment of the same weight (-1 = last), 0 };
+// chunk tables (int32[nchunk][2]) = { segment, element offset }: all segments for the dot pass, list heads only
+// for the unpack pass.
+// ---------------------------------------------------------------------------------------------------
+constexpr int kFinChunk = 16384;
+struct FinSeg {
+  const float* gp;
+  float* dw;
+  const float* w;
+  const float* u;
+  const float* v;
+  const float* inv_sigma;
+  long long N, T, C, sN, sC, flip, sn_cols, slot, next, pad1;
+};
+static_assert(sizeof(FinSeg) == 128, "finish segment must be 16 x int64");
+
+__device__ __forceinline__ size_t fin_ref_index(const FinSeg& s, size_t i) {
+  const int c = (int)(i % s.C);
+  const size_t r = i / s.C;
+  const int t = (int)(r % s.T);
+  const size_t n = r / s.T;
+  const long long toff = s.flip ? (s.T - 1 - t) : t;
+  return n * (size_t)s.sN + (size_t)c * s.sC + toff;
+}
+
+__global__ void __launch_bounds__(256) finish_dot_kernel(const FinSeg* __restrict__ segs, const int2* __restrict__ chunks,
+                                                         double* __restrict__ dots) {
+  __shared__ double sh[32];
+  const int2 ck = chunks[blockIdx.x];
+  const FinSeg s = segs[ck.x];
+  if (!s.inv_sigma) return;                         // uniform per block
+  const size_t total = (size_t)s.N * s.T * s.C;
+  const size_t end = min(total, (size_t)ck.y + kFinChunk);
+  double acc = 0.0;
+  for (size_t i = (size_t)ck.y + threadIdx.x; i < end; i += blockDim.x)
+    acc += (double)s.gp[i] * (double)__ldg(s.w + fin_ref_index(s, i));
+  acc = block_sum(acc, sh);
+  if (threadIdx.x == 0) atomicAdd(dots + s.slot, acc);
+}
+
+__global__ void __launch_bounds__(256) finish_unpack_kernel(const FinSeg* __restrict__ segs, const int2* __restrict__ chunks,
+                                                            const double* __restrict__ dots) {
+  const int2 ck = chunks[blockIdx.x];
+  const FinSeg head = segs[ck.x];
+  const size_t total = (size_t)head.N * head.T * head.C;
+  const size_t end = min(total, (size_t)ck.y + kFinChunk);
+  for (size_t i = (size_t)ck.y + threadIdx.x; i < end; i += blockDim.x) {
+    const size_t ref = fin_ref_index(head, i);
+    float sum = 0.f;
+    long long si = ck.x;
+    while (si >= 0) {                                   // every forward instance that used this weight
+      const FinSeg& s = segs[si];
+      float g = s.gp[i];
+      if (s.inv_sigma) {
+        const float alpha = __ldg(s.inv_sigma);
+        const float beta = (float)dots[s.slot] * alpha;
+        const size_t row = ref / (size_t)s.sn_cols, col = ref - row * (size_t)s.sn_cols;
+        g = alpha * (g - beta * __ldg(s.u + row) * __ldg(s.v + col));
+      }
+      sum += g;
+      si = s.next;
+    }
+    head.dw[ref] = sum;
+  }
 }
 
 // Fill the (sN, sC, toff) mapping for a reference weight tensor.
@@ -912,7 +1024,11 @@ int mtd_conv_wgrad(const float* x1, const float* x2, const float* dz, float* gp,
     w.pix_per_block = (int)((M + blocks - 1) / blocks);
     blocks = (int)((M + w.pix_per_block - 1) / w.pix_per_block);
     MTD_CUDA(cudaMemsetAsync(gp, 0, (size_t)N * a.T * Ctot * sizeof(float), st));
-    thin_wgrad_kernel<<<blocks, 256, 0, st>>>(w);
+    const int J = w.J1 + w.J2;
+    const bool vec4 = (w.J1 % 4 == 0) && (w.J2 % 4 == 0) && J >= 4 && mtd_aligned16(w.V1) && (!w.V2 || mtd_aligned16(w.V2));
+    const size_t smem = (size_t)a.T * J * sizeof(float);
+    if (vec4) thin_wgrad_kernel<true><<<blocks, 256, smem, st>>>(w);
+    else thin_wgrad_kernel<false><<<blocks, 256, smem, st>>>(w);
     MTD_CHECK_LAUNCH();
     return MTD_OK;
   }
@@ -966,6 +1082,26 @@ int mtd_act_bwd(const float* dy, const float* y, float* dz, float* dbias, long l
     }
   }
   act_bwd_kernel<<<blocks, 256, dbias ? N * sizeof(float) : 0, st>>>(dy, y, dz, dbias, total, N, act, slope);
+  MTD_CHECK_LAUNCH();
+  return MTD_OK;
+}
+
+int mtd_wgrad_finish_chunk_elems(void) { return kFinChunk; }
+
+// Batched form of mtd_conv_wgrad_finish (same arithmetic).  dots: n_segs doubles of device scratch (zeroed here).
+int mtd_wgrad_finish_batched(const void* seg_tab, int n_segs, const void* dot_chunks, int n_dot_chunks, const void* head_chunks,
+                             int n_head_chunks, double* dots, void* stream) {
+  MTD_REQUIRE(seg_tab && head_chunks && dots && n_segs > 0 && n_head_chunks > 0);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n_dot_chunks > 0) {
+    MTD_REQUIRE(dot_chunks);
+    MTD_CUDA(cudaMemsetAsync(dots, 0, (size_t)n_segs * sizeof(double), st));
+    finish_dot_kernel<<<n_dot_chunks, 256, 0, st>>>(reinterpret_cast<const FinSeg*>(seg_tab),
+                                                    reinterpret_cast<const int2*>(dot_chunks), dots);
+    MTD_CHECK_LAUNCH();
+  }
+  finish_unpack_kernel<<<n_head_chunks, 256, 0, st>>>(reinterpret_cast<const FinSeg*>(seg_tab),
+                                                      reinterpret_cast<const int2*>(head_chunks), dots);
   MTD_CHECK_LAUNCH();
   return MTD_OK;
 }

@@ -97,6 +97,61 @@ def _wgrad_wanted(weight) -> bool:
     return _wgrad_filter is None or weight.data_ptr() in _wgrad_filter
 
 
+# Deferred weight-gradient finishing.  Inside `deferred_wgrad_finish()` (the PCGrad driver wraps each of its
+# torch.autograd.grad calls in one) a layer only queues its packed gradient.  The FIRST forward instance of a weight
+# to run its backward returns the (still unfilled) dw tensor, later instances of the same weight return None, and
+# when the context exits one batched dot + one batched unpack launch finish every layer AND sum the instances —
+# replacing ~500 per-layer launches and autograd's ~600 gradient-accumulation adds per train step.  The dw tensors
+# are only consumed after autograd.grad returns, so filling them late is safe; under plain `.backward()`
+# (AccumulateGrad may clone or accumulate immediately) finishing stays immediate.
+_finish_queue = None          # None, or {weight data_ptr: (dw, [instance tuples])}
+_fin_chunk_cache: dict = {}
+
+
+class deferred_wgrad_finish:
+    def __enter__(self):
+        global _finish_queue
+        self.prev, _finish_queue = _finish_queue, {}
+        return self
+
+    def __exit__(self, *exc):
+        global _finish_queue
+        q, _finish_queue = _finish_queue, self.prev
+        if q and exc[0] is None:
+            _flush_finish(q)
+        return False
+
+
+def _flush_finish(groups):
+    first = next(iter(groups.values()))
+    dev = first[0].device
+    rows, dot_numels, head_numels, heads = [], [], [], []
+    for dw, insts in groups.values():
+        base = len(rows)
+        heads.append(base)
+        head_numels.append(dw.numel())
+        for k, (gp, w, u, v, inv, cfg) in enumerate(insts):
+            T = cfg.kh * cfg.kw
+            sN, sC, flip = (T, cfg.cout * T, 1) if cfg.transposed else (cfg.cin * T, T, 0)
+            sn = inv is not None
+            rows.append([gp.data_ptr(), dw.data_ptr(), w.data_ptr() if sn else 0, u.data_ptr() if sn else 0,
+                         v.data_ptr() if sn else 0, inv.data_ptr() if sn else 0, cfg.cout, T, cfg.cin, sN, sC, flip,
+                         cfg.cin * T, base + k, base + k + 1 if k + 1 < len(insts) else -1, 0])
+            dot_numels.append(gp.numel() if sn else 0)
+    key = (tuple(dot_numels), tuple(heads), str(dev))
+    ent = _fin_chunk_cache.get(key)
+    if ent is None:
+        ck = _ext.load().mtd_wgrad_finish_chunk_elems()
+        dchunks = [[s_, off] for s_, n in enumerate(dot_numels) for off in range(0, n, ck)]
+        hchunks = [[h, off] for h, n in zip(heads, head_numels) for off in range(0, n, ck)]
+        ent = (_ext.device_table(dchunks, torch.int32, dev) if dchunks else None, len(dchunks),
+               _ext.device_table(hchunks, torch.int32, dev), len(hchunks))
+        _fin_chunk_cache[key] = ent
+    seg = _ext.device_table(rows, torch.int64, dev)
+    dots = torch.empty(len(rows), dtype=torch.float64, device=dev)
+    call("mtd_wgrad_finish_batched", ptr(seg), len(rows), ptr(ent[0]), ent[1], ptr(ent[2]), ent[3], ptr(dots), stream())
+
+
 @dataclass(frozen=True)
 class ConvCfg:
     cin: int                 # total input channels (C1 + C2)
@@ -271,11 +326,20 @@ class ConvFn(Function):
         if need[2] and _wgrad_wanted(weight):
             gp = _empty((weight.numel(),), dy)
             _conv_wgrad_launch(x1, x2, dz, gp, B, H, W, C1, C2, cfg)
-            dw = torch.empty_like(weight)
-            scratch = torch.empty(4, dtype=torch.float32, device=dy.device) if inv_sigma is not None else None
-            call("mtd_conv_wgrad_finish", fptr(gp), fptr(dw), cfg.transposed, cfg.cout, cfg.cin, cfg.kh, cfg.kw,
-                 fptr(weight.detach()) if inv_sigma is not None else None, fptr(u), fptr(v), fptr(inv_sigma), ptr(scratch),
-                 st)
+            if _finish_queue is not None:
+                grp = _finish_queue.get(weight.data_ptr())
+                inst = (gp, weight.detach(), u, v, inv_sigma, cfg)
+                if grp is None:
+                    dw = torch.empty_like(weight)
+                    _finish_queue[weight.data_ptr()] = (dw, [inst])
+                else:
+                    grp[1].append(inst)            # summed into the first instance's dw by the batched unpack
+            else:
+                dw = torch.empty_like(weight)
+                scratch = torch.empty(4, dtype=torch.float32, device=dy.device) if inv_sigma is not None else None
+                call("mtd_conv_wgrad_finish", fptr(gp), fptr(dw), cfg.transposed, cfg.cout, cfg.cin, cfg.kh, cfg.kw,
+                     fptr(weight.detach()) if inv_sigma is not None else None, fptr(u), fptr(v), fptr(inv_sigma),
+                     ptr(scratch), st)
         d_add1 = d_add if (need[7] and not cfg.fuse_add1_is_input) else None
         d_add2 = d_add if need[8] else None
         return dx1, dx2, dw, dbias, None, None, None, d_add1, d_add2, None

@@ -18,7 +18,7 @@ import torch
 from . import _ext
 from . import distributed as mdist
 from ._ext import call, fptr, ptr, stream
-from .ops import wgrad_only_for
+from .ops import deferred_wgrad_finish, wgrad_only_for
 
 
 def draw_visit_orders(n_tasks: int, rng=None) -> List[List[int]]:
@@ -171,8 +171,11 @@ class PCGrad(WeightMethod):
             shared_parameters = [shared_parameters]
         shared_parameters = list(shared_parameters)
         # shared part (:431-439): one backward pass per task, weight-gradient GEMMs only for the shared set
+        shared_grads = []
         with wgrad_only_for(shared_parameters):
-            shared_grads = [torch.autograd.grad(l, shared_parameters, retain_graph=True) for l in losses]
+            for l in losses:
+                with deferred_wgrad_finish():        # one batched finishing pass per task backward
+                    shared_grads.append(torch.autograd.grad(l, shared_parameters, retain_graph=True))
         merged = self._project_conflicting(shared_grads)
         for p, g in zip(shared_parameters, merged):
             p.grad = g
@@ -181,7 +184,7 @@ class PCGrad(WeightMethod):
             if isinstance(task_specific_parameters, torch.Tensor):
                 task_specific_parameters = [task_specific_parameters]
             task_specific_parameters = list(task_specific_parameters)
-            with wgrad_only_for(task_specific_parameters):
+            with wgrad_only_for(task_specific_parameters), deferred_wgrad_finish():
                 ts_grads = torch.autograd.grad(losses.sum(), task_specific_parameters)
             if mdist.active():
                 ts_grads = mdist.allreduce_mean_list(ts_grads)
