@@ -82,6 +82,9 @@ int mtd_act_bwd(const float* dy, const float* y, float* dz, float* dbias, long l
  * uses mtd_conv_fwd).  passes = 1: TF32 operands, fp32 accumulate (rel. error <= 2e-3), wp tf32-rounded;
  * passes = 3: error-compensated 3xTF32 (fp32-grade, <= 1e-5), wp = [hi | lo] from mtd_split_tf32.  */
 int mtd_conv_fwd_tc_supported(int B, int H, int W, int C1, int C2, int N, int kh, int kw, int stride, int pad);
+/* kernel generation of the forward/dgrad tensor-core path: 1 = A through shared memory, 2 = A through TMEM with
+ * several pixel tiles per CTA (weights streamed once per group).  Returns the previous setting.              */
+int mtd_tc_set_version(int version);
 /* in-place round-to-nearest fp32 -> tf32 of a packed weight buffer (tcgen05 truncates its operands)  */
 int mtd_round_tf32(float* p, long long n, void* stream);
 int mtd_conv_fwd_tc(const float* x1, const float* x2, const float* wp, const float* bias, const float* scale, float* y,

@@ -50,6 +50,7 @@ struct TcArgs {
   int wrows_total;              // rows of the full packed weight buffer (offset of the lo half, passes == 3)
   int ksplit, kper;             // split-K: tile = mn_tile * ksplit + ks, k-steps [ks*kper, (ks+1)*kper)
   int inH, inW, es;             // input tensor dims and conv stride (A tile = TMA box with elementStrides es)
+  int m_tiles, n_groups, ra, rb; // v2 kernel: pixel tiles, groups of MT pixel tiles, raw-A / B ring depths
   int outH, outW, omy, omx, ooy, oox;   // output pixel = (h*omy+ooy, w*omx+oox) in a (B,outH,outW,N) tensor
   float* out;
   const float* scale;
@@ -379,6 +380,310 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
   }
 }
 
+
+// =====================================================================================================
+// v2 forward / dgrad kernel: A operand through TENSOR MEMORY, several pixel tiles per CTA.
+//
+// v1 keeps A_hi / A_lo in shared memory, which (with the 3xTF32 operand doubling) leaves room for only 2-5
+// pipeline stages and makes every pixel tile re-stream the weights from L2.  Here
+//   * TMA lands the raw fp32 A tile (16 KB) in a deep shared-memory ring;
+//   * the rounding warps read their own row (lane = pixel = TMEM lane, de-swizzled LDS.128), split it into
+//     tf32 hi / lo and write it with tcgen05.st into a 2-slot A ring in TMEM — the MMA takes A from TMEM
+//     (tcgen05.mma [d], [a_tmem], b_desc), so shared memory only holds raw A and the weight tiles;
+//   * each weight stage (B_hi | B_lo) is used by MT pixel tiles with MT accumulators in TMEM (MT*BN columns):
+//     weight traffic per FLOP drops by MT, and a skinny-M layer (<= MT pixel tiles) streams its weights once.
+// TMEM budget: MT*BN accumulator columns + 2 * (32 | 64) A-ring columns <= 512.
+// =====================================================================================================
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
+        "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]),
+        "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]),
+        "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+      : "memory");
+}
+
+__device__ __forceinline__ void tc_epilogue_chunk(const TcArgs& a, const uint32_t (&v)[32], bool valid, size_t rowoff, int n0,
+                                                  int c0, float scale) {
+  if (valid && a.ksplit > 1) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) atomicAdd(a.out + rowoff + c0 + j, __uint_as_float(v[j]));
+  } else if (valid) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      const size_t idx = rowoff + c0 + j;
+      float o[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float x = __uint_as_float(v[j + e]) * scale;
+        if (a.bias) x += __ldg(a.bias + n0 + c0 + j + e);
+        o[e] = mtd_act(x, a.pre_act, a.slope);
+      }
+      if (a.aux) *reinterpret_cast<float4*>(a.aux + idx) = make_float4(o[0], o[1], o[2], o[3]);
+      if (a.add1) { float4 t = __ldg(reinterpret_cast<const float4*>(a.add1 + idx)); o[0] += t.x; o[1] += t.y; o[2] += t.z; o[3] += t.w; }
+      if (a.add2) { float4 t = __ldg(reinterpret_cast<const float4*>(a.add2 + idx)); o[0] += t.x; o[1] += t.y; o[2] += t.z; o[3] += t.w; }
+#pragma unroll
+      for (int e = 0; e < 4; ++e) o[e] = mtd_act(o[e], a.post_act, a.slope);
+      if (a.mask_src) {
+        float4 t = __ldg(reinterpret_cast<const float4*>(a.mask_src + idx));
+        o[0] *= mtd_act_grad(t.x, a.mask_act, a.slope); o[1] *= mtd_act_grad(t.y, a.mask_act, a.slope);
+        o[2] *= mtd_act_grad(t.z, a.mask_act, a.slope); o[3] *= mtd_act_grad(t.w, a.mask_act, a.slope);
+      }
+      *reinterpret_cast<float4*>(a.out + idx) = make_float4(o[0], o[1], o[2], o[3]);
+    }
+  }
+}
+
+__host__ __device__ constexpr uint32_t next_pow2_cols(uint32_t c) { return c <= 32 ? 32 : c <= 64 ? 64 : c <= 128 ? 128 : c <= 256 ? 256 : 512; }
+
+template <int BN, int MT, int NPASS>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUtensorMap mapA2,
+                const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapBlo,
+                const __grid_constant__ TcArgs a) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  constexpr int kNB = NPASS == 3 ? 2 : 1;
+  constexpr int kBBytes = kNB * BN * 128;                        // B_hi (| B_lo) per k-step
+  constexpr uint32_t kACols = kNB * 32;                          // A_hi (| A_lo) columns per TMEM A slot
+  constexpr uint32_t kAccCols = MT * BN;
+  constexpr uint32_t kTmemCols = next_pow2_cols(kAccCols + 2 * kACols);
+  static_assert(kAccCols + 2 * kACols <= 512, "TMEM budget exceeded");
+
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int RA = a.ra, RB = a.rb;
+  const uint32_t b_base = base + (uint32_t)RA * kABytes;
+  const uint32_t bar_base = b_base + (uint32_t)RB * kBBytes;
+  auto rfull = [&](int s) { return bar_base + 8u * s; };
+  auto rempty = [&](int s) { return bar_base + 8u * (RA + s); };
+  auto bfull = [&](int s) { return bar_base + 8u * (2 * RA + s); };
+  auto bempty = [&](int s) { return bar_base + 8u * (2 * RA + RB + s); };
+  auto afull = [&](int s) { return bar_base + 8u * (2 * RA + 2 * RB + s); };
+  auto aempty = [&](int s) { return bar_base + 8u * (2 * RA + 2 * RB + 2 + s); };
+  const uint32_t tfull = bar_base + 8u * (2 * RA + 2 * RB + 4);
+  const uint32_t tempty = tfull + 8u;
+  const uint32_t tmem_slot = tfull + 16u;
+  unsigned char* gen_base = smem_raw + (base - smem_u32(smem_raw));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kchunks = a.kc1 + a.kc2;
+  const int kiters = a.T * kchunks;
+  const int Ctot = kchunks * 32;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&mapA1);
+    if (a.kc2) prefetch_tmap(&mapA2);
+    prefetch_tmap(&mapB);
+    if (NPASS == 3) prefetch_tmap(&mapBlo);
+    for (int s = 0; s < RA; ++s) { mbar_init(rfull(s), 1); mbar_init(rempty(s), 4); }
+    for (int s = 0; s < RB; ++s) { mbar_init(bfull(s), 1); mbar_init(bempty(s), 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(afull(s), 4); mbar_init(aempty(s), 1); }
+    mbar_init(tfull, 1);
+    mbar_init(tempty, 4);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(kTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gen_base + (tmem_slot - base));
+  const uint32_t tmem_a0 = tmem_base + kAccCols;
+
+  // tile = (group * n_nt + nt) * ksplit + ks ; group g covers pixel tiles g*MT .. g*MT+MT-1
+  auto decode_tile = [&](int tile, int& g, int& n0, int& k_begin, int& k_end) {
+    const int ks = tile % a.ksplit;
+    tile /= a.ksplit;
+    k_begin = ks * a.kper;
+    k_end = min(kiters, k_begin + a.kper);
+    n0 = (tile % a.n_nt) * BN;
+    g = tile / a.n_nt;
+  };
+  auto decode_mtile = [&](int mt, int& b0, int& h0, int& w0) {
+    int mw = mt % a.n_wt;
+    mt /= a.n_wt;
+    int mh = mt % a.n_ht, mb = mt / a.n_ht;
+    b0 = mb * a.TB; h0 = mh * a.TH; w0 = mw * a.TW;
+  };
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      PipeState sr, sb;
+      for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+        int g, n0, k_begin, k_end;
+        decode_tile(tile, g, n0, k_begin, k_end);
+        for (int it = k_begin; it < k_end; ++it) {
+          const int t = it / kchunks, cc = it - t * kchunks;
+          mbar_wait(bempty(sb.stage), sb.phase ^ 1u);
+          mbar_expect_tx(bfull(sb.stage), kBBytes);
+          const uint32_t sbm = b_base + (uint32_t)sb.stage * kBBytes;
+          tma_load_2d(&mapB, sbm, bfull(sb.stage), t * Ctot + cc * 32, n0);
+          if (NPASS == 3) tma_load_2d(&mapBlo, sbm + BN * 128, bfull(sb.stage), t * Ctot + cc * 32, n0);
+          sb.advance(RB);
+#pragma unroll 1
+          for (int j = 0; j < MT; ++j) {
+            const int mt = g * MT + j;
+            if (mt >= a.m_tiles) break;
+            int b0, h0, w0;
+            decode_mtile(mt, b0, h0, w0);
+            mbar_wait(rempty(sr.stage), sr.phase ^ 1u);
+            mbar_expect_tx(rfull(sr.stage), kABytes);
+            const uint32_t sam = base + (uint32_t)sr.stage * kABytes;
+            if (cc < a.kc1) tma_load_4d(&mapA1, sam, rfull(sr.stage), cc * 32, w0 * a.es + a.dx[t], h0 * a.es + a.dy[t], b0);
+            else tma_load_4d(&mapA2, sam, rfull(sr.stage), (cc - a.kc1) * 32, w0 * a.es + a.dx[t], h0 * a.es + a.dy[t], b0);
+            sr.advance(RA);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer: A from TMEM, B from shared memory =====
+    if (lane == 0) {
+      PipeState sb, sa;
+      constexpr uint32_t idesc = make_idesc(BN);
+      int lt = 0;
+      for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++lt) {
+        int g, n0, k_begin, k_end;
+        decode_tile(tile, g, n0, k_begin, k_end);
+        mbar_wait(tempty, ((uint32_t)lt & 1u) ^ 1u);
+        tc_fence_after();
+        for (int it = k_begin; it < k_end; ++it) {
+          mbar_wait(bfull(sb.stage), sb.phase);
+          const uint32_t sbm = b_base + (uint32_t)sb.stage * kBBytes;
+          const uint64_t db = make_sw128_desc(sbm), dbl = make_sw128_desc(sbm + BN * 128);
+#pragma unroll 1
+          for (int j = 0; j < MT; ++j) {
+            if (g * MT + j >= a.m_tiles) break;
+            mbar_wait(afull(sa.stage), sa.phase);
+            tc_fence_after();
+            const uint32_t a_hi = tmem_a0 + (uint32_t)sa.stage * kACols, a_lo = a_hi + 32;
+            const uint32_t d = tmem_base + (uint32_t)(j * BN);
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+              const uint32_t accum = (it > k_begin || kk > 0) ? 1u : 0u;
+              if (NPASS == 3) {
+                umma_tf32_ts(d, a_lo + 8u * kk, db + 2u * kk, idesc, accum);
+                umma_tf32_ts(d, a_hi + 8u * kk, dbl + 2u * kk, idesc, 1u);
+                umma_tf32_ts(d, a_hi + 8u * kk, db + 2u * kk, idesc, 1u);
+              } else {
+                umma_tf32_ts(d, a_hi + 8u * kk, db + 2u * kk, idesc, accum);
+              }
+            }
+            umma_commit(aempty(sa.stage));
+            sa.advance(2);
+          }
+          umma_commit(bempty(sb.stage));
+          sb.advance(RB);
+        }
+        umma_commit(tfull);
+      }
+    }
+  } else if (warp < 6) {
+    // ===== operand split: own row of the raw A tile -> tf32 hi / lo -> TMEM =====
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    PipeState sr, sa;
+    for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+      int g, n0, k_begin, k_end;
+      decode_tile(tile, g, n0, k_begin, k_end);
+      for (int it = k_begin; it < k_end; ++it) {
+#pragma unroll 1
+        for (int j = 0; j < MT; ++j) {
+          if (g * MT + j >= a.m_tiles) break;
+          mbar_wait(rfull(sr.stage), sr.phase);
+          const unsigned char* rowp = gen_base + (size_t)sr.stage * kABytes + (size_t)row * 128;
+          uint32_t hi[32], lo[32];
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {                 // logical 16-byte chunk c lives at physical chunk c ^ (row & 7)
+            const float4 v = *reinterpret_cast<const float4*>(rowp + ((c ^ (row & 7)) << 4));
+            const float f[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              uint32_t h;
+              asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(f[e]));
+              hi[c * 4 + e] = h;
+              if (NPASS == 3) {
+                uint32_t l;
+                asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(f[e] - __uint_as_float(h)));
+                lo[c * 4 + e] = l;
+              }
+            }
+          }
+          mbar_wait(aempty(sa.stage), sa.phase ^ 1u);     // the MMAs that read this TMEM slot have completed
+          tc_fence_after();
+          const uint32_t ta = tmem_a0 + lane_addr + (uint32_t)sa.stage * kACols;
+          tmem_st32(ta, hi);
+          if (NPASS == 3) tmem_st32(ta + 32, lo);
+          asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            mbar_arrive(rempty(sr.stage));                // raw slot may be refilled by TMA
+            mbar_arrive(afull(sa.stage));
+          }
+          sr.advance(RA);
+          sa.advance(2);
+        }
+      }
+    }
+  } else {
+    // ===== epilogue =====
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const int bl = r / (a.TH * a.TW), rem = r - bl * (a.TH * a.TW);
+    const int hl = rem / a.TW, wl = rem - hl * a.TW;
+    const float scale = a.scale ? __ldg(a.scale) : 1.f;
+    int lt = 0;
+    for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++lt) {
+      int g, n0, k_begin, k_end;
+      decode_tile(tile, g, n0, k_begin, k_end);
+      mbar_wait(tfull, (uint32_t)lt & 1u);
+      tc_fence_after();
+#pragma unroll 1
+      for (int j = 0; j < MT; ++j) {
+        const int mt = g * MT + j;
+        if (mt >= a.m_tiles) break;
+        int b0, h0, w0;
+        decode_mtile(mt, b0, h0, w0);
+        const int b = b0 + bl;
+        const bool valid = b < a.B;
+        const size_t rowoff =
+            (((size_t)b * a.outH + ((h0 + hl) * a.omy + a.ooy)) * a.outW + ((w0 + wl) * a.omx + a.oox)) * a.N + n0;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(j * BN + c0), v);
+          tc_epilogue_chunk(a, v, valid, rowoff, n0, c0, scale);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+  }
+}
+
 // second phase of a split-K launch: `out` holds raw sums over a dense (B,outH,outW,N) tensor
 __global__ void tc_finish_kernel(const __grid_constant__ TcArgs a, size_t total) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
@@ -550,6 +855,64 @@ void choose_tiling(int m_tiles, int N, int kiters, int passes, int force_split, 
   *ksplit_out = ksplit;
 }
 
+
+// ---- v2 host side -------------------------------------------------------------------------------------
+int g_tc_version = 1;      // 1: A through shared memory (conv_tc_kernel); 2: A through TMEM, MT pixel tiles per CTA
+
+struct V2Cfg { int bn, mt; };
+constexpr V2Cfg kV2Cfgs[3] = {{128, 3}, {64, 6}, {32, 8}};
+
+void choose_tiling_v2(int m_tiles, int N, int kiters, int passes, int force_split, int* cfg_out, int* ksplit_out) {
+  const int sms = mtd_sm_count();
+  double best = 1e30;
+  int bc = -1, bks = 1;
+  for (int ci = 0; ci < 3; ++ci) {
+    const int bn = kV2Cfgs[ci].bn, mt = kV2Cfgs[ci].mt;
+    if (N % bn) continue;
+    const int groups = (m_tiles + mt - 1) / mt;
+    const double mtv = (double)m_tiles / groups;                      // average pixel tiles per group
+    const int mn = groups * (N / bn);
+    const double mma = mtv * (passes == 3 ? 12.0 : 4.0) * (bn / 2.0);  // cycles: 4 k-slices x passes, 128 x bn x 8 each
+    const double byt = (mtv * 16.0 + (passes == 3 ? 2.0 : 1.0) * bn / 8.0) * 1024.0 / 36.0;
+    double t_step = mma > byt ? mma : byt;
+    if (t_step < 1200.0) t_step = 1200.0;
+    int ks = 1;
+    if (force_split > 0) ks = force_split;
+    else if (mn < sms && kiters >= 8) {
+      ks = sms / mn;
+      if (ks > kiters / 2) ks = kiters / 2;
+      if (ks < 1) ks = 1;
+    }
+    const int kper = (kiters + ks - 1) / ks;
+    ks = (kiters + kper - 1) / kper;
+    const int rounds = (mn * ks + sms - 1) / sms;
+    const double cost = (double)rounds * (kper * t_step + mtv * bn * 24.0 + 4000.0) + (ks > 1 ? 8000.0 : 0.0);
+    if (cost < best) { best = cost; bc = ci; bks = ks; }
+  }
+  *cfg_out = bc;
+  *ksplit_out = bks;
+}
+
+template <int BN, int MT, int NPASS>
+int launch_v2(const CUtensorMap& mA1, const CUtensorMap& mA2, const CUtensorMap& mB, const CUtensorMap& mBlo, TcArgs& a,
+              cudaStream_t st) {
+  const int b_bytes = (NPASS == 3 ? 2 : 1) * BN * 128;
+  a.rb = 2;
+  int ra = (200 * 1024 - a.rb * b_bytes) / kABytes;
+  if (ra > 10) ra = 10;
+  a.ra = ra;
+  size_t smem = 1024 + (size_t)a.ra * kABytes + (size_t)a.rb * b_bytes + 8 * (2 * a.ra + 2 * a.rb + 8);
+  static bool attr_set = false;
+  if (!attr_set) {
+    MTD_CUDA(cudaFuncSetAttribute(conv_tc2_kernel<BN, MT, NPASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  int grid = a.n_tiles < mtd_sm_count() ? a.n_tiles : mtd_sm_count();
+  conv_tc2_kernel<BN, MT, NPASS><<<grid, kThreads, smem, st>>>(mA1, mA2, mB, mBlo, a);
+  MTD_CHECK_LAUNCH();
+  return MTD_OK;
+}
+
 // wp: packed weights [N][T][C]; for passes == 3 the buffer holds [hi | lo] (2 x N*T*C floats, mtd_split_tf32).
 // `finish`: run the split-K finishing pass here (false when the caller batches several launches into one
 // output, e.g. the four parity classes of a stride-2 dgrad).  Returns the chosen ksplit through a.ksplit.
@@ -563,10 +926,18 @@ int launch_tc(const float* x1, const float* x2, const float* wp, int passes, TcA
   a.kc1 = a.C1 / 32; a.kc2 = a.C2 / 32;
   const int kiters = a.T * (a.kc1 + a.kc2);
   const int sms = mtd_sm_count();
-  int BN = 32, ksplit = 1;
-  choose_tiling(m_tiles, a.N, kiters, passes, force_split, &BN, &ksplit);
+  int BN = 32, ksplit = 1, v2cfg = -1;
+  a.m_tiles = m_tiles;
+  if (g_tc_version == 2) {
+    choose_tiling_v2(m_tiles, a.N, kiters, passes, force_split, &v2cfg, &ksplit);
+    if (v2cfg < 0) return MTD_EINVAL;
+    BN = kV2Cfgs[v2cfg].bn;
+    a.n_groups = (m_tiles + kV2Cfgs[v2cfg].mt - 1) / kV2Cfgs[v2cfg].mt;
+  } else {
+    choose_tiling(m_tiles, a.N, kiters, passes, force_split, &BN, &ksplit);
+  }
   a.n_nt = a.N / BN;
-  int mn_tiles = m_tiles * a.n_nt;
+  int mn_tiles = (v2cfg >= 0 ? a.n_groups : m_tiles) * a.n_nt;
   a.kper = (kiters + ksplit - 1) / ksplit;
   ksplit = (kiters + a.kper - 1) / a.kper;          // no empty splits
   a.ksplit = ksplit;
@@ -590,10 +961,16 @@ int launch_tc(const float* x1, const float* x2, const float* wp, int passes, TcA
   }
 #define TC_DISPATCH(BN_)                                                           \
   rc = passes == 3 ? launch_bn<BN_, 3>(mA1, mA2, mB, mBlo, a, st) : launch_bn<BN_, 1>(mA1, mA2, mB, mBlo, a, st)
-  if (BN == 128) { TC_DISPATCH(128); }
+#define TC2_DISPATCH(BN_, MT_)                                                     \
+  rc = passes == 3 ? launch_v2<BN_, MT_, 3>(mA1, mA2, mB, mBlo, a, st) : launch_v2<BN_, MT_, 1>(mA1, mA2, mB, mBlo, a, st)
+  if (v2cfg == 0) { TC2_DISPATCH(128, 3); }
+  else if (v2cfg == 1) { TC2_DISPATCH(64, 6); }
+  else if (v2cfg == 2) { TC2_DISPATCH(32, 8); }
+  else if (BN == 128) { TC_DISPATCH(128); }
   else if (BN == 64) { TC_DISPATCH(64); }
   else { TC_DISPATCH(32); }
 #undef TC_DISPATCH
+#undef TC2_DISPATCH
   if (rc) return rc;
   if (ksplit > 1 && finish) {
     int blocks = (int)((total + 255) / 256);
@@ -913,6 +1290,14 @@ __global__ void round_tf32_kernel(float* __restrict__ p, size_t n) {
 
 extern "C" {
 
+// 1 = A operand through shared memory (conv_tc_kernel), 2 = A operand through TMEM with several pixel tiles per CTA
+// (conv_tc2_kernel).  Process-wide; returns the previous value.
+int mtd_tc_set_version(int version) {
+  int prev = g_tc_version;
+  if (version == 1 || version == 2) g_tc_version = version;
+  return prev;
+}
+
 int mtd_conv_fwd_tc_supported(int B, int H, int W, int C1, int C2, int N, int kh, int kw, int stride, int pad) {
   int tw, th, tb;
   return tc_geometry(B, H, W, C1, C2, N, kh, kw, stride, pad, &tw, &th, &tb) && get_encode() != nullptr ? 1 : 0;
@@ -1005,7 +1390,8 @@ int mtd_conv_dgrad_tc(const float* dz, const float* wpd, float* dx, const float*
         TcArgs probe = c;
         probe.n_wt = probe.W / tw; probe.n_ht = probe.H / th; probe.n_bt = (B + tb - 1) / tb;
         int m_tiles = probe.n_wt * probe.n_ht * probe.n_bt, kiters = 4 * (Cout / 32), bn_unused = 32;
-        choose_tiling(m_tiles, Cin, kiters, passes, 0, &bn_unused, &ksplit);
+        if (g_tc_version == 2) choose_tiling_v2(m_tiles, Cin, kiters, passes, 0, &bn_unused, &ksplit);
+        else choose_tiling(m_tiles, Cin, kiters, passes, 0, &bn_unused, &ksplit);
         if (ksplit > 1) MTD_CUDA(cudaMemsetAsync(dx, 0, total * sizeof(float), st));
       }
       int rc = launch_tc(dz, nullptr, wpd + (size_t)(py * 2 + px) * cls_elems, passes, c, st, ksplit, false);

@@ -176,6 +176,11 @@ _TC_PASSES = 1 if os.environ.get("MTDGAN_TF32", "x3") == "x1" else 3
 _WGRAD_PASSES = 3 if os.environ.get("MTDGAN_WGRAD_TF32", "x1") == "x3" else 1
 
 
+def set_tc_version(version: int) -> int:
+    """Forward/dgrad tensor-core kernel generation (1: A through shared memory, 2: A through TMEM, multi-tile)."""
+    return _ext.load().mtd_tc_set_version(int(version))
+
+
 def set_wgrad_passes(passes: int):
     global _WGRAD_PASSES
     assert passes in (1, 3)

@@ -112,9 +112,19 @@ TC_CASES = [
 ]
 
 
+@pytest.fixture(params=[1, 2], ids=["v1_smemA", "v2_tmemA"])
+def tc_version(request):
+    """Both generations of the forward/dgrad tensor-core kernel: v1 keeps the rounded A tile in shared memory, v2
+    writes it to TMEM (tcgen05.st) and shares every weight stage among several pixel tiles."""
+    from mtdgan_b200 import ops
+    prev = ops.set_tc_version(request.param)
+    yield request.param
+    ops.set_tc_version(prev)
+
+
 @pytest.mark.parametrize("passes,tol", [(1, 2e-3), (3, 5e-5)], ids=["tf32", "tf32x3"])
 @pytest.mark.parametrize("B,H,C", [(2, 64, 64), (20, 8, 512), (20, 2, 512), (3, 16, 256)])
-def test_conv_tcgen05_stride2(B, H, C, passes, tol):
+def test_conv_tcgen05_stride2(B, H, C, passes, tol, tc_version):
     """down* layers (4x4, stride 2, pad 1) on the tcgen05 kernels: forward and wgrad through TMA element strides,
     data gradient as four output-parity classes."""
     from mtdgan_b200 import ops
@@ -147,7 +157,7 @@ def test_conv_tcgen05_stride2(B, H, C, passes, tol):
 
 @pytest.mark.parametrize("passes,tol", [(1, 2e-3), (3, 5e-5)], ids=["tf32", "tf32x3"])
 @pytest.mark.parametrize("case", TC_CASES, ids=lambda c: "x".join(map(str, c)))
-def test_conv_tcgen05_forward_backward(case, passes, tol):
+def test_conv_tcgen05_forward_backward(case, passes, tol, tc_version):
     """tcgen05/TMEM kernel (forward + dgrad) vs fp64 torch: plain TF32 <= 2e-3, error-compensated 3xTF32 <= 2e-5;
     and it must really be the kernel that ran.  The backward reference uses the activation mask of the CUDA
     forward (a ReLU sign flip at |z| ~ 1e-3 is not a kernel error; the mask kernels are tested on their own)."""
