@@ -857,7 +857,7 @@ void choose_tiling(int m_tiles, int N, int kiters, int passes, int force_split, 
 
 
 // ---- v2 host side -------------------------------------------------------------------------------------
-int g_tc_version = 1;      // 1: A through shared memory (conv_tc_kernel); 2: A through TMEM, MT pixel tiles per CTA
+int g_tc_version = 2;      // 1: A through shared memory (conv_tc_kernel); 2 (default): A through TMEM, MT pixel tiles per CTA
 
 struct V2Cfg { int bn, mt; };
 constexpr V2Cfg kV2Cfgs[3] = {{128, 3}, {64, 6}, {32, 8}};
