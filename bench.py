@@ -114,7 +114,7 @@ def flops_of(name, a):
 
 
 GROUPS = {"conv": ("mtd_conv_fwd", "mtd_conv_fwd_tc", "mtd_conv_dgrad", "mtd_conv_dgrad_tc", "mtd_conv_wgrad", "mtd_conv_wgrad_tc"),
-          "conv_aux": ("mtd_conv_pack_fwd", "mtd_conv_pack_dgrad", "mtd_conv_wgrad_finish", "mtd_act_bwd", "mtd_split_tf32",
+          "conv_aux": ("mtd_conv_pack_fwd", "mtd_conv_pack_dgrad", "mtd_conv_pack_fwd_blocked", "mtd_conv_pack_dgrad_blocked", "mtd_conv_wgrad_finish", "mtd_act_bwd", "mtd_split_tf32",
                        "mtd_round_tf32"),
           "fft": ("mtd_fft_rows_fwd", "mtd_fft_cols_mix", "mtd_fft_rows_inv", "mtd_fft_cols_mix_bwd"),
           "spectral_norm": ("mtd_sn_power_iter",), "pcgrad": ("mtd_pcgrad_project",), "adamw": ("mtd_adamw_step",)}

@@ -46,6 +46,14 @@ long long mtd_kernel_launch_count(void);
 int mtd_conv_pack_fwd(const float* w_ref, int transposed, int Cout, int Cin, int kh, int kw, float* out, void* stream);
 int mtd_conv_pack_dgrad(const float* w_ref, int transposed, int Cout, int Cin, int kh, int kw, int stride, float* out,
                         void* stream);
+/* the same packs in the tile-major layout the tcgen05 kernels consume: [rows/32][K/32][32][32], K = kh*kw*channels
+ * (every 32x32 tile is 4 KB contiguous, so a TMA weight box is a few contiguous runs), TF32 operand preparation
+ * fused in: tf32 = 0 fp32 copy, 1 rounded to nearest tf32, 3 [hi | lo] split for the 3xTF32 mode (out: 2 x numel).
+ * Needs Cout, Cin % 32 == 0. */
+int mtd_conv_pack_fwd_blocked(const float* w_ref, int transposed, int Cout, int Cin, int kh, int kw, int tf32, float* out,
+                              void* stream);
+int mtd_conv_pack_dgrad_blocked(const float* w_ref, int transposed, int Cout, int Cin, int kh, int kw, int stride, int tf32,
+                                float* out, void* stream);
 /* y = post_act( pre_act( scale * conv(cat[x1,x2]) + bias ) + add1 + add2 );  aux (optional) receives the
  * value after pre_act.  x2/C2 = second source concatenated along channels (torch.cat at
  * networks.py:421-466) or null/0.  scale = device scalar 1/sigma of spectral norm, or null.       */
@@ -85,6 +93,9 @@ int mtd_conv_fwd_tc_supported(int B, int H, int W, int C1, int C2, int N, int kh
 /* kernel generation of the forward/dgrad tensor-core path: 1 = A through shared memory, 2 = A through TMEM with
  * several pixel tiles per CTA (weights streamed once per group).  Returns the previous setting.              */
 int mtd_tc_set_version(int version);
+/* tuning hook: force the Cout tile width (32/64/128) and/or split-K factor of the forward/dgrad tensor-core kernels;
+ * 0 = chosen by the built-in cost model (the default).                                                        */
+int mtd_tc_set_tuning(int bn, int ksplit);
 /* in-place round-to-nearest fp32 -> tf32 of a packed weight buffer (tcgen05 truncates its operands)  */
 int mtd_round_tf32(float* p, long long n, void* stream);
 int mtd_conv_fwd_tc(const float* x1, const float* x2, const float* wp, const float* bias, const float* scale, float* y,

@@ -489,6 +489,10 @@ struct PackArgs {
   int N, T, C;
   long long sN, sC;
   int toff[kMaxTaps];
+  int blocked;     // 1: tile-major layout [N/32][T*C/32][32 n][32 k] (every 32x32 tile = 4 KB contiguous) for the TMA /
+                   //    tcgen05 kernels: a weight tile is a few contiguous 4 KB runs instead of 128 B pieces 4*T*C bytes apart
+  int tf32;        // 0: fp32 copy; 1: rounded to tf32 (nearest); 3: tf32 hi at out[o], tf32 residual at out[o + lo_off]
+  long long lo_off;
 };
 
 __global__ void pack_weights_kernel(const float* __restrict__ w, float* __restrict__ out, const __grid_constant__ PackArgs p) {
@@ -500,7 +504,21 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, float* __restri
     size_t r = i / p.C;
     int t = (int)(r % p.T);
     int n = (int)(r / p.T);
-    out[i] = __ldg(w + (size_t)n * p.sN + (size_t)c * p.sC + p.toff[t]);
+    size_t o = i;
+    if (p.blocked) {
+      const size_t k = (size_t)t * p.C + c, KS = (size_t)p.T * p.C / 32;
+      o = ((((size_t)(n >> 5) * KS + (k >> 5)) * 32 + (n & 31)) << 5) + (k & 31);
+    }
+    const float v = __ldg(w + (size_t)n * p.sN + (size_t)c * p.sC + p.toff[t]);
+    if (p.tf32 == 0) { out[o] = v; continue; }
+    uint32_t h;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(v));
+    out[o] = __uint_as_float(h);
+    if (p.tf32 == 3) {
+      uint32_t l;
+      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(v - __uint_as_float(h)));     // the residual is exact in fp32
+      out[o + p.lo_off] = __uint_as_float(l);
+    }
   }
 }
 
@@ -889,10 +907,15 @@ void tap_table_fwd(int* dy, int* dx, int kh, int kw, int pad) {
 // =============================================================================================
 extern "C" {
 
+static int g_pack_blocked = 0;     // set by the *_blocked entry points around the shared implementation
+static int g_pack_tf32 = 0;
+
 int mtd_conv_pack_fwd(const float* w_ref, int transposed, int Cout, int Cin, int kh, int kw, float* out, void* stream) {
   MTD_REQUIRE(w_ref && out && Cout > 0 && Cin > 0 && kh > 0 && kw > 0 && kh * kw <= kMaxTaps);
   PackArgs p;
   fwd_mapping(p, transposed, Cout, Cin, kh, kw);
+  p.blocked = g_pack_blocked; p.tf32 = g_pack_tf32; p.lo_off = (long long)Cout * Cin * kh * kw;
+  if (p.blocked) MTD_REQUIRE(Cout % 32 == 0 && Cin % 32 == 0);
   return pack_launch(w_ref, out, p, (cudaStream_t)stream);
 }
 
@@ -909,12 +932,16 @@ int mtd_conv_pack_dgrad(const float* w_ref, int transposed, int Cout, int Cin, i
     PackArgs p;
     p.N = Cin; p.T = kh * kw; p.C = Cout; p.sN = f.sC; p.sC = f.sN;
     for (int t = 0; t < p.T; ++t) p.toff[t] = f.toff[t];
+    p.blocked = g_pack_blocked; p.tf32 = g_pack_tf32; p.lo_off = (long long)Cout * Cin * kh * kw;
+    if (p.blocked) MTD_REQUIRE(Cout % 32 == 0 && Cin % 32 == 0);
     return pack_launch(w_ref, out, p, st);
   }
   MTD_REQUIRE(stride == 2 && kh == 4 && kw == 4 && !transposed);
   for (int py = 0; py < 2; ++py)
     for (int px = 0; px < 2; ++px) {
       PackArgs p;
+      p.blocked = g_pack_blocked; p.tf32 = g_pack_tf32; p.lo_off = (long long)Cout * Cin * kh * kw;
+      if (p.blocked) MTD_REQUIRE(Cout % 32 == 0 && Cin % 32 == 0);
       p.N = Cin; p.T = 4; p.C = Cout; p.sN = f.sC; p.sC = f.sN;
       for (int a = 0; a < 2; ++a)
         for (int b = 0; b < 2; ++b) {
@@ -925,6 +952,27 @@ int mtd_conv_pack_dgrad(const float* w_ref, int transposed, int Cout, int Cin, i
       if (rc) return rc;
     }
   return MTD_OK;
+}
+
+// Same packs in the tile-major layout the tensor-core kernels read: [rows/32][K/32][32][32] (rows = Cout for the
+// forward pack, Cin for dgrad; K = taps x channels), with the TF32 operand preparation fused in: tf32 = 0 plain
+// copy, 1 rounded to nearest tf32, 3 [hi | lo] halves for the 3xTF32 mode (`out` then holds 2 x numel floats).
+// Requires Cout % 32 == 0 and Cin % 32 == 0.
+int mtd_conv_pack_fwd_blocked(const float* w_ref, int transposed, int Cout, int Cin, int kh, int kw, int tf32, float* out,
+                              void* stream) {
+  MTD_REQUIRE(tf32 == 0 || tf32 == 1 || tf32 == 3);
+  g_pack_blocked = 1; g_pack_tf32 = tf32;
+  int rc = mtd_conv_pack_fwd(w_ref, transposed, Cout, Cin, kh, kw, out, stream);
+  g_pack_blocked = 0; g_pack_tf32 = 0;
+  return rc;
+}
+int mtd_conv_pack_dgrad_blocked(const float* w_ref, int transposed, int Cout, int Cin, int kh, int kw, int stride, int tf32,
+                                float* out, void* stream) {
+  MTD_REQUIRE(tf32 == 0 || tf32 == 1 || tf32 == 3);
+  g_pack_blocked = 1; g_pack_tf32 = tf32;
+  int rc = mtd_conv_pack_dgrad(w_ref, transposed, Cout, Cin, kh, kw, stride, out, stream);
+  g_pack_blocked = 0; g_pack_tf32 = 0;
+  return rc;
 }
 
 int mtd_conv_fwd(const float* x1, const float* x2, const float* wp, const float* bias, const float* scale, float* y,

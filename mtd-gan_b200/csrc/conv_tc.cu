@@ -236,8 +236,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
           const uint32_t sa = base + (uint32_t)st.stage * kStageBytes, sb = sa + kOffB;
           if (cc < a.kc1) tma_load_4d(&mapA1, sa, full_bar(st.stage), cc * 32, w0 * a.es + a.dx[t], h0 * a.es + a.dy[t], b0);
           else tma_load_4d(&mapA2, sa, full_bar(st.stage), (cc - a.kc1) * 32, w0 * a.es + a.dx[t], h0 * a.es + a.dy[t], b0);
-          tma_load_2d(&mapB, sb, full_bar(st.stage), t * Ctot + cc * 32, n0);
-          if (NPASS == 3) tma_load_2d(&mapBlo, sa + kOffBlo, full_bar(st.stage), t * Ctot + cc * 32, n0);
+          tma_load_4d(&mapB, sb, full_bar(st.stage), 0, 0, it, n0 >> 5);          // k-step `it` == (t*Ctot + cc*32)/32
+          if (NPASS == 3) tma_load_4d(&mapBlo, sa + kOffBlo, full_bar(st.stage), 0, 0, it, n0 >> 5);
           st.advance(S);
         }
       }
@@ -287,25 +287,26 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
       decode_tile(tile, b0, h0, w0, n0, k_begin, k_end);
       for (int it = k_begin; it < k_end; ++it) {
         mbar_wait(full_bar(st.stage), st.phase);
-        float4* tileA = reinterpret_cast<float4*>(gen_base + (size_t)st.stage * kStageBytes);
+        uint4* tileA = reinterpret_cast<uint4*>(gen_base + (size_t)st.stage * kStageBytes);
+        // Integer arithmetic instead of cvt.rna.tf32.f32 (quarter-rate, was the k-step bound for BN <= 64).
+        // 3xTF32: the tensor core truncates its fp32 operand to tf32, so the raw tile already IS a_hi = trunc(a);
+        // only a_lo = rn_tf32(a - trunc(a)) (the difference is exact in fp32) has to be produced.
+        // 1xTF32: round to nearest in place ((bits + 0x1000) & ~0x1fff == cvt.rna: ties away from zero).
 #pragma unroll 8
         for (int j = 0; j < kABytes / 16 / 128; ++j) {
-          float4 v = tileA[ct + 128 * j];
-          uint32_t r0, r1, r2, r3;
-          asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r0) : "f"(v.x));
-          asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r1) : "f"(v.y));
-          asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r2) : "f"(v.z));
-          asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r3) : "f"(v.w));
-          const float4 hi = make_float4(__uint_as_float(r0), __uint_as_float(r1), __uint_as_float(r2), __uint_as_float(r3));
-          tileA[ct + 128 * j] = hi;
-          if (NPASS == 3) {                      // residual a - a_hi is exact in fp32; round it to tf32 as well
-            uint32_t l0, l1, l2, l3;
-            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l0) : "f"(v.x - hi.x));
-            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l1) : "f"(v.y - hi.y));
-            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l2) : "f"(v.z - hi.z));
-            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l3) : "f"(v.w - hi.w));
-            tileA[kOffAlo / 16 + ct + 128 * j] =
-                make_float4(__uint_as_float(l0), __uint_as_float(l1), __uint_as_float(l2), __uint_as_float(l3));
+          const uint4 v = tileA[ct + 128 * j];
+          if (NPASS == 3) {
+            uint4 l;
+            l.x = (__float_as_uint(__uint_as_float(v.x) - __uint_as_float(v.x & 0xffffe000u)) + 0x1000u) & 0xffffe000u;
+            l.y = (__float_as_uint(__uint_as_float(v.y) - __uint_as_float(v.y & 0xffffe000u)) + 0x1000u) & 0xffffe000u;
+            l.z = (__float_as_uint(__uint_as_float(v.z) - __uint_as_float(v.z & 0xffffe000u)) + 0x1000u) & 0xffffe000u;
+            l.w = (__float_as_uint(__uint_as_float(v.w) - __uint_as_float(v.w & 0xffffe000u)) + 0x1000u) & 0xffffe000u;
+            tileA[kOffAlo / 16 + ct + 128 * j] = l;
+          } else {
+            uint4 h;
+            h.x = (v.x + 0x1000u) & 0xffffe000u; h.y = (v.y + 0x1000u) & 0xffffe000u;
+            h.z = (v.z + 0x1000u) & 0xffffe000u; h.w = (v.w + 0x1000u) & 0xffffe000u;
+            tileA[ct + 128 * j] = h;
           }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> tensor-core (async proxy) reads
@@ -530,8 +531,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant
           mbar_wait(bempty(sb.stage), sb.phase ^ 1u);
           mbar_expect_tx(bfull(sb.stage), kBBytes);
           const uint32_t sbm = b_base + (uint32_t)sb.stage * kBBytes;
-          tma_load_2d(&mapB, sbm, bfull(sb.stage), t * Ctot + cc * 32, n0);
-          if (NPASS == 3) tma_load_2d(&mapBlo, sbm + BN * 128, bfull(sb.stage), t * Ctot + cc * 32, n0);
+          tma_load_4d(&mapB, sbm, bfull(sb.stage), 0, 0, it, n0 >> 5);               // k-step `it` == (t*Ctot + cc*32)/32
+          if (NPASS == 3) tma_load_4d(&mapBlo, sbm + BN * 128, bfull(sb.stage), 0, 0, it, n0 >> 5);
           sb.advance(RB);
 #pragma unroll 1
           for (int j = 0; j < MT; ++j) {
@@ -757,10 +758,13 @@ int make_act_map(CUtensorMap* out, const float* ptr, int C, int W, int H, int B,
   return MTD_OK;
 }
 
-// packed weights: rank-2 (K = T*Ctot, rows) fp32, box (32, BN)
+// packed weights in the tile-major layout [rows/32][K/32][32][32] (mtd_conv_pack_*_blocked): rank-4 map
+// (k_in = 32, n_in = 32, kstep = K/32, n_blk = rows/32), box (32, 32, 1, BN/32): a BN x 32 tile lands as BN rows of
+// 128 B (SWIZZLE_128B) and is read from BN/32 contiguous 4 KB runs.
 int make_w_map(CUtensorMap* out, const float* ptr, long long K, int rows, int BN) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return MTD_EINVAL;
+  if (K % 32 || rows % 32 || BN % 32) return MTD_EINVAL;
   char keybuf[128];
   snprintf(keybuf, sizeof(keybuf), "W%p:%lld:%d:%d", (const void*)ptr, K, rows, BN);
   std::string key(keybuf);
@@ -769,11 +773,12 @@ int make_w_map(CUtensorMap* out, const float* ptr, long long K, int rows, int BN
     auto it = g_map_cache.find(key);
     if (it != g_map_cache.end()) { *out = it->second; return MTD_OK; }
   }
-  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)K * 4};
-  cuuint32_t box[2] = {32, (cuuint32_t)BN};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+  const cuuint64_t KS = (cuuint64_t)(K / 32);
+  cuuint64_t dims[4] = {32, 32, KS, (cuuint64_t)(rows / 32)};
+  cuuint64_t strides[3] = {128, 4096, KS * 4096};
+  cuuint32_t box[4] = {32, 32, 1, (cuuint32_t)(BN / 32)};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return MTD_EINVAL;
   std::lock_guard<std::mutex> lk(g_map_mutex);
@@ -826,30 +831,33 @@ int launch_bn(const CUtensorMap& mA1, const CUtensorMap& mA2, const CUtensorMap&
   return MTD_OK;
 }
 
-// Tile / split selection by a small cost model.  Every k-step costs roughly max(latency floor, bytes / per-SM
-// L2 bandwidth) and a CTA runs ceil(tiles / SMs) rounds of `kper` k-steps, so for skinny-M (weight-streaming)
-// layers the best choice is the WIDEST Cout tile whose (m-tiles x n-tiles x k-splits) still fits one wave.
+// Tile / split selection by a cost model fitted (least squares, 9 % rms) to the sweep of tools/tune_tc.py over the
+// layer shapes of the B = 20 train step (profiles/r01_tune_tc_v1.txt); times in microseconds:
+//   T = F0 + rounds * (Ft + kper * ts[BN]) + [ksplit > 1] * ca * ksplit * (padded M x N / 65536)
+// F0 = launch + pipeline fill + drain, Ft = per-tile epilogue not hidden by the next tile, ts = one 32-channel k-step
+// (L2 -> SM ingest of the A tile and the hi|lo weight tile, ~32 B/clk/SM), ca = the fp32 atomics of the split-K
+// partial sums.  The model picks within 1.2 % of the best measured (BN, ksplit) summed over the sweep.
+int g_tune_bn = 0, g_tune_ksplit = 0;      // tools/tune_tc.py overrides (0 = cost model)
+
 void choose_tiling(int m_tiles, int N, int kiters, int passes, int force_split, int* BN_out, int* ksplit_out) {
   const int sms = mtd_sm_count();
   double best = 1e30;
   int BN = 32, ksplit = 1;
+  if (g_tune_ksplit > 0 && force_split == 0) force_split = g_tune_ksplit;
   for (int bn = 128; bn >= 32; bn >>= 1) {
     if (N % bn) continue;
+    if (g_tune_bn > 0 && bn != g_tune_bn && N % g_tune_bn == 0) continue;
+    const double ts = (bn == 128 ? 0.78 : bn == 64 ? 0.57 : 0.52) * (passes == 3 ? 1.0 : 0.7);
     const int mn = m_tiles * (N / bn);
-    const double kb = (passes == 3 ? 2.0 : 1.0) * (16.0 + bn * 0.125);          // smem KB landed / produced per k-step
-    const double t_step = kb < 28.0 ? 28.0 : kb;                                  // latency floor ~ a 28 KB step
-    int ks = 1;
-    if (force_split > 0) ks = force_split;
-    else if (mn < sms && kiters >= 8) {
-      ks = sms / mn;
-      if (ks > kiters / 2) ks = kiters / 2;
-      if (ks < 1) ks = 1;
+    const int ks_max = force_split > 0 ? force_split : (kiters >= 4 ? (kiters / 2 < 48 ? kiters / 2 : 48) : 1);
+    for (int ks0 = force_split > 0 ? force_split : 1; ks0 <= ks_max; ++ks0) {
+      const int kper = (kiters + ks0 - 1) / ks0;
+      const int ks = (kiters + kper - 1) / kper;                                  // no empty splits
+      const int rounds = (mn * ks + sms - 1) / sms;
+      double cost = 6.0 + rounds * (2.2 + kper * ts);
+      if (ks > 1) cost += 0.33 * ks * (double)m_tiles * kBM * N / 65536.0;
+      if (cost < best) { best = cost; BN = bn; ksplit = ks; }
     }
-    const int kper = (kiters + ks - 1) / ks;
-    ks = (kiters + kper - 1) / kper;                                              // no empty splits
-    const int rounds = (mn * ks + sms - 1) / sms;
-    const double cost = (double)rounds * kper * t_step + (ks > 1 ? 6.0 * t_step : 0.0);   // + memset / finish pass
-    if (cost < best) { best = cost; BN = bn; ksplit = ks; }
   }
   *BN_out = BN;
   *ksplit_out = ksplit;
@@ -857,7 +865,8 @@ void choose_tiling(int m_tiles, int N, int kiters, int passes, int force_split, 
 
 
 // ---- v2 host side -------------------------------------------------------------------------------------
-int g_tc_version = 2;      // 1: A through shared memory (conv_tc_kernel); 2 (default): A through TMEM, MT pixel tiles per CTA
+int g_tc_version = 1;      // 1 (default): A through shared memory (conv_tc_kernel); 2: A through TMEM, MT pixel tiles per CTA
+                           // (slower on every measured layer shape -- kept selectable for experiments)
 
 struct V2Cfg { int bn, mt; };
 constexpr V2Cfg kV2Cfgs[3] = {{128, 3}, {64, 6}, {32, 8}};
@@ -866,9 +875,11 @@ void choose_tiling_v2(int m_tiles, int N, int kiters, int passes, int force_spli
   const int sms = mtd_sm_count();
   double best = 1e30;
   int bc = -1, bks = 1;
+  if (g_tune_ksplit > 0 && force_split == 0) force_split = g_tune_ksplit;
   for (int ci = 0; ci < 3; ++ci) {
     const int bn = kV2Cfgs[ci].bn, mt = kV2Cfgs[ci].mt;
     if (N % bn) continue;
+    if (g_tune_bn > 0 && bn != g_tune_bn && N % g_tune_bn == 0) continue;
     const int groups = (m_tiles + mt - 1) / mt;
     const double mtv = (double)m_tiles / groups;                      // average pixel tiles per group
     const int mn = groups * (N / bn);
@@ -1296,6 +1307,14 @@ int mtd_tc_set_version(int version) {
   int prev = g_tc_version;
   if (version == 1 || version == 2) g_tc_version = version;
   return prev;
+}
+
+// Tuning hook (tools/tune_tc.py): force the Cout tile width and/or the split-K factor of the forward/dgrad tensor-core
+// kernels; 0 = let the cost model decide.
+int mtd_tc_set_tuning(int bn, int ksplit) {
+  if ((bn != 0 && bn != 32 && bn != 64 && bn != 128) || ksplit < 0) return MTD_EINVAL;
+  g_tune_bn = bn; g_tune_ksplit = ksplit;
+  return MTD_OK;
 }
 
 int mtd_conv_fwd_tc_supported(int B, int H, int W, int C1, int C2, int N, int kh, int kw, int stride, int pad) {

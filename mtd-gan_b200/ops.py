@@ -58,16 +58,20 @@ def _packed(weight: torch.Tensor, kind: str, cfg: "ConvCfg") -> torch.Tensor:
         return ent[1]
     w = weight.detach()
     out = _empty((w.numel() * (2 if kind.endswith("_tf32x3") else 1),), w)
-    if kind.startswith("fwd"):
+    if "_tf32" in kind:
+        # tensor-core packs: tile-major (blocked) layout with the TF32 rounding ([hi | lo] split for 3xTF32) fused in
+        mode = 3 if kind.endswith("_tf32x3") else 1
+        if kind.startswith("fwd"):
+            call("mtd_conv_pack_fwd_blocked", fptr(w), cfg.transposed, cfg.cout, cfg.cin, cfg.kh, cfg.kw, mode, fptr(out),
+                 stream())
+        else:
+            call("mtd_conv_pack_dgrad_blocked", fptr(w), cfg.transposed, cfg.cout, cfg.cin, cfg.kh, cfg.kw, cfg.stride, mode,
+                 fptr(out), stream())
+    elif kind.startswith("fwd"):
         call("mtd_conv_pack_fwd", fptr(w), cfg.transposed, cfg.cout, cfg.cin, cfg.kh, cfg.kw, fptr(out), stream())
     else:
         call("mtd_conv_pack_dgrad", fptr(w), cfg.transposed, cfg.cout, cfg.cin, cfg.kh, cfg.kw, cfg.stride, fptr(out),
              stream())
-    if kind.endswith("_tf32"):          # B operand of the tcgen05 kernels: round to nearest (the MMA truncates)
-        call("mtd_round_tf32", fptr(out), out.numel(), stream())
-    elif kind.endswith("_tf32x3"):      # [hi | lo] halves for the error-compensated 3xTF32 mode
-        n = w.numel()
-        call("mtd_split_tf32", fptr(out), out.data_ptr() + 4 * n, n, stream())
     slot[key] = (tag, out)
     return out
 
