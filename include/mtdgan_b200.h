@@ -33,6 +33,9 @@ int mtd_abi_version(void);
 int mtd_device_ok(void);
 /* number of CUDA kernels this library has launched in this process (host-side counter) */
 long long mtd_kernel_launch_count(void);
+/* programmatic dependent launch (every kernel waits on griddepcontrol before touching memory and lets the next
+ * grid be scheduled early); on by default, returns the previous setting.  Off = plain stream serialization.   */
+int mtd_set_pdl(int enabled);
 
 /* ---- convolution (conv_simt.cu, conv_tc.cu) ----------------------------------------------------
  * Replaces nn.Conv2d / nn.ConvTranspose2d / nn.Linear forward and ATen convolution_backward:

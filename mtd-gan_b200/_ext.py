@@ -68,6 +68,8 @@ def load():
         fn.restype = _CTYPES[ret]
         fn.argtypes = [ctypes.c_void_p if t == "ptr" else _CTYPES[t] for t in types]
     _lib = lib
+    if os.environ.get("MTD_PDL", "1") == "0":       # A/B switch for the programmatic-dependent-launch path
+        lib.mtd_set_pdl(0)
     return lib
 
 

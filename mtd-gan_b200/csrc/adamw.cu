@@ -22,12 +22,14 @@ struct Seg {
 static_assert(sizeof(Seg) == 64, "segment entry must be 8 x int64");
 
 __global__ void adamw_inc_kernel(const Seg* __restrict__ segs, int nseg) {
+  mtd_pdl_prologue();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < nseg) *segs[i].step += 1.f;
 }
 
 __global__ void __launch_bounds__(256) adamw_kernel(const Seg* __restrict__ segs, const int2* __restrict__ chunks, float lr,
                                                     float b1, float b2, float eps, float wd) {
+  mtd_pdl_prologue();
   const int2 ck = chunks[blockIdx.x];
   const Seg s = segs[ck.x];
   const long long end = min(s.numel, (long long)ck.y + kChunk);
@@ -49,9 +51,9 @@ __global__ void __launch_bounds__(256) adamw_kernel(const Seg* __restrict__ segs
 extern "C" int mtd_adamw_step(const void* seg_tab, int n_segs, const void* chunk_tab, int n_chunks, float lr, float beta1,
                               float beta2, float eps, float weight_decay, void* stream) {
   MTD_REQUIRE(seg_tab && chunk_tab && n_chunks > 0 && n_segs > 0);
-  adamw_inc_kernel<<<(n_segs + 127) / 128, 128, 0, (cudaStream_t)stream>>>(reinterpret_cast<const Seg*>(seg_tab), n_segs);
+  mtd_launch(adamw_inc_kernel, (n_segs + 127) / 128, 128, 0, (cudaStream_t)stream, reinterpret_cast<const Seg*>(seg_tab), n_segs);
   MTD_CHECK_LAUNCH();
-  adamw_kernel<<<n_chunks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const Seg*>(seg_tab),
+  mtd_launch(adamw_kernel, n_chunks, 256, 0, (cudaStream_t)stream, reinterpret_cast<const Seg*>(seg_tab),
                                                            reinterpret_cast<const int2*>(chunk_tab), lr, beta1, beta2, eps,
                                                            weight_decay);
   MTD_CHECK_LAUNCH();

@@ -58,6 +58,7 @@ __device__ __forceinline__ float conv_epilogue_one(const ConvArgs& a, float v, s
 
 template <int TM, int TN, bool VEC>
 __global__ void __launch_bounds__(256) conv_igemm_kernel(const __grid_constant__ ConvArgs a) {
+  mtd_pdl_prologue();
   constexpr int BM = 16 * TM, BN = 16 * TN, BK = 16;
   constexpr int A_PER = (BM * 4 + 255) / 256;
   constexpr int B_PER = (BN * 4 + 255) / 256;
@@ -233,6 +234,7 @@ __global__ void __launch_bounds__(256) conv_igemm_kernel(const __grid_constant__
 //                    (s_/r_dconv61 128->1, generator decoder[0] 32->1; dgrad of every Cin = 1 layer)
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) conv_c1_kernel(const __grid_constant__ ConvArgs a) {
+  mtd_pdl_prologue();
   extern __shared__ __align__(16) float wsm[];   // [T][N4]  (N padded to a multiple of 4, zero filled)
   const int N4 = (a.N + 3) & ~3;
   for (int i = threadIdx.x; i < a.T * N4; i += blockDim.x) {
@@ -285,6 +287,7 @@ __global__ void __launch_bounds__(256) conv_c1_kernel(const __grid_constant__ Co
 // LPP lanes cooperate on one pixel (LPP = min(32, Ctot/4)); N <= 4 accumulators per lane, shuffle-reduced.
 // Requires Ctot == 4 * LPP * k; the generic case loops over channel groups.
 __global__ void __launch_bounds__(256) conv_n1_kernel(const __grid_constant__ ConvArgs a, int lpp) {
+  mtd_pdl_prologue();
   extern __shared__ __align__(16) float wsm[];   // [N][T][Ctot]
   const int Ctot = a.C1 + a.C2;
   for (int i = threadIdx.x; i < a.N * a.T * Ctot; i += blockDim.x) wsm[i] = __ldg(a.wp + i);
@@ -362,6 +365,7 @@ struct ThinWgArgs {
 
 template <bool VEC4>
 __global__ void __launch_bounds__(256) thin_wgrad_kernel(const __grid_constant__ ThinWgArgs a) {
+  mtd_pdl_prologue();
   extern __shared__ float red[];                        // [T][J]
   const int J = a.J1 + a.J2;
   const int HW = a.H * a.W;
@@ -418,6 +422,7 @@ __global__ void __launch_bounds__(256) thin_wgrad_kernel(const __grid_constant__
 
 // second phase of a split-K conv: out holds raw sums
 __global__ void conv_epilogue_kernel(const __grid_constant__ ConvArgs a, size_t total) {
+  mtd_pdl_prologue();
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   size_t stride = (size_t)gridDim.x * blockDim.x;
   for (; i < total; i += stride) {
@@ -436,7 +441,7 @@ int launch_conv(ConvArgs& a, cudaStream_t st) {
   if (Ctot == 1 && a.T * a.N * sizeof(float) <= 40 * 1024) {                 // single-channel source: streaming kernel
     size_t work = (size_t)M * ((a.N + 3) / 4);
     int blocks = (int)std::min<size_t>((work + 255) / 256, (size_t)mtd_sm_count() * 16);
-    conv_c1_kernel<<<blocks, 256, a.T * ((a.N + 3) & ~3) * sizeof(float), st>>>(a);
+    mtd_launch(conv_c1_kernel, blocks, 256, a.T * ((a.N + 3) & ~3) * sizeof(float), st, a);
     MTD_CHECK_LAUNCH();
     return MTD_OK;
   }
@@ -445,7 +450,7 @@ int launch_conv(ConvArgs& a, cudaStream_t st) {
     while (lpp < 32 && lpp * 2 * 4 <= Ctot) lpp <<= 1;
     size_t warps = ((size_t)M + (32 / lpp) - 1) / (32 / lpp);
     int blocks = (int)std::min<size_t>((warps + 7) / 8, (size_t)mtd_sm_count() * 16);
-    conv_n1_kernel<<<blocks, 256, (size_t)a.N * a.T * Ctot * sizeof(float), st>>>(a, lpp);
+    mtd_launch(conv_n1_kernel, blocks, 256, (size_t)a.N * a.T * Ctot * sizeof(float), st, a, lpp);
     MTD_CHECK_LAUNCH();
     return MTD_OK;
   }
@@ -467,16 +472,16 @@ int launch_conv(ConvArgs& a, cudaStream_t st) {
   size_t total = (size_t)a.B * a.outH * a.outW * a.N;
   if (splits > 1) MTD_CUDA(cudaMemsetAsync(a.out, 0, total * sizeof(float), st));
   if (thin_n) {
-    if (vec) conv_igemm_kernel<8, 1, true><<<grid, 256, 0, st>>>(a);
-    else conv_igemm_kernel<8, 1, false><<<grid, 256, 0, st>>>(a);
+    if (vec) mtd_launch(conv_igemm_kernel<8, 1, true>, grid, 256, 0, st, a);
+    else mtd_launch(conv_igemm_kernel<8, 1, false>, grid, 256, 0, st, a);
   } else {
-    if (vec) conv_igemm_kernel<4, 4, true><<<grid, 256, 0, st>>>(a);
-    else conv_igemm_kernel<4, 4, false><<<grid, 256, 0, st>>>(a);
+    if (vec) mtd_launch(conv_igemm_kernel<4, 4, true>, grid, 256, 0, st, a);
+    else mtd_launch(conv_igemm_kernel<4, 4, false>, grid, 256, 0, st, a);
   }
   MTD_CHECK_LAUNCH();
   if (splits > 1) {
     int blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)mtd_sm_count() * 8);
-    conv_epilogue_kernel<<<blocks, 256, 0, st>>>(a, total);
+    mtd_launch(conv_epilogue_kernel, blocks, 256, 0, st, a, total);
     MTD_CHECK_LAUNCH();
   }
   return MTD_OK;
@@ -496,6 +501,7 @@ struct PackArgs {
 };
 
 __global__ void pack_weights_kernel(const float* __restrict__ w, float* __restrict__ out, const __grid_constant__ PackArgs p) {
+  mtd_pdl_prologue();
   size_t total = (size_t)p.N * p.T * p.C;
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   size_t stride = (size_t)gridDim.x * blockDim.x;
@@ -536,6 +542,7 @@ struct UnpackArgs {
 };
 
 __global__ void unpack_grad_kernel(const float* __restrict__ gp, float* __restrict__ dw, const __grid_constant__ UnpackArgs a) {
+  mtd_pdl_prologue();
   const PackArgs& p = a.p;
   size_t total = (size_t)p.N * p.T * p.C;
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -564,6 +571,7 @@ __global__ void unpack_grad_kernel(const float* __restrict__ gp, float* __restri
 // final value converted by dot_finish_kernel.
 __global__ void dot_packed_ref_kernel(const float* __restrict__ gp, const float* __restrict__ w, double* __restrict__ acc,
                                       const __grid_constant__ PackArgs p) {
+  mtd_pdl_prologue();
   __shared__ double sh[32];
   size_t total = (size_t)p.N * p.T * p.C;
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -613,6 +621,7 @@ __device__ __forceinline__ size_t fin_ref_index(const FinSeg& s, size_t i) {
 
 __global__ void __launch_bounds__(256) finish_dot_kernel(const FinSeg* __restrict__ segs, const int2* __restrict__ chunks,
                                                          double* __restrict__ dots) {
+  mtd_pdl_prologue();
   __shared__ double sh[32];
   const int2 ck = chunks[blockIdx.x];
   const FinSeg s = segs[ck.x];
@@ -628,6 +637,7 @@ __global__ void __launch_bounds__(256) finish_dot_kernel(const FinSeg* __restric
 
 __global__ void __launch_bounds__(256) finish_unpack_kernel(const FinSeg* __restrict__ segs, const int2* __restrict__ chunks,
                                                             const double* __restrict__ dots) {
+  mtd_pdl_prologue();
   const int2 ck = chunks[blockIdx.x];
   const FinSeg head = segs[ck.x];
   const size_t total = (size_t)head.N * head.T * head.C;
@@ -671,7 +681,7 @@ void fwd_mapping(PackArgs& p, int transposed, int Cout, int Cin, int kh, int kw)
 int pack_launch(const float* w, float* out, const PackArgs& p, cudaStream_t st) {
   size_t total = (size_t)p.N * p.T * p.C;
   int blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)mtd_sm_count() * 16);
-  pack_weights_kernel<<<blocks, 256, 0, st>>>(w, out, p);
+  mtd_launch(pack_weights_kernel, blocks, 256, 0, st, w, out, p);
   MTD_CHECK_LAUNCH();
   return MTD_OK;
 }
@@ -694,6 +704,7 @@ struct WgradArgs {
 
 template <int TN, int TC, bool VEC>
 __global__ void __launch_bounds__(256) conv_wgrad_kernel(const __grid_constant__ WgradArgs a) {
+  mtd_pdl_prologue();
   constexpr int BN = 16 * TN, BC = 16 * TC, BK = 16;
   constexpr int A_Q = BN / 4, B_Q = BC / 4;                 // float4 slots per pixel row
   constexpr int A_PER = (BK * A_Q + 255) / 256, B_PER = (BK * B_Q + 255) / 256;
@@ -843,8 +854,8 @@ int launch_wgrad(WgradArgs& a, cudaStream_t st) {
   if (splits > 1) MTD_CUDA(cudaMemsetAsync(a.gp, 0, (size_t)a.N * a.T * Ctot * sizeof(float), st));
 #define WG_LAUNCH(TN_, TC_)                                                              \
   do {                                                                                   \
-    if (vec) conv_wgrad_kernel<TN_, TC_, true><<<grid, 256, 0, st>>>(a);                 \
-    else conv_wgrad_kernel<TN_, TC_, false><<<grid, 256, 0, st>>>(a);                    \
+    if (vec) mtd_launch(conv_wgrad_kernel<TN_, TC_, true>, grid, 256, 0, st, a);                 \
+    else mtd_launch(conv_wgrad_kernel<TN_, TC_, false>, grid, 256, 0, st, a);                    \
   } while (0)
   if (thin_n && thin_c) WG_LAUNCH(1, 1);
   else if (thin_n) WG_LAUNCH(1, 4);
@@ -861,6 +872,7 @@ int launch_wgrad(WgradArgs& a, cudaStream_t st) {
 // ---------------------------------------------------------------------------------------------
 __global__ void act_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y, float* __restrict__ dz,
                                float* __restrict__ dbias, size_t total, int N, int act, float slope) {
+  mtd_pdl_prologue();
   extern __shared__ float colsum[];   // N floats when dbias != null
   if (dbias) {
     for (int i = threadIdx.x; i < N; i += blockDim.x) colsum[i] = 0.f;
@@ -1075,8 +1087,8 @@ int mtd_conv_wgrad(const float* x1, const float* x2, const float* dz, float* gp,
     const int J = w.J1 + w.J2;
     const bool vec4 = (w.J1 % 4 == 0) && (w.J2 % 4 == 0) && J >= 4 && mtd_aligned16(w.V1) && (!w.V2 || mtd_aligned16(w.V2));
     const size_t smem = (size_t)a.T * J * sizeof(float);
-    if (vec4) thin_wgrad_kernel<true><<<blocks, 256, smem, st>>>(w);
-    else thin_wgrad_kernel<false><<<blocks, 256, smem, st>>>(w);
+    if (vec4) mtd_launch(thin_wgrad_kernel<true>, blocks, 256, smem, st, w);
+    else mtd_launch(thin_wgrad_kernel<false>, blocks, 256, smem, st, w);
     MTD_CHECK_LAUNCH();
     return MTD_OK;
   }
@@ -1099,12 +1111,12 @@ int mtd_conv_wgrad_finish(const float* gp, float* dw_ref, int transposed, int Co
     MTD_REQUIRE(w_ref && u && v && scratch && !transposed);
     double* acc = (double*)scratch;
     MTD_CUDA(cudaMemsetAsync(acc, 0, 8, st));
-    dot_packed_ref_kernel<<<blocks, 256, 0, st>>>(gp, w_ref, acc, a.p);
+    mtd_launch(dot_packed_ref_kernel, blocks, 256, 0, st, gp, w_ref, acc, a.p);
     MTD_CHECK_LAUNCH();
     a.inv_sigma = inv_sigma; a.dotgw = acc; a.u = u; a.v = v;
     a.sn_rows = Cout; a.sn_cols = (long long)Cin * kh * kw;
   }
-  unpack_grad_kernel<<<blocks, 256, 0, st>>>(gp, dw_ref, a);
+  mtd_launch(unpack_grad_kernel, blocks, 256, 0, st, gp, dw_ref, a);
   MTD_CHECK_LAUNCH();
   return MTD_OK;
 }
@@ -1129,7 +1141,7 @@ int mtd_act_bwd(const float* dy, const float* y, float* dz, float* dbias, long l
       blocks = (N + 255) / 256;
     }
   }
-  act_bwd_kernel<<<blocks, 256, dbias ? N * sizeof(float) : 0, st>>>(dy, y, dz, dbias, total, N, act, slope);
+  mtd_launch(act_bwd_kernel, blocks, 256, dbias ? N * sizeof(float) : 0, st, dy, y, dz, dbias, total, N, act, slope);
   MTD_CHECK_LAUNCH();
   return MTD_OK;
 }
@@ -1144,11 +1156,11 @@ int mtd_wgrad_finish_batched(const void* seg_tab, int n_segs, const void* dot_ch
   if (n_dot_chunks > 0) {
     MTD_REQUIRE(dot_chunks);
     MTD_CUDA(cudaMemsetAsync(dots, 0, (size_t)n_segs * sizeof(double), st));
-    finish_dot_kernel<<<n_dot_chunks, 256, 0, st>>>(reinterpret_cast<const FinSeg*>(seg_tab),
+    mtd_launch(finish_dot_kernel, n_dot_chunks, 256, 0, st, reinterpret_cast<const FinSeg*>(seg_tab),
                                                     reinterpret_cast<const int2*>(dot_chunks), dots);
     MTD_CHECK_LAUNCH();
   }
-  finish_unpack_kernel<<<n_head_chunks, 256, 0, st>>>(reinterpret_cast<const FinSeg*>(seg_tab),
+  mtd_launch(finish_unpack_kernel, n_head_chunks, 256, 0, st, reinterpret_cast<const FinSeg*>(seg_tab),
                                                       reinterpret_cast<const int2*>(head_chunks), dots);
   MTD_CHECK_LAUNCH();
   return MTD_OK;

@@ -147,6 +147,29 @@ __host__ __device__ constexpr uint32_t make_idesc(int bn) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
 }
 
+// scale / bias / pre-activation / aux copy / residual adds / post-activation / gradient mask of 4 consecutive
+// output channels, then the store (the one epilogue of every forward / dgrad path)
+__device__ __forceinline__ void tc_store4(const TcArgs& a, size_t idx, int n, float scale, float x0, float x1, float x2, float x3) {
+  float o[4] = {x0 * scale, x1 * scale, x2 * scale, x3 * scale};
+  if (a.bias) {
+    const float4 b = __ldg(reinterpret_cast<const float4*>(a.bias + n));
+    o[0] += b.x; o[1] += b.y; o[2] += b.z; o[3] += b.w;
+  }
+#pragma unroll
+  for (int e = 0; e < 4; ++e) o[e] = mtd_act(o[e], a.pre_act, a.slope);
+  if (a.aux) *reinterpret_cast<float4*>(a.aux + idx) = make_float4(o[0], o[1], o[2], o[3]);
+  if (a.add1) { float4 t = __ldg(reinterpret_cast<const float4*>(a.add1 + idx)); o[0] += t.x; o[1] += t.y; o[2] += t.z; o[3] += t.w; }
+  if (a.add2) { float4 t = __ldg(reinterpret_cast<const float4*>(a.add2 + idx)); o[0] += t.x; o[1] += t.y; o[2] += t.z; o[3] += t.w; }
+#pragma unroll
+  for (int e = 0; e < 4; ++e) o[e] = mtd_act(o[e], a.post_act, a.slope);
+  if (a.mask_src) {
+    float4 t = __ldg(reinterpret_cast<const float4*>(a.mask_src + idx));
+    o[0] *= mtd_act_grad(t.x, a.mask_act, a.slope); o[1] *= mtd_act_grad(t.y, a.mask_act, a.slope);
+    o[2] *= mtd_act_grad(t.z, a.mask_act, a.slope); o[3] *= mtd_act_grad(t.w, a.mask_act, a.slope);
+  }
+  *reinterpret_cast<float4*>(a.out + idx) = make_float4(o[0], o[1], o[2], o[3]);
+}
+
 struct PipeState {
   int stage = 0;
   uint32_t phase = 0;
@@ -209,6 +232,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gen_base + (tmem_slot - base));
+  // barriers initialised, TMEM allocated, descriptors prefetched: all of it overlapped the previous kernel's tail
+  mtd_pdl_prologue();
 
   auto decode_tile = [&](int tile, int& b0, int& h0, int& w0, int& n0, int& k_begin, int& k_end) {
     const int ks = tile % a.ksplit;
@@ -288,25 +313,24 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
       for (int it = k_begin; it < k_end; ++it) {
         mbar_wait(full_bar(st.stage), st.phase);
         uint4* tileA = reinterpret_cast<uint4*>(gen_base + (size_t)st.stage * kStageBytes);
-        // Integer arithmetic instead of cvt.rna.tf32.f32 (quarter-rate, was the k-step bound for BN <= 64).
-        // 3xTF32: the tensor core truncates its fp32 operand to tf32, so the raw tile already IS a_hi = trunc(a);
-        // only a_lo = rn_tf32(a - trunc(a)) (the difference is exact in fp32) has to be produced.
-        // 1xTF32: round to nearest in place ((bits + 0x1000) & ~0x1fff == cvt.rna: ties away from zero).
+        // Integer arithmetic instead of cvt.rna.tf32.f32 (quarter-rate: it was the k-step bound for BN <= 64):
+        // (bits + 0x1000) & ~0x1fff == cvt.rna (nearest, ties away from zero).  a_hi replaces the raw tile (the
+        // tensor core would TRUNCATE the raw fp32, which biases the split and doubles the dropped lo*lo term);
+        // a_lo = rn_tf32(a - a_hi), the difference being exact in fp32.
 #pragma unroll 8
         for (int j = 0; j < kABytes / 16 / 128; ++j) {
           const uint4 v = tileA[ct + 128 * j];
+          uint4 h;
+          h.x = (v.x + 0x1000u) & 0xffffe000u; h.y = (v.y + 0x1000u) & 0xffffe000u;
+          h.z = (v.z + 0x1000u) & 0xffffe000u; h.w = (v.w + 0x1000u) & 0xffffe000u;
+          tileA[ct + 128 * j] = h;
           if (NPASS == 3) {
             uint4 l;
-            l.x = (__float_as_uint(__uint_as_float(v.x) - __uint_as_float(v.x & 0xffffe000u)) + 0x1000u) & 0xffffe000u;
-            l.y = (__float_as_uint(__uint_as_float(v.y) - __uint_as_float(v.y & 0xffffe000u)) + 0x1000u) & 0xffffe000u;
-            l.z = (__float_as_uint(__uint_as_float(v.z) - __uint_as_float(v.z & 0xffffe000u)) + 0x1000u) & 0xffffe000u;
-            l.w = (__float_as_uint(__uint_as_float(v.w) - __uint_as_float(v.w & 0xffffe000u)) + 0x1000u) & 0xffffe000u;
+            l.x = (__float_as_uint(__uint_as_float(v.x) - __uint_as_float(h.x)) + 0x1000u) & 0xffffe000u;
+            l.y = (__float_as_uint(__uint_as_float(v.y) - __uint_as_float(h.y)) + 0x1000u) & 0xffffe000u;
+            l.z = (__float_as_uint(__uint_as_float(v.z) - __uint_as_float(h.z)) + 0x1000u) & 0xffffe000u;
+            l.w = (__float_as_uint(__uint_as_float(v.w) - __uint_as_float(h.w)) + 0x1000u) & 0xffffe000u;
             tileA[kOffAlo / 16 + ct + 128 * j] = l;
-          } else {
-            uint4 h;
-            h.x = (v.x + 0x1000u) & 0xffffe000u; h.y = (v.y + 0x1000u) & 0xffffe000u;
-            h.z = (v.z + 0x1000u) & 0xffffe000u; h.w = (v.w + 0x1000u) & 0xffffe000u;
-            tileA[ct + 128 * j] = h;
           }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> tensor-core (async proxy) reads
@@ -339,32 +363,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
         uint32_t v[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0), v);
         if (valid && a.ksplit > 1) {
-          // split-K: raw partial sums; scale / bias / activation / adds run in tc_finish_kernel
+          // split-K: raw partial sums into the pre-zeroed output; tc_finish_kernel runs the epilogue
 #pragma unroll
           for (int j = 0; j < 32; ++j) atomicAdd(a.out + rowoff + c0 + j, __uint_as_float(v[j]));
         } else if (valid) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const size_t idx = rowoff + c0 + j;
-            float o[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              float x = __uint_as_float(v[j + e]) * scale;
-              if (a.bias) x += __ldg(a.bias + n0 + c0 + j + e);
-              o[e] = mtd_act(x, a.pre_act, a.slope);
-            }
-            if (a.aux) *reinterpret_cast<float4*>(a.aux + idx) = make_float4(o[0], o[1], o[2], o[3]);
-            if (a.add1) { float4 t = __ldg(reinterpret_cast<const float4*>(a.add1 + idx)); o[0] += t.x; o[1] += t.y; o[2] += t.z; o[3] += t.w; }
-            if (a.add2) { float4 t = __ldg(reinterpret_cast<const float4*>(a.add2 + idx)); o[0] += t.x; o[1] += t.y; o[2] += t.z; o[3] += t.w; }
-#pragma unroll
-            for (int e = 0; e < 4; ++e) o[e] = mtd_act(o[e], a.post_act, a.slope);
-            if (a.mask_src) {
-              float4 t = __ldg(reinterpret_cast<const float4*>(a.mask_src + idx));
-              o[0] *= mtd_act_grad(t.x, a.mask_act, a.slope); o[1] *= mtd_act_grad(t.y, a.mask_act, a.slope);
-              o[2] *= mtd_act_grad(t.z, a.mask_act, a.slope); o[3] *= mtd_act_grad(t.w, a.mask_act, a.slope);
-            }
-            *reinterpret_cast<float4*>(a.out + idx) = make_float4(o[0], o[1], o[2], o[3]);
-          }
+          for (int j = 0; j < 32; j += 4)
+            tc_store4(a, rowoff + c0 + j, n0 + c0 + j, scale, __uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                      __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
         }
       }
       tc_fence_before();
@@ -501,6 +507,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gen_base + (tmem_slot - base));
+  // barriers initialised, TMEM allocated, descriptors prefetched: all of it overlapped the previous kernel's tail
+  mtd_pdl_prologue();
   const uint32_t tmem_a0 = tmem_base + kAccCols;
 
   // tile = (group * n_nt + nt) * ksplit + ks ; group g covers pixel tiles g*MT .. g*MT+MT-1
@@ -687,6 +695,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant
 
 // second phase of a split-K launch: `out` holds raw sums over a dense (B,outH,outW,N) tensor
 __global__ void tc_finish_kernel(const __grid_constant__ TcArgs a, size_t total) {
+  mtd_pdl_prologue();
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
   const float scale = a.scale ? __ldg(a.scale) : 1.f;
   for (; i < total; i += stride) {
@@ -826,7 +835,7 @@ int launch_bn(const CUtensorMap& mA1, const CUtensorMap& mA2, const CUtensorMap&
     attr_set = true;
   }
   int grid = a.n_tiles < mtd_sm_count() ? a.n_tiles : mtd_sm_count();
-  conv_tc_kernel<BN, NPASS><<<grid, kThreads, smem, st>>>(mA1, mA2, mB, mBlo, a);
+  mtd_launch(conv_tc_kernel<BN, NPASS>, grid, kThreads, smem, st, mA1, mA2, mB, mBlo, a);
   MTD_CHECK_LAUNCH();
   return MTD_OK;
 }
@@ -919,7 +928,7 @@ int launch_v2(const CUtensorMap& mA1, const CUtensorMap& mA2, const CUtensorMap&
     attr_set = true;
   }
   int grid = a.n_tiles < mtd_sm_count() ? a.n_tiles : mtd_sm_count();
-  conv_tc2_kernel<BN, MT, NPASS><<<grid, kThreads, smem, st>>>(mA1, mA2, mB, mBlo, a);
+  mtd_launch(conv_tc2_kernel<BN, MT, NPASS>, grid, kThreads, smem, st, mA1, mA2, mB, mBlo, a);
   MTD_CHECK_LAUNCH();
   return MTD_OK;
 }
@@ -931,7 +940,9 @@ int launch_tc(const float* x1, const float* x2, const float* wp, int passes, TcA
               bool finish = true) {
   if (passes != 1 && passes != 3) return MTD_EINVAL;
   if (!tc_geometry(a.B, a.H, a.W, a.C1, a.C2, a.N, 1, 1, 1, 0, &a.TW, &a.TH, &a.TB)) return MTD_EINVAL;
-  if (!mtd_aligned16(x1) || !mtd_aligned16(wp) || !mtd_aligned16(a.out) || (x2 && !mtd_aligned16(x2))) return MTD_EALIGN;
+  if (!mtd_aligned16(x1) || !mtd_aligned16(wp) || !mtd_aligned16(a.out) || (x2 && !mtd_aligned16(x2)) ||
+      (a.bias && !mtd_aligned16(a.bias)))
+    return MTD_EALIGN;
   a.n_wt = a.W / a.TW; a.n_ht = a.H / a.TH; a.n_bt = (a.B + a.TB - 1) / a.TB;
   const int m_tiles = a.n_wt * a.n_ht * a.n_bt;
   a.kc1 = a.C1 / 32; a.kc2 = a.C2 / 32;
@@ -986,13 +997,14 @@ int launch_tc(const float* x1, const float* x2, const float* wp, int passes, TcA
   if (ksplit > 1 && finish) {
     int blocks = (int)((total + 255) / 256);
     if (blocks > sms * 8) blocks = sms * 8;
-    tc_finish_kernel<<<blocks, 256, 0, st>>>(a, total);
+    mtd_launch(tc_finish_kernel, blocks, 256, 0, st, a, total);
     MTD_CHECK_LAUNCH();
   }
   return MTD_OK;
 }
 
 __global__ void split_tf32_kernel(float* __restrict__ hi, float* __restrict__ lo, size_t n) {
+  mtd_pdl_prologue();
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
   for (; i < n; i += stride) {
     float w = hi[i];
@@ -1096,6 +1108,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapX1, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gen_base + (tmem_slot - base));
+  // barriers initialised, TMEM allocated, descriptors prefetched: all of it overlapped the previous kernel's tail
+  mtd_pdl_prologue();
 
   // tile = ((mt * n_nt) + nt) * ksplit + ks
   auto decode_tile = [&](int tile, int& mt, int& n0, int& k_begin, int& k_end) {
@@ -1265,7 +1279,7 @@ int launch_wg(const CUtensorMap& mX1, const CUtensorMap& mX2, const CUtensorMap&
     attr_set = true;
   }
   int grid = a.n_tiles < mtd_sm_count() ? a.n_tiles : mtd_sm_count();
-  wgrad_tc_kernel<BN, NPASS, KP><<<grid, kThreads, smem, st>>>(mX1, mX2, mDz, a);
+  mtd_launch(wgrad_tc_kernel<BN, NPASS, KP>, grid, kThreads, smem, st, mX1, mX2, mDz, a);
   MTD_CHECK_LAUNCH();
   return MTD_OK;
 }
@@ -1289,6 +1303,7 @@ bool wg_geometry(int B, int H, int W, int C1, int C2, int N, int kh, int kw, int
 }
 
 __global__ void round_tf32_kernel(float* __restrict__ p, size_t n) {
+  mtd_pdl_prologue();
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
   for (; i < n; i += stride) {
     uint32_t r;
@@ -1328,7 +1343,7 @@ int mtd_round_tf32(float* p, long long n, void* stream) {
   MTD_REQUIRE(p && n > 0);
   int blocks = (int)(((size_t)n + 255) / 256);
   if (blocks > mtd_sm_count() * 16) blocks = mtd_sm_count() * 16;
-  round_tf32_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(p, (size_t)n);
+  mtd_launch(round_tf32_kernel, blocks, 256, 0, (cudaStream_t)stream, p, (size_t)n);
   MTD_CHECK_LAUNCH();
   return MTD_OK;
 }
@@ -1338,7 +1353,7 @@ int mtd_split_tf32(float* hi, float* lo, long long n, void* stream) {
   MTD_REQUIRE(hi && lo && n > 0);
   int blocks = (int)(((size_t)n + 255) / 256);
   if (blocks > mtd_sm_count() * 16) blocks = mtd_sm_count() * 16;
-  split_tf32_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(hi, lo, (size_t)n);
+  mtd_launch(split_tf32_kernel, blocks, 256, 0, (cudaStream_t)stream, hi, lo, (size_t)n);
   MTD_CHECK_LAUNCH();
   return MTD_OK;
 }
@@ -1420,7 +1435,7 @@ int mtd_conv_dgrad_tc(const float* dz, const float* wpd, float* dx, const float*
   if (ksplit > 1) {
     int blocks = (int)((total + 255) / 256);
     if (blocks > mtd_sm_count() * 8) blocks = mtd_sm_count() * 8;
-    tc_finish_kernel<<<blocks, 256, 0, st>>>(a, total);
+    mtd_launch(tc_finish_kernel, blocks, 256, 0, st, a, total);
     MTD_CHECK_LAUNCH();
   }
   // ksplit == 1: the per-class epilogues already applied scale / adds / mask (each output pixel belongs to one class)

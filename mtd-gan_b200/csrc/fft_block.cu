@@ -84,6 +84,7 @@ __device__ __forceinline__ int bitrev(int k, int logn) { return (int)(__brev((un
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) fft_rows_fwd_kernel(const float* __restrict__ x, float2* __restrict__ spec,
                                                            int H, int W, int C, int logW) {
+  mtd_pdl_prologue();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float2* Z = reinterpret_cast<float2*>(smem_raw);                 // [W][Q]
   const int Q = C >> 1, Wh = (W >> 1) + 1;
@@ -114,6 +115,7 @@ __global__ void __launch_bounds__(256) fft_rows_fwd_kernel(const float* __restri
 __global__ void __launch_bounds__(256) fft_rows_inv_kernel(const float2* __restrict__ spec, const float* __restrict__ add1,
                                                            const float* __restrict__ add2, float* __restrict__ out, int H,
                                                            int W, int C, int logW) {
+  mtd_pdl_prologue();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float2* Z = reinterpret_cast<float2*>(smem_raw);
   const int Q = C >> 1, Wh = (W >> 1) + 1;
@@ -157,6 +159,7 @@ constexpr int kC = 32, kC2 = 64;
 __global__ void __launch_bounds__(256) fft_cols_mix_kernel(const float2* __restrict__ spec_in, float2* __restrict__ spec_out,
                                                            const float* __restrict__ w, const float* __restrict__ bias,
                                                            int H) {
+  mtd_pdl_prologue();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float2* S = reinterpret_cast<float2*>(smem_raw);
   float* Mt = reinterpret_cast<float*>(S + (size_t)H * kC);          // Mt[j][o] = w[o][j] / sqrt(H)
@@ -231,6 +234,7 @@ __global__ void __launch_bounds__(256) fft_cols_mix_bwd_kernel(const float2* __r
                                                                float2* __restrict__ spec_out, const float* __restrict__ w,
                                                                const float* __restrict__ bias, float* __restrict__ part,
                                                                int H, int Wh, int W) {
+  mtd_pdl_prologue();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float2* S = reinterpret_cast<float2*>(smem_raw);
   float2* T = S + (size_t)H * kC;
@@ -385,6 +389,7 @@ __global__ void __launch_bounds__(256) fft_cols_mix_bwd_kernel(const float2* __r
 
 __global__ void fft_wgrad_reduce_kernel(const float* __restrict__ part, int nparts, float* __restrict__ dw,
                                         float* __restrict__ db) {
+  mtd_pdl_prologue();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int per = kC2 * kC2 + kC2;
   if (i >= per) return;
@@ -430,7 +435,7 @@ int mtd_fft_rows_fwd(const float* x, float* spec, int B, int H, int W, int C, vo
   size_t smem = (size_t)W * C * 4 + (size_t)(W / 2) * 8;
   int rc = set_smem(fft_rows_fwd_kernel, smem);
   if (rc) return rc;
-  fft_rows_fwd_kernel<<<B * H, 256, smem, (cudaStream_t)stream>>>(x, reinterpret_cast<float2*>(spec), H, W, C, lw);
+  mtd_launch(fft_rows_fwd_kernel, B * H, 256, smem, (cudaStream_t)stream, x, reinterpret_cast<float2*>(spec), H, W, C, lw);
   MTD_CHECK_LAUNCH();
   return MTD_OK;
 }
@@ -443,7 +448,7 @@ int mtd_fft_rows_inv(const float* spec, const float* add1, const float* add2, fl
   size_t smem = (size_t)W * C * 4 + (size_t)(W / 2) * 8;
   int rc = set_smem(fft_rows_inv_kernel, smem);
   if (rc) return rc;
-  fft_rows_inv_kernel<<<B * H, 256, smem, (cudaStream_t)stream>>>(reinterpret_cast<const float2*>(spec), add1, add2, out,
+  mtd_launch(fft_rows_inv_kernel, B * H, 256, smem, (cudaStream_t)stream, reinterpret_cast<const float2*>(spec), add1, add2, out,
                                                                   H, W, C, lw);
   MTD_CHECK_LAUNCH();
   return MTD_OK;
@@ -457,7 +462,7 @@ int mtd_fft_cols_mix(const float* spec_in, float* spec_out, const float* w, cons
   size_t smem = (size_t)H * kC * 8 + (size_t)kC2 * kC2 * 4 + kC2 * 4 + (size_t)(H / 2) * 8;
   int rc = set_smem(fft_cols_mix_kernel, smem);
   if (rc) return rc;
-  fft_cols_mix_kernel<<<B * (W / 2 + 1), 256, smem, (cudaStream_t)stream>>>(
+  mtd_launch(fft_cols_mix_kernel, B * (W / 2 + 1), 256, smem, (cudaStream_t)stream, 
       reinterpret_cast<const float2*>(spec_in), reinterpret_cast<float2*>(spec_out), w, bias, H);
   MTD_CHECK_LAUNCH();
   return MTD_OK;
@@ -473,12 +478,12 @@ int mtd_fft_cols_mix_bwd(const float* spec_x, const float* spec_g, float* spec_o
   if (rc) return rc;
   const int Wh = W / 2 + 1, nparts = B * Wh;
   cudaStream_t st = (cudaStream_t)stream;
-  fft_cols_mix_bwd_kernel<<<nparts, 256, smem, st>>>(reinterpret_cast<const float2*>(spec_x),
+  mtd_launch(fft_cols_mix_bwd_kernel, nparts, 256, smem, st, reinterpret_cast<const float2*>(spec_x),
                                                      reinterpret_cast<const float2*>(spec_g),
                                                      reinterpret_cast<float2*>(spec_out), w, bias, part, H, Wh, W);
   MTD_CHECK_LAUNCH();
   const int per = kC2 * kC2 + kC2;
-  fft_wgrad_reduce_kernel<<<(per + 127) / 128, 128, 0, st>>>(part, nparts, dw, db);
+  mtd_launch(fft_wgrad_reduce_kernel, (per + 127) / 128, 128, 0, st, part, nparts, dw, db);
   MTD_CHECK_LAUNCH();
   return MTD_OK;
 }

@@ -29,6 +29,7 @@ __device__ __forceinline__ void block_accumulate(double v, double* dst) {
 }
 
 __global__ void nds_mask_kernel(const float* __restrict__ x, const float* __restrict__ y, unsigned char* __restrict__ m, size_t n) {
+  mtd_pdl_prologue();
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
   for (; i < n; i += stride) m[i] = nds_keep(x[i], y[i]) ? 1 : 0;
 }
@@ -36,6 +37,7 @@ __global__ void nds_mask_kernel(const float* __restrict__ x, const float* __rest
 // sum mask * (in - t)^2
 __global__ void sum_sqerr_kernel(const float* __restrict__ in, float t, const float* __restrict__ x, const float* __restrict__ y,
                                  size_t n, double* acc) {
+  mtd_pdl_prologue();
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
   double s = 0.0;
   for (; i < n; i += stride) {
@@ -49,6 +51,7 @@ __global__ void sum_sqerr_kernel(const float* __restrict__ in, float t, const fl
 // din = coef * mask * 2 (in - t), coef = (g[0] + g[k]) * scale
 __global__ void sqerr_bwd_kernel(const float* __restrict__ in, float t, const float* __restrict__ x, const float* __restrict__ y,
                                  size_t n, const float* __restrict__ g, int k, float scale, float* __restrict__ din) {
+  mtd_pdl_prologue();
   const float coef = (g[0] + g[k]) * scale * 2.f;
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
   for (; i < n; i += stride) {
@@ -61,6 +64,7 @@ __global__ void sqerr_bwd_kernel(const float* __restrict__ in, float t, const fl
 // mode 0: |a-b|   mode 1: (a-b)^2   mode 2: sqrt((a-b)^2 + eps^2)
 __global__ void sum_diff_kernel(const float* __restrict__ a, const float* __restrict__ b, size_t n, int mode, float eps2,
                                 double* acc) {
+  mtd_pdl_prologue();
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
   double s = 0.0;
   for (; i < n; i += stride) {
@@ -73,6 +77,7 @@ __global__ void sum_diff_kernel(const float* __restrict__ a, const float* __rest
 // da = coef * f'(a-b); db = -da (optional)
 __global__ void diff_bwd_kernel(const float* __restrict__ a, const float* __restrict__ b, size_t n, int mode, float eps2,
                                 const float* __restrict__ g, int k, float scale, float* __restrict__ da, float* __restrict__ db) {
+  mtd_pdl_prologue();
   const float coef = (g[0] + g[k]) * scale;
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
   for (; i < n; i += stride) {
@@ -140,6 +145,7 @@ __device__ void gauss_scatter(const float* src, float* dst, int H, int W, bool s
 __global__ void __launch_bounds__(256) edge_kernel(const float* __restrict__ x, const float* __restrict__ y, int H, int W,
                                                    float eps2, double* acc, const float* __restrict__ g, int k_edge,
                                                    float scale_edge, int k_pix, float scale_pix, float* __restrict__ dfake) {
+  mtd_pdl_prologue();
   extern __shared__ float sm[];
   float* d = sm;
   float* t1 = d + H * W;
@@ -185,6 +191,7 @@ __global__ void __launch_bounds__(256) edge_kernel(const float* __restrict__ x, 
 
 __global__ void loss_finalize_kernel(const double* __restrict__ acc, int k, float s0, float s1, float s2, float s3,
                                      float* __restrict__ out) {
+  mtd_pdl_prologue();
   const float sc[4] = {s0, s1, s2, s3};
   float total = 0.f;
   for (int i = 0; i < k; ++i) {
@@ -201,7 +208,7 @@ extern "C" {
 
 int mtd_nds_mask(const float* x, const float* y, unsigned char* mask, long long n, void* stream) {
   MTD_REQUIRE(x && y && mask && n > 0);
-  nds_mask_kernel<<<grid_for((size_t)n), 256, 0, (cudaStream_t)stream>>>(x, y, mask, (size_t)n);
+  mtd_launch(nds_mask_kernel, grid_for((size_t)n), 256, 0, (cudaStream_t)stream, x, y, mask, (size_t)n);
   MTD_CHECK_LAUNCH();
   return MTD_OK;
 }
@@ -209,28 +216,28 @@ int mtd_nds_mask(const float* x, const float* y, unsigned char* mask, long long 
 // acc[0] += sum_i mask_i (in_i - target)^2 ; mask = NDS mask of (x, y) or all-true when x == null
 int mtd_sum_sqerr(const float* in, float target, const float* x, const float* y, long long n, double* acc, void* stream) {
   MTD_REQUIRE(in && acc && n > 0 && ((x == nullptr) == (y == nullptr)));
-  sum_sqerr_kernel<<<grid_for((size_t)n), 256, 0, (cudaStream_t)stream>>>(in, target, x, y, (size_t)n, acc);
+  mtd_launch(sum_sqerr_kernel, grid_for((size_t)n), 256, 0, (cudaStream_t)stream, in, target, x, y, (size_t)n, acc);
   MTD_CHECK_LAUNCH();
   return MTD_OK;
 }
 int mtd_sqerr_bwd(const float* in, float target, const float* x, const float* y, long long n, const float* gout, int k,
                   float scale, float* din, void* stream) {
   MTD_REQUIRE(in && gout && din && n > 0 && ((x == nullptr) == (y == nullptr)));
-  sqerr_bwd_kernel<<<grid_for((size_t)n), 256, 0, (cudaStream_t)stream>>>(in, target, x, y, (size_t)n, gout, k, scale, din);
+  mtd_launch(sqerr_bwd_kernel, grid_for((size_t)n), 256, 0, (cudaStream_t)stream, in, target, x, y, (size_t)n, gout, k, scale, din);
   MTD_CHECK_LAUNCH();
   return MTD_OK;
 }
 // mode 0 L1, 1 squared, 2 Charbonnier(eps)
 int mtd_sum_diff(const float* a, const float* b, long long n, int mode, float eps, double* acc, void* stream) {
   MTD_REQUIRE(a && b && acc && n > 0 && mode >= 0 && mode <= 2);
-  sum_diff_kernel<<<grid_for((size_t)n), 256, 0, (cudaStream_t)stream>>>(a, b, (size_t)n, mode, eps * eps, acc);
+  mtd_launch(sum_diff_kernel, grid_for((size_t)n), 256, 0, (cudaStream_t)stream, a, b, (size_t)n, mode, eps * eps, acc);
   MTD_CHECK_LAUNCH();
   return MTD_OK;
 }
 int mtd_diff_bwd(const float* a, const float* b, long long n, int mode, float eps, const float* gout, int k, float scale,
                  float* da, float* db, void* stream) {
   MTD_REQUIRE(a && b && gout && (da || db) && n > 0 && mode >= 0 && mode <= 2);
-  diff_bwd_kernel<<<grid_for((size_t)n), 256, 0, (cudaStream_t)stream>>>(a, b, (size_t)n, mode, eps * eps, gout, k, scale, da, db);
+  mtd_launch(diff_bwd_kernel, grid_for((size_t)n), 256, 0, (cudaStream_t)stream, a, b, (size_t)n, mode, eps * eps, gout, k, scale, da, db);
   MTD_CHECK_LAUNCH();
   return MTD_OK;
 }
@@ -240,7 +247,7 @@ int mtd_sum_edge(const float* x, const float* y, int B, int H, int W, float eps,
   size_t smem = (size_t)H * W * 4 * sizeof(float);
   MTD_REQUIRE(smem <= 200 * 1024);
   if (smem > 48 * 1024) MTD_CUDA(cudaFuncSetAttribute(edge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  edge_kernel<<<B, 256, smem, (cudaStream_t)stream>>>(x, y, H, W, eps * eps, acc, nullptr, 0, 0.f, -1, 0.f, nullptr);
+  mtd_launch(edge_kernel, B, 256, smem, (cudaStream_t)stream, x, y, H, W, eps * eps, acc, nullptr, 0, 0.f, -1, 0.f, nullptr);
   MTD_CHECK_LAUNCH();
   return MTD_OK;
 }
@@ -251,7 +258,7 @@ int mtd_edge_bwd(const float* x, const float* y, int B, int H, int W, float eps,
   size_t smem = (size_t)H * W * 4 * sizeof(float);
   MTD_REQUIRE(smem <= 200 * 1024);
   if (smem > 48 * 1024) MTD_CUDA(cudaFuncSetAttribute(edge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  edge_kernel<<<B, 256, smem, (cudaStream_t)stream>>>(x, y, H, W, eps * eps, nullptr, gout, k_edge, scale_edge, k_pix,
+  mtd_launch(edge_kernel, B, 256, smem, (cudaStream_t)stream, x, y, H, W, eps * eps, nullptr, gout, k_edge, scale_edge, k_pix,
                                                       scale_pix, dx);
   MTD_CHECK_LAUNCH();
   return MTD_OK;
@@ -259,7 +266,7 @@ int mtd_edge_bwd(const float* x, const float* y, int B, int H, int W, float eps,
 // out[1+i] = acc[i]*scale[i] (i < k <= 4); out[0] = their fp32 sum
 int mtd_loss_finalize(const double* acc, int k, float s0, float s1, float s2, float s3, float* out, void* stream) {
   MTD_REQUIRE(acc && out && k >= 1 && k <= 4);
-  loss_finalize_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(acc, k, s0, s1, s2, s3, out);
+  mtd_launch(loss_finalize_kernel, 1, 1, 0, (cudaStream_t)stream, acc, k, s0, s1, s2, s3, out);
   MTD_CHECK_LAUNCH();
   return MTD_OK;
 }

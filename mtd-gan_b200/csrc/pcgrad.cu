@@ -32,6 +32,7 @@ static_assert(sizeof(Seg) == 64, "segment entry must be 8 x int64");
 
 __global__ void __launch_bounds__(256) pcgrad_gram_kernel(const Seg* __restrict__ segs, const int2* __restrict__ chunks,
                                                           int T, double* __restrict__ gram) {
+  mtd_pdl_prologue();
   __shared__ double sh[32];
   const int2 ck = chunks[blockIdx.x];
   const Seg s = segs[ck.x];
@@ -73,6 +74,7 @@ __global__ void __launch_bounds__(256) pcgrad_gram_kernel(const Seg* __restrict_
 // outer task i.  coef_out[k] = sum_i C[i][k] * (mean ? 1/T : 1); cmat_out[T][T] = C (for tests).
 __global__ void pcgrad_solve_kernel(double* __restrict__ gram, const int* __restrict__ orders, int T, int mean,
                                     float* __restrict__ coef_out, float* __restrict__ cmat_out, double* __restrict__ gram_out) {
+  mtd_pdl_prologue();
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   double G[kMaxTasks][kMaxTasks], C[kMaxTasks][kMaxTasks];
   for (int a = 0; a < T; ++a)
@@ -101,6 +103,7 @@ __global__ void pcgrad_solve_kernel(double* __restrict__ gram, const int* __rest
 
 __global__ void __launch_bounds__(256) pcgrad_combine_kernel(const Seg* __restrict__ segs, const int2* __restrict__ chunks,
                                                              int T, const float* __restrict__ coef) {
+  mtd_pdl_prologue();
   const int2 ck = chunks[blockIdx.x];
   const Seg s = segs[ck.x];
   const long long end = min(s.numel, (long long)ck.y + kChunk);
@@ -129,7 +132,7 @@ int mtd_pcgrad_gram(const void* seg_tab, const void* chunk_tab, int n_chunks, in
   MTD_REQUIRE(seg_tab && chunk_tab && gram_ws && n_chunks > 0 && T >= 1 && T <= kMaxTasks);
   cudaStream_t st = (cudaStream_t)stream;
   MTD_CUDA(cudaMemsetAsync(gram_ws, 0, 16 * sizeof(double), st));
-  pcgrad_gram_kernel<<<n_chunks, 256, 0, st>>>(reinterpret_cast<const Seg*>(seg_tab),
+  mtd_launch(pcgrad_gram_kernel, n_chunks, 256, 0, st, reinterpret_cast<const Seg*>(seg_tab),
                                                reinterpret_cast<const int2*>(chunk_tab), T, gram_ws);
   MTD_CHECK_LAUNCH();
   return MTD_OK;
@@ -140,9 +143,9 @@ int mtd_pcgrad_solve_combine(const void* seg_tab, const void* chunk_tab, int n_c
                              double* gram_ws, float* coef_out, float* cmat_out, double* gram_out, void* stream) {
   MTD_REQUIRE(seg_tab && chunk_tab && orders && gram_ws && coef_out && n_chunks > 0 && T >= 1 && T <= kMaxTasks);
   cudaStream_t st = (cudaStream_t)stream;
-  pcgrad_solve_kernel<<<1, 32, 0, st>>>(gram_ws, orders, T, mean, coef_out, cmat_out, gram_out);
+  mtd_launch(pcgrad_solve_kernel, 1, 32, 0, st, gram_ws, orders, T, mean, coef_out, cmat_out, gram_out);
   MTD_CHECK_LAUNCH();
-  pcgrad_combine_kernel<<<n_chunks, 256, 0, st>>>(reinterpret_cast<const Seg*>(seg_tab),
+  mtd_launch(pcgrad_combine_kernel, n_chunks, 256, 0, st, reinterpret_cast<const Seg*>(seg_tab),
                                                   reinterpret_cast<const int2*>(chunk_tab), T, coef_out);
   MTD_CHECK_LAUNCH();
   return MTD_OK;

@@ -17,6 +17,7 @@ inline int grid_for(size_t n, int per_block = 256, int waves = 16) {
 
 // out[b, Y, X, c]: source coordinate src = max(0, (Y+0.5)/2 - 0.5), i0 = floor, i1 = min(i0+1, H-1)
 __global__ void upsample2x_fwd_kernel(const float* __restrict__ in, float* __restrict__ out, int B, int H, int W, int C) {
+  mtd_pdl_prologue();
   const int Ho = 2 * H, Wo = 2 * W;
   size_t total = (size_t)B * Ho * Wo * C;
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
@@ -40,6 +41,7 @@ __global__ void upsample2x_fwd_kernel(const float* __restrict__ in, float* __res
 
 // adjoint: din[i] gathers from Y in {2i, 2i+1 (0.75)}, {max(2i-1,0), min(2i+2, 2H-1) (0.25)}
 __global__ void upsample2x_bwd_kernel(const float* __restrict__ dout, float* __restrict__ din, int B, int H, int W, int C) {
+  mtd_pdl_prologue();
   const int Ho = 2 * H, Wo = 2 * W;
   size_t total = (size_t)B * H * W * C;
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
@@ -69,6 +71,7 @@ __global__ void upsample2x_bwd_kernel(const float* __restrict__ dout, float* __r
 // out[b, 2h+i, 2w+j, c] = in[b, h, w, 4c + 2i + j]
 __global__ void pixel_shuffle2_kernel(const float* __restrict__ in, float* __restrict__ out, int B, int H, int W, int C,
                                       int inverse) {
+  mtd_pdl_prologue();
   // C = output channels; `in` has 4C channels.  inverse: scatter direction swapped (backward).
   const int Ho = 2 * H, Wo = 2 * W;
   size_t total = (size_t)B * Ho * Wo * C;
@@ -88,6 +91,7 @@ __global__ void pixel_shuffle2_kernel(const float* __restrict__ in, float* __res
 
 // (B,C,H,W) <-> (B,H,W,C) through a 32x32 shared tile; hw = H*W
 __global__ void transpose_chw_kernel(const float* __restrict__ in, float* __restrict__ out, int rows, int cols) {
+  mtd_pdl_prologue();
   // per batch item: in is (rows, cols) row-major, out is (cols, rows)
   __shared__ float tile[32][33];
   const size_t boff = (size_t)blockIdx.z * rows * cols;
@@ -104,6 +108,7 @@ __global__ void transpose_chw_kernel(const float* __restrict__ in, float* __rest
 }
 
 __global__ void clip01_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, size_t n) {
+  mtd_pdl_prologue();
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
   for (; i < n; i += stride) {
     float v = x[i];
@@ -111,6 +116,7 @@ __global__ void clip01_fwd_kernel(const float* __restrict__ x, float* __restrict
   }
 }
 __global__ void clip01_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dx, size_t n) {
+  mtd_pdl_prologue();
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
   for (; i < n; i += stride) {
     float v = x[i];
@@ -118,12 +124,14 @@ __global__ void clip01_bwd_kernel(const float* __restrict__ x, const float* __re
   }
 }
 __global__ void mul_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out, size_t n) {
+  mtd_pdl_prologue();
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
   for (; i < n; i += stride) out[i] = a[i] * b[i];
 }
 // out = a + b (+ c): gradient fan-in of skip tensors
 __global__ void add3_kernel(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ c,
                             float* __restrict__ out, size_t n) {
+  mtd_pdl_prologue();
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
   for (; i < n; i += stride) out[i] = a[i] + b[i] + (c ? c[i] : 0.f);
 }
@@ -135,14 +143,14 @@ extern "C" {
 int mtd_upsample2x_fwd(const float* in, float* out, int B, int H, int W, int C, void* stream) {
   MTD_REQUIRE(in && out && B > 0 && H > 0 && W > 0 && C > 0);
   size_t n = (size_t)B * 4 * H * W * C;
-  upsample2x_fwd_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(in, out, B, H, W, C);
+  mtd_launch(upsample2x_fwd_kernel, grid_for(n), 256, 0, (cudaStream_t)stream, in, out, B, H, W, C);
   MTD_CHECK_LAUNCH();
   return MTD_OK;
 }
 int mtd_upsample2x_bwd(const float* dout, float* din, int B, int H, int W, int C, void* stream) {
   MTD_REQUIRE(dout && din && B > 0 && H > 0 && W > 0 && C > 0);
   size_t n = (size_t)B * H * W * C;
-  upsample2x_bwd_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(dout, din, B, H, W, C);
+  mtd_launch(upsample2x_bwd_kernel, grid_for(n), 256, 0, (cudaStream_t)stream, dout, din, B, H, W, C);
   MTD_CHECK_LAUNCH();
   return MTD_OK;
 }
@@ -150,7 +158,7 @@ int mtd_upsample2x_bwd(const float* dout, float* din, int B, int H, int W, int C
 int mtd_pixel_shuffle2(const float* in, float* out, int B, int H, int W, int C, int backward, void* stream) {
   MTD_REQUIRE(in && out && B > 0 && H > 0 && W > 0 && C > 0);
   size_t n = (size_t)B * 4 * H * W * C;
-  pixel_shuffle2_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(in, out, B, H, W, C, backward);
+  mtd_launch(pixel_shuffle2_kernel, grid_for(n), 256, 0, (cudaStream_t)stream, in, out, B, H, W, C, backward);
   MTD_CHECK_LAUNCH();
   return MTD_OK;
 }
@@ -160,31 +168,31 @@ int mtd_layout_transpose(const float* in, float* out, int B, int C, int HW, int 
   int rows = to_nhwc ? C : HW, cols = to_nhwc ? HW : C;
   dim3 grid((cols + 31) / 32, (rows + 31) / 32, B), block(32, 8);
   MTD_REQUIRE(grid.y <= 65535);
-  transpose_chw_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(in, out, rows, cols);
+  mtd_launch(transpose_chw_kernel, grid, block, 0, (cudaStream_t)stream, in, out, rows, cols);
   MTD_CHECK_LAUNCH();
   return MTD_OK;
 }
 int mtd_clip01_fwd(const float* x, float* y, long long n, void* stream) {
   MTD_REQUIRE(x && y && n > 0);
-  clip01_fwd_kernel<<<grid_for((size_t)n), 256, 0, (cudaStream_t)stream>>>(x, y, (size_t)n);
+  mtd_launch(clip01_fwd_kernel, grid_for((size_t)n), 256, 0, (cudaStream_t)stream, x, y, (size_t)n);
   MTD_CHECK_LAUNCH();
   return MTD_OK;
 }
 int mtd_clip01_bwd(const float* x, const float* dy, float* dx, long long n, void* stream) {
   MTD_REQUIRE(x && dy && dx && n > 0);
-  clip01_bwd_kernel<<<grid_for((size_t)n), 256, 0, (cudaStream_t)stream>>>(x, dy, dx, (size_t)n);
+  mtd_launch(clip01_bwd_kernel, grid_for((size_t)n), 256, 0, (cudaStream_t)stream, x, dy, dx, (size_t)n);
   MTD_CHECK_LAUNCH();
   return MTD_OK;
 }
 int mtd_mul(const float* a, const float* b, float* out, long long n, void* stream) {
   MTD_REQUIRE(a && b && out && n > 0);
-  mul_kernel<<<grid_for((size_t)n), 256, 0, (cudaStream_t)stream>>>(a, b, out, (size_t)n);
+  mtd_launch(mul_kernel, grid_for((size_t)n), 256, 0, (cudaStream_t)stream, a, b, out, (size_t)n);
   MTD_CHECK_LAUNCH();
   return MTD_OK;
 }
 int mtd_add3(const float* a, const float* b, const float* c, float* out, long long n, void* stream) {
   MTD_REQUIRE(a && b && out && n > 0);
-  add3_kernel<<<grid_for((size_t)n), 256, 0, (cudaStream_t)stream>>>(a, b, c, out, (size_t)n);
+  mtd_launch(add3_kernel, grid_for((size_t)n), 256, 0, (cudaStream_t)stream, a, b, c, out, (size_t)n);
   MTD_CHECK_LAUNCH();
   return MTD_OK;
 }

@@ -25,6 +25,7 @@ constexpr int kRowsPerWtu = 32;
 // work item: {layer, col0, row0, 0}; 256 columns x 32 rows per CTA
 __global__ void __launch_bounds__(256) sn_wtu_kernel(const SnLayer* __restrict__ tab, const int4* __restrict__ work,
                                                      float* __restrict__ t_ws) {
+  mtd_pdl_prologue();
   const int4 wk = work[blockIdx.x];
   const SnLayer L = tab[wk.x];
   const long long col = wk.y + threadIdx.x;
@@ -39,6 +40,7 @@ __global__ void __launch_bounds__(256) sn_wtu_kernel(const SnLayer* __restrict__
 // one CTA per layer: v = t / max(|t|, eps)
 __global__ void __launch_bounds__(256) sn_norm_v_kernel(const SnLayer* __restrict__ tab, const float* __restrict__ t_ws,
                                                         float* __restrict__ v_snap, float eps) {
+  mtd_pdl_prologue();
   __shared__ float sh[32];
   const SnLayer L = tab[blockIdx.x];
   const float* t = t_ws + L.voff;
@@ -56,6 +58,7 @@ __global__ void __launch_bounds__(256) sn_norm_v_kernel(const SnLayer* __restric
 // work item: {layer, row0}; 8 rows per CTA, one warp per row
 __global__ void __launch_bounds__(256) sn_wv_kernel(const SnLayer* __restrict__ tab, const int2* __restrict__ work,
                                                     float* __restrict__ s_ws) {
+  mtd_pdl_prologue();
   const int2 wk = work[blockIdx.x];
   const SnLayer L = tab[wk.x];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -72,6 +75,7 @@ __global__ void __launch_bounds__(256) sn_wv_kernel(const SnLayer* __restrict__ 
 __global__ void __launch_bounds__(256) sn_norm_u_kernel(const SnLayer* __restrict__ tab, const float* __restrict__ s_ws,
                                                         float* __restrict__ u_snap, float* __restrict__ inv_sigma,
                                                         int update, float eps) {
+  mtd_pdl_prologue();
   __shared__ float sh[32];
   const SnLayer L = tab[blockIdx.x];
   const float* s = s_ws + L.uoff;
@@ -102,6 +106,7 @@ __global__ void __launch_bounds__(256) sn_norm_u_kernel(const SnLayer* __restric
 }
 
 __global__ void sn_copy_v_kernel(const SnLayer* __restrict__ tab, float* __restrict__ v_snap) {
+  mtd_pdl_prologue();
   const SnLayer L = tab[blockIdx.x];
   for (int k = threadIdx.x; k < L.cols; k += blockDim.x) v_snap[L.voff + k] = L.v[k];
 }
@@ -123,17 +128,17 @@ int mtd_sn_power_iter(const void* layer_tab, int n_layers, const void* work_wtu,
   if (update) {
     MTD_REQUIRE(work_wtu && t_ws && n_wtu > 0 && t_elems > 0);
     MTD_CUDA(cudaMemsetAsync(t_ws, 0, (size_t)t_elems * sizeof(float), st));
-    sn_wtu_kernel<<<n_wtu, 256, 0, st>>>(tab, reinterpret_cast<const int4*>(work_wtu), t_ws);
+    mtd_launch(sn_wtu_kernel, n_wtu, 256, 0, st, tab, reinterpret_cast<const int4*>(work_wtu), t_ws);
     MTD_CHECK_LAUNCH();
-    sn_norm_v_kernel<<<n_layers, 256, 0, st>>>(tab, t_ws, v_snap, eps);
+    mtd_launch(sn_norm_v_kernel, n_layers, 256, 0, st, tab, t_ws, v_snap, eps);
     MTD_CHECK_LAUNCH();
   } else {
-    sn_copy_v_kernel<<<n_layers, 256, 0, st>>>(tab, v_snap);
+    mtd_launch(sn_copy_v_kernel, n_layers, 256, 0, st, tab, v_snap);
     MTD_CHECK_LAUNCH();
   }
-  sn_wv_kernel<<<n_wv, 256, 0, st>>>(tab, reinterpret_cast<const int2*>(work_wv), s_ws);
+  mtd_launch(sn_wv_kernel, n_wv, 256, 0, st, tab, reinterpret_cast<const int2*>(work_wv), s_ws);
   MTD_CHECK_LAUNCH();
-  sn_norm_u_kernel<<<n_layers, 256, 0, st>>>(tab, s_ws, u_snap, inv_sigma, update, eps);
+  mtd_launch(sn_norm_u_kernel, n_layers, 256, 0, st, tab, s_ws, u_snap, inv_sigma, update, eps);
   MTD_CHECK_LAUNCH();
   return MTD_OK;
 }

@@ -7,7 +7,7 @@ import random
 import pytest
 import torch
 
-from _golden_util import check_summary, load, rel_err
+from _golden_util import GradTally, check_summary, load, rel_err
 from oracle import mtdgan_oracle as O
 
 pytestmark = pytest.mark.gpu
@@ -38,7 +38,7 @@ class Tol:
         self.mode = mode
         self.out = {"simt": 1e-4, "tc3": 3e-4, "tc1": 1e-2}[mode]
         self.grad = {"simt": 2e-4, "tc3": 2e-3, "tc1": 1e-1}[mode]
-        self.median = {"simt": 1e-4, "tc3": 3e-4, "tc1": 1e-2}[mode]
+        self.median = {"simt": 1e-4, "tc3": 1e-3, "tc1": 1e-2}[mode]   # tc3: weight gradients run in plain TF32 (2e-3 class)
 
 
 @pytest.fixture(params=["simt", "tc3", "tc1"])
@@ -97,12 +97,11 @@ def test_generator_backward_vs_oracle(conv_mode):
     # noise floor: the oracle's own fp32-vs-fp64 gap on the same weights (ReLU-mask flips, see _golden_util)
     sd64 = {k: v.detach().double().requires_grad_(True) for k, v in sd.items()}
     (O.generator_forward(sd64, x.double()) * w.double()).sum().backward()
-    errs = []
+    tally = GradTally()
     for k, p in m.Generator.named_parameters():
         floor = rel_err(sd[k].grad, sd64[k].grad)
-        errs.append(rel_err(p.grad, sd[k].grad))
-        assert errs[-1] <= max(conv_mode.grad, 30 * floor), (k, errs[-1], floor)
-    assert sorted(errs)[len(errs) // 2] <= conv_mode.median
+        tally.add(k, rel_err(p.grad, sd[k].grad), max(conv_mode.grad, 30 * floor))
+    tally.finish(conv_mode.median)
 
 
 def test_discriminator_vs_golden(masks, conv_mode):
@@ -118,12 +117,15 @@ def test_discriminator_vs_golden(masks, conv_mode):
     g = torch.Generator().manual_seed(15)
     a, b, c = (torch.randn(s, generator=g).to(DEV) for s in (enc.shape, dec.shape, rec.shape))
     ((enc * a).sum() + (dec * b).sum() / 64 + (rec * c).sum() / 64).backward()
+    tally = GradTally()
     for k, p in D.named_parameters():
         if k in fix["grads"]:
             if conv_mode.mode != "tc1":
-                check_summary(p.grad, fix["grads"][k], conv_mode.grad, k)
+                check_summary(p.grad, fix["grads"][k], conv_mode.grad, k, tally=tally)
         else:
             assert p.grad is None, k
+    if conv_mode.mode != "tc1":
+        tally.finish()
     for k, v in D.named_buffers():
         check_summary(v, fix["buffers"][k], 1e-5, k)
     D.eval()
@@ -162,11 +164,13 @@ def test_full_train_step_b4_vs_golden(masks, conv_mode):
                                 task_specific_parameters=list(D.task_specific_parameters()),
                                 last_shared_parameters=list(D.last_shared_parameters()))
     assert loss_D is None and extra == {}
+    tally = GradTally()
     for k, p in D.named_parameters():
         if fix["d_grads"][k] is None:
             assert p.grad is None, k                               # c_fc.* 
         else:
-            check_summary(p.grad, fix["d_grads"][k], cm.grad, k, noise=fix["d_grads_noise"][k])
+            check_summary(p.grad, fix["d_grads"][k], cm.grad, k, noise=fix["d_grads_noise"][k], tally=tally)
+    tally.finish()
     opt_D.step()
     opt_G.zero_grad(); G.zero_grad()
     g_loss, gdet = m.g_loss(x, y)
@@ -174,8 +178,10 @@ def test_full_train_step_b4_vs_golden(masks, conv_mode):
     for k, v in fix["g_details"].items():
         assert torch.allclose(gdet[k].cpu(), v, rtol=cm.out, atol=1e-8), k
     g_loss.backward()
-    errs = [check_summary(p.grad, fix["g_grads"][k], cm.grad, k, noise=fix["g_grads_noise"][k])[0]
+    tally = GradTally()
+    errs = [check_summary(p.grad, fix["g_grads"][k], cm.grad, k, noise=fix["g_grads_noise"][k], tally=tally)[0]
             for k, p in G.named_parameters()]
+    tally.finish()
     assert sorted(errs)[len(errs) // 2] <= cm.median     # median norm error over the 128 generator tensors
     opt_G.step()
     sd = m.state_dict()

@@ -22,6 +22,7 @@ def main():
     ap.add_argument("--batch", type=int, default=20)
     ap.add_argument("--passes", type=int, default=3)
     ap.add_argument("--quick", action="store_true")
+    ap.add_argument("--only", type=int, default=-1, help="index of a single shape to sweep")
     ap.add_argument("--versions", default="1,2", help="kernel generations to sweep")
     args = ap.parse_args()
     from mtdgan_b200 import ops, _ext
@@ -39,6 +40,8 @@ def main():
     ]
     if args.quick:
         shapes = shapes[::3]
+    if args.only >= 0:
+        shapes = [shapes[args.only]]
     lib = _ext.load()
     versions = [int(v) for v in args.versions.split(",")]
     for (H, C1, C2, N, k) in shapes:
