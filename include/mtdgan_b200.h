@@ -96,20 +96,25 @@ int mtd_conv_fwd_tc_supported(int B, int H, int W, int C1, int C2, int N, int kh
 /* kernel generation of the forward/dgrad tensor-core path: 1 = A through shared memory, 2 = A through TMEM with
  * several pixel tiles per CTA (weights streamed once per group).  Returns the previous setting.              */
 int mtd_tc_set_version(int version);
-/* tuning hook: force the Cout tile width (32/64/128) and/or split-K factor of the forward/dgrad tensor-core kernels;
- * 0 = chosen by the built-in cost model (the default).                                                        */
-int mtd_tc_set_tuning(int bn, int ksplit);
+/* tuning hook: force the Cout tile width (32/64/128) and/or the stream-K piece length (k-steps per CTA, -1 = whole
+ * tiles only) of the forward/dgrad tensor-core kernel; 0 = chosen by the built-in cost model (the default).     */
+int mtd_tc_set_tuning(int bn, int sk_per);
 /* in-place round-to-nearest fp32 -> tf32 of a packed weight buffer (tcgen05 truncates its operands)  */
 int mtd_round_tf32(float* p, long long n, void* stream);
+/* ws / ws_floats (both TC entry points): caller-owned fp32 scratch (contents undefined before and after; one per
+ * stream).  With it, layers whose tile count is not a multiple of the SM count run their remainder as a stream-K wave
+ * (k-range pieces -> partial tiles in ws -> ordered reduction + epilogue): balanced SMs, deterministic, no atomics.
+ * ws = NULL: whole output tiles only (correct, slower for skinny layers).  32 MB covers every layer of the model. */
 int mtd_conv_fwd_tc(const float* x1, const float* x2, const float* wp, const float* bias, const float* scale, float* y,
                     float* aux, const float* add1, const float* add2, int B, int H, int W, int C1, int C2, int N, int kh,
-                    int kw, int stride, int pad, int pre_act, int post_act, float slope, int passes, void* stream);
+                    int kw, int stride, int pad, int pre_act, int post_act, float slope, int passes, float* ws, long long ws_floats,
+                    void* stream);
 /* dgrad on the tensor cores (stride 1, or stride 2 with 4x4/pad 1); same contract as mtd_conv_dgrad.
  * passes = 1: wpd tf32-rounded (mtd_round_tf32); passes = 3: wpd = [hi | lo] halves of the full dgrad pack
  * (mtd_split_tf32); for stride 1 wpd may point at a row slice of the hi half of [cin_total][T][Cout].  */
 int mtd_conv_dgrad_tc(const float* dz, const float* wpd, float* dx, const float* scale, const float* add1, const float* add2,
                       const float* mask_src, int mask_act, float slope, int B, int H, int W, int Cin, int Cout, int kh, int kw,
-                      int stride, int pad, int passes, int cin_total, void* stream);
+                      int stride, int pad, int passes, int cin_total, float* ws, long long ws_floats, void* stream);
 /* weight gradient on the tensor cores (stride-1 same convs, C % 32 == 0, N % 32 == 0): both operands are
  * MN-major TMA boxes, split-K over pixels, fp32 atomics into gp (zeroed here).  Same gp layout as
  * mtd_conv_wgrad.                                                                                    */

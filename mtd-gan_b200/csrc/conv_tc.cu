@@ -63,6 +63,13 @@ struct TcArgs {
   int mask_act;
   float slope;
   float* aux;
+  // v1 kernel work decomposition (see "stream-K" below): tiles [0, n_dp) are processed whole, round-robin over the
+  // CTAs; the k-steps of tiles [n_dp, n_dp + sk_tiles) form one flat range cut into equal pieces of sk_per steps,
+  // piece c going to CTA c, partial sums to ws[slot][128][BN] with slot = sk_tile * sk_P + (c - first CTA of the tile)
+  int n_dp, sk_tiles, sk_per, sk_P;
+  float* ws;
+  long long ws_floats;          // host side only: capacity of ws
+  int grid;                     // host side only: CTAs to launch
 };
 
 // ---------------------------------------------------------------------------------------------------
@@ -170,6 +177,39 @@ __device__ __forceinline__ void tc_store4(const TcArgs& a, size_t idx, int n, fl
   *reinterpret_cast<float4*>(a.out + idx) = make_float4(o[0], o[1], o[2], o[3]);
 }
 
+// ---- work decomposition of the v1 kernel: data-parallel waves + one stream-K wave ---------------------------
+// A layer with mn output tiles of K k-steps each runs floor(mn / #SM) full waves tile-per-CTA; the remaining
+// (mn mod #SM) tiles -- or ALL tiles of a layer with fewer tiles than SMs -- are cut along K into #CTA equal pieces,
+// so every SM gets the same number of k-steps (a 160-tile layer on 148 SMs takes 1.08 instead of 2 tile-times, a
+// 12-tile layer gets 12-way split-K).  Pieces write raw fp32 partial tiles to the workspace with plain stores;
+// tc_sk_finish_kernel adds the pieces of a tile IN ORDER (deterministic, no atomics, no memset) and runs the epilogue.
+struct Work { int tile, kb, ke, slot; };
+struct WorkIter {
+  int dp_tile, pos, end;
+  __device__ __forceinline__ WorkIter(const TcArgs& a, int K) {
+    dp_tile = blockIdx.x;
+    pos = (int)blockIdx.x * a.sk_per;
+    end = min(pos + a.sk_per, a.sk_tiles * K);
+  }
+  __device__ __forceinline__ bool next(const TcArgs& a, int K, Work& w) {
+    if (dp_tile < a.n_dp) {
+      w.tile = dp_tile; w.kb = 0; w.ke = K; w.slot = -1;
+      dp_tile += gridDim.x;
+      return true;
+    }
+    if (pos < end) {
+      const int st = pos / K;
+      w.tile = a.n_dp + st;
+      w.kb = pos - st * K;
+      w.ke = min(K, w.kb + end - pos);
+      w.slot = st * a.sk_P + ((int)blockIdx.x - (st * K) / a.sk_per);
+      pos += w.ke - w.kb;
+      return true;
+    }
+    return false;
+  }
+};
+
 struct PipeState {
   int stage = 0;
   uint32_t phase = 0;
@@ -235,11 +275,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
   // barriers initialised, TMEM allocated, descriptors prefetched: all of it overlapped the previous kernel's tail
   mtd_pdl_prologue();
 
-  auto decode_tile = [&](int tile, int& b0, int& h0, int& w0, int& n0, int& k_begin, int& k_end) {
-    const int ks = tile % a.ksplit;
-    tile /= a.ksplit;
-    k_begin = ks * a.kper;
-    k_end = min(kiters, k_begin + a.kper);
+  auto decode_tile = [&](int tile, int& b0, int& h0, int& w0, int& n0) {
     int nt = tile % a.n_nt, m = tile / a.n_nt;
     int mw = m % a.n_wt;
     m /= a.n_wt;
@@ -251,10 +287,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
     // ===== TMA producer =====
     if (lane == 0) {
       PipeState st;
-      for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
-        int b0, h0, w0, n0, k_begin, k_end;
-        decode_tile(tile, b0, h0, w0, n0, k_begin, k_end);
-        for (int it = k_begin; it < k_end; ++it) {
+      WorkIter wi(a, kiters);
+      Work wk;
+      while (wi.next(a, kiters, wk)) {
+        int b0, h0, w0, n0;
+        decode_tile(wk.tile, b0, h0, w0, n0);
+        for (int it = wk.kb; it < wk.ke; ++it) {
           mbar_wait(empty_bar(st.stage), st.phase ^ 1u);
           mbar_expect_tx(full_bar(st.stage), kTxBytes);
           const int t = it / kchunks, cc = it - t * kchunks;
@@ -272,12 +310,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
     if (lane == 0) {
       PipeState st;
       constexpr uint32_t idesc = make_idesc(BN);
-      int lt = 0;
-      for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++lt) {
+      WorkIter wi(a, kiters);
+      Work wk;
+      for (int lt = 0; wi.next(a, kiters, wk); ++lt) {
         const int acc = lt & 1;
         const uint32_t acc_phase = (uint32_t)(lt >> 1) & 1u;
-        int b0, h0, w0, n0, k_begin, k_end;
-        decode_tile(tile, b0, h0, w0, n0, k_begin, k_end);
+        const int k_begin = wk.kb, k_end = wk.ke;
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
@@ -307,10 +345,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
     // ===== operand rounding (fp32 -> tf32, round to nearest) =====
     const int ct = threadIdx.x - 64;               // 0..127
     PipeState st;
-    for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
-      int b0, h0, w0, n0, k_begin, k_end;
-      decode_tile(tile, b0, h0, w0, n0, k_begin, k_end);
-      for (int it = k_begin; it < k_end; ++it) {
+    WorkIter wi(a, kiters);
+    Work wk;
+    while (wi.next(a, kiters, wk)) {
+      for (int it = wk.kb; it < wk.ke; ++it) {
         mbar_wait(full_bar(st.stage), st.phase);
         uint4* tileA = reinterpret_cast<uint4*>(gen_base + (size_t)st.stage * kStageBytes);
         // Integer arithmetic instead of cvt.rna.tf32.f32 (quarter-rate: it was the k-step bound for BN <= 64):
@@ -346,10 +384,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
     const int bl = r / (a.TH * a.TW), rem = r - bl * (a.TH * a.TW);
     const int hl = rem / a.TW, wl = rem - hl * a.TW;
     const float scale = a.scale ? __ldg(a.scale) : 1.f;
-    int lt = 0;
-    for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++lt) {
-      int b0, h0, w0, n0, k_begin, k_end;
-      decode_tile(tile, b0, h0, w0, n0, k_begin, k_end);
+    WorkIter wi(a, kiters);
+    Work wk;
+    for (int lt = 0; wi.next(a, kiters, wk); ++lt) {
+      int b0, h0, w0, n0;
+      decode_tile(wk.tile, b0, h0, w0, n0);
       const int acc = lt & 1;
       const uint32_t acc_phase = (uint32_t)(lt >> 1) & 1u;
       mbar_wait(tfull_bar(acc), acc_phase);
@@ -362,10 +401,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
       for (int c0 = 0; c0 < BN; c0 += 32) {
         uint32_t v[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0), v);
-        if (valid && a.ksplit > 1) {
-          // split-K: raw partial sums into the pre-zeroed output; tc_finish_kernel runs the epilogue
+        if (wk.slot >= 0) {
+          // stream-K piece: raw partial sums to the workspace tile (plain stores; rows past the batch are zeros)
+          float* wrow = a.ws + ((size_t)wk.slot * kBM + r) * BN + c0;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) atomicAdd(a.out + rowoff + c0 + j, __uint_as_float(v[j]));
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<float4*>(wrow + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                                                               __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
         } else if (valid) {
 #pragma unroll
           for (int j = 0; j < 32; j += 4)
@@ -712,6 +754,41 @@ __global__ void tc_finish_kernel(const __grid_constant__ TcArgs a, size_t total)
   }
 }
 
+// second phase of a stream-K launch (v1 kernel): out tile = epilogue( sum over the tile's pieces, in piece order ).
+// One thread per 4 output channels of one tile row; consecutive threads walk a row, so workspace reads and output
+// writes are coalesced.
+__global__ void __launch_bounds__(256) tc_sk_finish_kernel(const __grid_constant__ TcArgs a, int BN, int K) {
+  mtd_pdl_prologue();
+  const int c4n = BN >> 2;
+  const long long total = (long long)a.sk_tiles * kBM * c4n;
+  const float scale = a.scale ? __ldg(a.scale) : 1.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % c4n) * 4;
+    const int r = (int)((i / c4n) % kBM);
+    const int st = (int)(i / ((long long)c4n * kBM));
+    const int first = (st * K) / a.sk_per, last = ((st + 1) * K - 1) / a.sk_per;
+    int tile = a.n_dp + st;
+    const int nt = tile % a.n_nt;
+    int m = tile / a.n_nt;
+    const int mw = m % a.n_wt;
+    m /= a.n_wt;
+    const int mh = m % a.n_ht, mb = m / a.n_ht;
+    const int bl = r / (a.TH * a.TW), rem = r - bl * (a.TH * a.TW);
+    const int hl = rem / a.TW, wl = rem - hl * a.TW;
+    const int b = mb * a.TB + bl;
+    if (b >= a.B) continue;
+    const float* wsp = a.ws + ((size_t)st * a.sk_P * kBM + r) * BN + c;
+    float4 sum = __ldcg(reinterpret_cast<const float4*>(wsp));
+    for (int p = 1; p <= last - first; ++p) {
+      const float4 t = __ldcg(reinterpret_cast<const float4*>(wsp + (size_t)p * kBM * BN));
+      sum.x += t.x; sum.y += t.y; sum.z += t.z; sum.w += t.w;
+    }
+    const size_t rowoff = (((size_t)b * a.outH + ((mh * a.TH + hl) * a.omy + a.ooy)) * a.outW +
+                           ((mw * a.TW + wl) * a.omx + a.oox)) * a.N + nt * BN;
+    tc_store4(a, rowoff + c, nt * BN + c, scale, sum.x, sum.y, sum.z, sum.w);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------
 // host side: tensor maps
 // ---------------------------------------------------------------------------------------------------
@@ -823,10 +900,8 @@ template <int BN, int NPASS>
 int launch_bn(const CUtensorMap& mA1, const CUtensorMap& mA2, const CUtensorMap& mB, const CUtensorMap& mBlo, TcArgs& a,
               cudaStream_t st) {
   const int stage_bytes = (NPASS == 3 ? 2 : 1) * (kABytes + BN * 128);
-  const int kiters = a.kper;
   int stages = (200 * 1024) / stage_bytes;
   if (stages > 6) stages = 6;
-  if (stages > kiters) stages = kiters < 2 ? 2 : kiters;
   a.stages = stages;
   size_t smem = 1024 + (size_t)stages * stage_bytes + 8 * (3 * stages + 4) + 16;
   static bool attr_set = false;
@@ -834,44 +909,61 @@ int launch_bn(const CUtensorMap& mA1, const CUtensorMap& mA2, const CUtensorMap&
     MTD_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, NPASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
-  int grid = a.n_tiles < mtd_sm_count() ? a.n_tiles : mtd_sm_count();
-  mtd_launch(conv_tc_kernel<BN, NPASS>, grid, kThreads, smem, st, mA1, mA2, mB, mBlo, a);
+  mtd_launch(conv_tc_kernel<BN, NPASS>, a.grid, kThreads, smem, st, mA1, mA2, mB, mBlo, a);
   MTD_CHECK_LAUNCH();
   return MTD_OK;
 }
 
-// Tile / split selection by a cost model fitted (least squares, 9 % rms) to the sweep of tools/tune_tc.py over the
-// layer shapes of the B = 20 train step (profiles/r01_tune_tc_v1.txt); times in microseconds:
-//   T = F0 + rounds * (Ft + kper * ts[BN]) + [ksplit > 1] * ca * ksplit * (padded M x N / 65536)
+// Tile width / work decomposition of the v1 kernel by a cost model (microseconds) fitted to the sweeps of
+// tools/tune_tc.py over the layer shapes of the B = 20 train step (profiles/r01_tune_tc_*.txt):
+//   T = F0 + waves * (Ft + K * ts[BN]) + [stream-K wave] * (Ft + per * ts[BN] + finish)
 // F0 = launch + pipeline fill + drain, Ft = per-tile epilogue not hidden by the next tile, ts = one 32-channel k-step
-// (L2 -> SM ingest of the A tile and the hi|lo weight tile, ~32 B/clk/SM), ca = the fp32 atomics of the split-K
-// partial sums.  The model picks within 1.2 % of the best measured (BN, ksplit) summed over the sweep.
-int g_tune_bn = 0, g_tune_ksplit = 0;      // tools/tune_tc.py overrides (0 = cost model)
+// (L2 -> SM ingest of the A tile and the hi|lo weight tile, ~32 B/clk/SM), finish = the reduction launch reading the
+// pieces of every stream-K tile from L2.  See "work decomposition" above WorkIter.
+int g_tune_bn = 0, g_tune_per = 0;      // tools/tune_tc.py overrides: Cout tile; stream-K piece length (-1: none)
 
-void choose_tiling(int m_tiles, int N, int kiters, int passes, int force_split, int* BN_out, int* ksplit_out) {
+struct Schedule { int bn, n_dp, sk_tiles, sk_per, sk_P, grid; double cost; };
+
+Schedule choose_schedule(int m_tiles, int N, int K, int passes, long long ws_floats) {
   const int sms = mtd_sm_count();
-  double best = 1e30;
-  int BN = 32, ksplit = 1;
-  if (g_tune_ksplit > 0 && force_split == 0) force_split = g_tune_ksplit;
+  Schedule best{};
+  best.cost = 1e30;
   for (int bn = 128; bn >= 32; bn >>= 1) {
     if (N % bn) continue;
     if (g_tune_bn > 0 && bn != g_tune_bn && N % g_tune_bn == 0) continue;
     const double ts = (bn == 128 ? 0.78 : bn == 64 ? 0.57 : 0.52) * (passes == 3 ? 1.0 : 0.7);
+    const double F0 = 6.0, Ft = 2.2;
     const int mn = m_tiles * (N / bn);
-    const int ks_max = force_split > 0 ? force_split : (kiters >= 4 ? (kiters / 2 < 48 ? kiters / 2 : 48) : 1);
-    for (int ks0 = force_split > 0 ? force_split : 1; ks0 <= ks_max; ++ks0) {
-      const int kper = (kiters + ks0 - 1) / ks0;
-      const int ks = (kiters + kper - 1) / kper;                                  // no empty splits
-      const int rounds = (mn * ks + sms - 1) / sms;
-      double cost = 6.0 + rounds * (2.2 + kper * ts);
-      if (ks > 1) cost += 0.33 * ks * (double)m_tiles * kBM * N / 65536.0;
-      if (cost < best) { best = cost; BN = bn; ksplit = ks; }
+    // (a) whole tiles only
+    if (g_tune_per <= 0) {
+      const int waves = (mn + sms - 1) / sms;
+      const double cost = F0 + waves * (Ft + K * ts);
+      if (cost < best.cost) best = Schedule{bn, mn, 0, 0, 0, mn < sms ? mn : sms, cost};
+    }
+    // (b) full waves whole + the remainder as one stream-K wave
+    const int n_dp = (mn / sms) * sms, rem = mn - n_dp;
+    if (rem == 0 || ws_floats <= 0 || g_tune_per < 0) continue;
+    const long long total = (long long)rem * K;
+    const int per_min = (int)((total + sms - 1) / sms);
+    for (int f = 0; f < 8; ++f) {
+      static const double mult[8] = {1.0, 1.25, 1.5, 2.0, 3.0, 4.0, 6.0, 8.0};
+      int per = g_tune_per > 0 ? g_tune_per : (int)(per_min * mult[f] + 0.5);
+      if (per < per_min) per = per_min;
+      if (per < 2 && K >= 2) per = 2;
+      if (per >= K && n_dp == 0 && g_tune_per <= 0) break;     // no split left: covered by (a)
+      const int grid_sk = (int)((total + per - 1) / per);
+      const int P = (K - 1) / per + 2;
+      if ((long long)rem * P * kBM * bn > ws_floats) continue;
+      const double pieces = (double)K / per + 1.0;                       // average pieces per stream-K tile
+      const double fin = 3.0 + (double)rem * kBM * bn * 4.0 * (pieces + 1.0) / 2.5e6;     // L2-resident traffic at ~2.5 TB/s
+      const double per_cta_pieces = (double)per / K + 1.0;
+      const double cost = F0 + (n_dp / sms) * (Ft + K * ts) + per_cta_pieces * Ft + per * ts + fin;
+      if (cost < best.cost) best = Schedule{bn, n_dp, rem, per, P, n_dp ? sms : grid_sk, cost};
+      if (g_tune_per > 0) break;
     }
   }
-  *BN_out = BN;
-  *ksplit_out = ksplit;
+  return best;
 }
-
 
 // ---- v2 host side -------------------------------------------------------------------------------------
 int g_tc_version = 1;      // 1 (default): A through shared memory (conv_tc_kernel); 2: A through TMEM, MT pixel tiles per CTA
@@ -884,11 +976,9 @@ void choose_tiling_v2(int m_tiles, int N, int kiters, int passes, int force_spli
   const int sms = mtd_sm_count();
   double best = 1e30;
   int bc = -1, bks = 1;
-  if (g_tune_ksplit > 0 && force_split == 0) force_split = g_tune_ksplit;
   for (int ci = 0; ci < 3; ++ci) {
     const int bn = kV2Cfgs[ci].bn, mt = kV2Cfgs[ci].mt;
     if (N % bn) continue;
-    if (g_tune_bn > 0 && bn != g_tune_bn && N % g_tune_bn == 0) continue;
     const int groups = (m_tiles + mt - 1) / mt;
     const double mtv = (double)m_tiles / groups;                      // average pixel tiles per group
     const int mn = groups * (N / bn);
@@ -933,39 +1023,18 @@ int launch_v2(const CUtensorMap& mA1, const CUtensorMap& mA2, const CUtensorMap&
   return MTD_OK;
 }
 
-// wp: packed weights [N][T][C]; for passes == 3 the buffer holds [hi | lo] (2 x N*T*C floats, mtd_split_tf32).
-// `finish`: run the split-K finishing pass here (false when the caller batches several launches into one
-// output, e.g. the four parity classes of a stride-2 dgrad).  Returns the chosen ksplit through a.ksplit.
-int launch_tc(const float* x1, const float* x2, const float* wp, int passes, TcArgs& a, cudaStream_t st, int force_split = 0,
-              bool finish = true) {
-  if (passes != 1 && passes != 3) return MTD_EINVAL;
-  if (!tc_geometry(a.B, a.H, a.W, a.C1, a.C2, a.N, 1, 1, 1, 0, &a.TW, &a.TH, &a.TB)) return MTD_EINVAL;
-  if (!mtd_aligned16(x1) || !mtd_aligned16(wp) || !mtd_aligned16(a.out) || (x2 && !mtd_aligned16(x2)) ||
-      (a.bias && !mtd_aligned16(a.bias)))
-    return MTD_EALIGN;
-  a.n_wt = a.W / a.TW; a.n_ht = a.H / a.TH; a.n_bt = (a.B + a.TB - 1) / a.TB;
+// v1 kernel: whole-tile waves + one stream-K wave (choose_schedule), partial sums through a.ws, no atomics.
+int launch_tc_v1(const float* x1, const float* x2, const float* wp, int passes, TcArgs& a, cudaStream_t st) {
   const int m_tiles = a.n_wt * a.n_ht * a.n_bt;
-  a.kc1 = a.C1 / 32; a.kc2 = a.C2 / 32;
   const int kiters = a.T * (a.kc1 + a.kc2);
-  const int sms = mtd_sm_count();
-  int BN = 32, ksplit = 1, v2cfg = -1;
-  a.m_tiles = m_tiles;
-  if (g_tc_version == 2) {
-    choose_tiling_v2(m_tiles, a.N, kiters, passes, force_split, &v2cfg, &ksplit);
-    if (v2cfg < 0) return MTD_EINVAL;
-    BN = kV2Cfgs[v2cfg].bn;
-    a.n_groups = (m_tiles + kV2Cfgs[v2cfg].mt - 1) / kV2Cfgs[v2cfg].mt;
-  } else {
-    choose_tiling(m_tiles, a.N, kiters, passes, force_split, &BN, &ksplit);
-  }
+  if (a.ws && !mtd_aligned16(a.ws)) return MTD_EALIGN;
+  const Schedule sc = choose_schedule(m_tiles, a.N, kiters, passes, a.ws ? a.ws_floats : 0);
+  if (sc.cost >= 1e30) return MTD_EINVAL;
+  const int BN = sc.bn;
   a.n_nt = a.N / BN;
-  int mn_tiles = (v2cfg >= 0 ? a.n_groups : m_tiles) * a.n_nt;
-  a.kper = (kiters + ksplit - 1) / ksplit;
-  ksplit = (kiters + a.kper - 1) / a.kper;          // no empty splits
-  a.ksplit = ksplit;
-  a.n_tiles = mn_tiles * ksplit;
-  const size_t total = (size_t)a.B * a.outH * a.outW * a.N;
-  if (ksplit > 1 && finish) MTD_CUDA(cudaMemsetAsync(a.out, 0, total * sizeof(float), st));
+  a.n_tiles = m_tiles * a.n_nt;
+  a.n_dp = sc.n_dp; a.sk_tiles = sc.sk_tiles; a.sk_per = sc.sk_per; a.sk_P = sc.sk_P; a.grid = sc.grid;
+  a.ksplit = 1; a.kper = kiters;
   CUtensorMap mA1, mA2, mB;
   if (a.es < 1) { a.es = 1; a.inH = a.H; a.inW = a.W; }
   int rc = make_act_map(&mA1, x1, a.C1, a.inW, a.inH, a.B, a.TW, a.TH, a.TB, false, a.es);
@@ -983,15 +1052,70 @@ int launch_tc(const float* x1, const float* x2, const float* wp, int passes, TcA
   }
 #define TC_DISPATCH(BN_)                                                           \
   rc = passes == 3 ? launch_bn<BN_, 3>(mA1, mA2, mB, mBlo, a, st) : launch_bn<BN_, 1>(mA1, mA2, mB, mBlo, a, st)
+  if (BN == 128) { TC_DISPATCH(128); }
+  else if (BN == 64) { TC_DISPATCH(64); }
+  else { TC_DISPATCH(32); }
+#undef TC_DISPATCH
+  if (rc) return rc;
+  if (a.sk_tiles > 0) {
+    const long long work = (long long)a.sk_tiles * kBM * (BN / 4);
+    int blocks = (int)((work + 255) / 256);
+    if (blocks > mtd_sm_count() * 8) blocks = mtd_sm_count() * 8;
+    mtd_launch(tc_sk_finish_kernel, blocks, 256, 0, st, a, BN, kiters);
+    MTD_CHECK_LAUNCH();
+  }
+  return MTD_OK;
+}
+
+// wp: packed weights, tile-major (mtd_conv_pack_*_blocked); for passes == 3 the buffer holds [hi | lo].
+// v2 kernel only: `finish` = run the split-K finishing pass here (false when the caller batches several launches into
+// one output, e.g. the four parity classes of a stride-2 dgrad); the chosen ksplit is returned through a.ksplit.
+int launch_tc(const float* x1, const float* x2, const float* wp, int passes, TcArgs& a, cudaStream_t st, int force_split = 0,
+              bool finish = true) {
+  if (passes != 1 && passes != 3) return MTD_EINVAL;
+  if (!tc_geometry(a.B, a.H, a.W, a.C1, a.C2, a.N, 1, 1, 1, 0, &a.TW, &a.TH, &a.TB)) return MTD_EINVAL;
+  if (!mtd_aligned16(x1) || !mtd_aligned16(wp) || !mtd_aligned16(a.out) || (x2 && !mtd_aligned16(x2)) ||
+      (a.bias && !mtd_aligned16(a.bias)))
+    return MTD_EALIGN;
+  a.n_wt = a.W / a.TW; a.n_ht = a.H / a.TH; a.n_bt = (a.B + a.TB - 1) / a.TB;
+  const int m_tiles = a.n_wt * a.n_ht * a.n_bt;
+  a.kc1 = a.C1 / 32; a.kc2 = a.C2 / 32;
+  a.m_tiles = m_tiles;
+  if (g_tc_version != 2) return launch_tc_v1(x1, x2, wp, passes, a, st);
+  const int kiters = a.T * (a.kc1 + a.kc2);
+  const int sms = mtd_sm_count();
+  int BN = 32, ksplit = 1, v2cfg = -1;
+  choose_tiling_v2(m_tiles, a.N, kiters, passes, force_split, &v2cfg, &ksplit);
+  if (v2cfg < 0) return MTD_EINVAL;
+  BN = kV2Cfgs[v2cfg].bn;
+  a.n_groups = (m_tiles + kV2Cfgs[v2cfg].mt - 1) / kV2Cfgs[v2cfg].mt;
+  a.n_nt = a.N / BN;
+  int mn_tiles = a.n_groups * a.n_nt;
+  a.kper = (kiters + ksplit - 1) / ksplit;
+  ksplit = (kiters + a.kper - 1) / a.kper;          // no empty splits
+  a.ksplit = ksplit;
+  a.n_tiles = mn_tiles * ksplit;
+  const size_t total = (size_t)a.B * a.outH * a.outW * a.N;
+  if (ksplit > 1 && finish) MTD_CUDA(cudaMemsetAsync(a.out, 0, total * sizeof(float), st));
+  CUtensorMap mA1, mA2, mB;
+  if (a.es < 1) { a.es = 1; a.inH = a.H; a.inW = a.W; }
+  int rc = make_act_map(&mA1, x1, a.C1, a.inW, a.inH, a.B, a.TW, a.TH, a.TB, false, a.es);
+  if (rc) return rc;
+  if (a.C2) { rc = make_act_map(&mA2, x2, a.C2, a.inW, a.inH, a.B, a.TW, a.TH, a.TB, false, a.es); if (rc) return rc; }
+  else mA2 = mA1;
+  const long long K = (long long)a.T * (a.C1 + a.C2);
+  rc = make_w_map(&mB, wp, K, a.N, BN);
+  if (rc) return rc;
+  CUtensorMap mBlo = mB;
+  if (passes == 3) {
+    rc = make_w_map(&mBlo, wp + (size_t)a.wrows_total * K, K, a.N, BN);
+    if (rc) return rc;
+  }
 #define TC2_DISPATCH(BN_, MT_)                                                     \
   rc = passes == 3 ? launch_v2<BN_, MT_, 3>(mA1, mA2, mB, mBlo, a, st) : launch_v2<BN_, MT_, 1>(mA1, mA2, mB, mBlo, a, st)
   if (v2cfg == 0) { TC2_DISPATCH(128, 3); }
   else if (v2cfg == 1) { TC2_DISPATCH(64, 6); }
-  else if (v2cfg == 2) { TC2_DISPATCH(32, 8); }
-  else if (BN == 128) { TC_DISPATCH(128); }
-  else if (BN == 64) { TC_DISPATCH(64); }
-  else { TC_DISPATCH(32); }
-#undef TC_DISPATCH
+  else { TC2_DISPATCH(32, 8); }
 #undef TC2_DISPATCH
   if (rc) return rc;
   if (ksplit > 1 && finish) {
@@ -1324,11 +1448,11 @@ int mtd_tc_set_version(int version) {
   return prev;
 }
 
-// Tuning hook (tools/tune_tc.py): force the Cout tile width and/or the split-K factor of the forward/dgrad tensor-core
-// kernels; 0 = let the cost model decide.
-int mtd_tc_set_tuning(int bn, int ksplit) {
-  if ((bn != 0 && bn != 32 && bn != 64 && bn != 128) || ksplit < 0) return MTD_EINVAL;
-  g_tune_bn = bn; g_tune_ksplit = ksplit;
+// Tuning hook (tools/tune_tc.py): force the Cout tile width and/or the stream-K piece length (k-steps per CTA; -1 =
+// whole tiles only) of the forward/dgrad tensor-core kernel; 0 = let the cost model decide.
+int mtd_tc_set_tuning(int bn, int sk_per) {
+  if (bn != 0 && bn != 32 && bn != 64 && bn != 128) return MTD_EINVAL;
+  g_tune_bn = bn; g_tune_per = sk_per;
   return MTD_OK;
 }
 
@@ -1360,7 +1484,8 @@ int mtd_split_tf32(float* hi, float* lo, long long n, void* stream) {
 
 int mtd_conv_fwd_tc(const float* x1, const float* x2, const float* wp, const float* bias, const float* scale, float* y,
                     float* aux, const float* add1, const float* add2, int B, int H, int W, int C1, int C2, int N, int kh,
-                    int kw, int stride, int pad, int pre_act, int post_act, float slope, int passes, void* stream) {
+                    int kw, int stride, int pad, int pre_act, int post_act, float slope, int passes, float* ws, long long ws_floats,
+                    void* stream) {
   MTD_REQUIRE(x1 && wp && y && ((C2 == 0) == (x2 == nullptr)));
   int tw, th, tb;
   if (!tc_geometry(B, H, W, C1, C2, N, kh, kw, stride, pad, &tw, &th, &tb)) return MTD_EINVAL;
@@ -1374,6 +1499,7 @@ int mtd_conv_fwd_tc(const float* x1, const float* x2, const float* wp, const flo
   a.mask_src = nullptr; a.mask_act = 0; a.slope = slope; a.aux = aux;
   a.wrows_total = N;
   a.outH = Ho; a.outW = Wo; a.omy = a.omx = 1; a.ooy = a.oox = 0;
+  a.ws = ws; a.ws_floats = ws ? ws_floats : 0;
   return launch_tc(x1, x2, wp, passes, a, (cudaStream_t)stream);
 }
 
@@ -1383,11 +1509,12 @@ int mtd_conv_fwd_tc(const float* x1, const float* x2, const float* wp, const flo
 // (2i+py, 2j+px).  (H, W) are the conv INPUT dims = dx dims.
 int mtd_conv_dgrad_tc(const float* dz, const float* wpd, float* dx, const float* scale, const float* add1, const float* add2,
                       const float* mask_src, int mask_act, float slope, int B, int H, int W, int Cin, int Cout, int kh, int kw,
-                      int stride, int pad, int passes, int cin_total, void* stream) {
+                      int stride, int pad, int passes, int cin_total, float* ws, long long ws_floats, void* stream) {
   MTD_REQUIRE(dz && wpd && dx);
   cudaStream_t st = (cudaStream_t)stream;
   int tw, th, tb;
   TcArgs a{};
+  a.ws = ws; a.ws_floats = ws ? ws_floats : 0;
   a.B = B; a.C1 = Cout; a.C2 = 0; a.N = Cin;
   a.out = dx; a.scale = scale; a.bias = nullptr; a.pre_act = 0; a.add1 = add1; a.add2 = add2; a.post_act = 0;
   a.mask_src = mask_src; a.mask_act = mask_act; a.slope = slope; a.aux = nullptr;
@@ -1419,13 +1546,18 @@ int mtd_conv_dgrad_tc(const float* dz, const float* wpd, float* dx, const float*
       c.ooy = py; c.oox = px;
       // packed layout [4 classes][Cin][4][Cout]; for passes == 3 the lo half starts after all four classes
       c.wrows_total = 4 * Cin;                            // rows from this class's base to the lo copy of the same class
+      if (g_tc_version != 2) {
+        // v1 kernel: every class launch reduces its own stream-K pieces (the classes own disjoint output pixels)
+        int rc = launch_tc(dz, nullptr, wpd + (size_t)(py * 2 + px) * cls_elems, passes, c, st);
+        if (rc) return rc;
+        continue;
+      }
       if (py == 0 && px == 0) {
         // decide the split once so all classes agree; zero dx up front when partial sums will be accumulated
         TcArgs probe = c;
         probe.n_wt = probe.W / tw; probe.n_ht = probe.H / th; probe.n_bt = (B + tb - 1) / tb;
         int m_tiles = probe.n_wt * probe.n_ht * probe.n_bt, kiters = 4 * (Cout / 32), bn_unused = 32;
-        if (g_tc_version == 2) choose_tiling_v2(m_tiles, Cin, kiters, passes, 0, &bn_unused, &ksplit);
-        else choose_tiling(m_tiles, Cin, kiters, passes, 0, &bn_unused, &ksplit);
+        choose_tiling_v2(m_tiles, Cin, kiters, passes, 0, &bn_unused, &ksplit);
         if (ksplit > 1) MTD_CUDA(cudaMemsetAsync(dx, 0, total * sizeof(float), st));
       }
       int rc = launch_tc(dz, nullptr, wpd + (size_t)(py * 2 + px) * cls_elems, passes, c, st, ksplit, false);

@@ -212,6 +212,22 @@ def _tc_ok(B, H, W, C1, C2, N, kh, kw, stride, pad) -> bool:
     return _USE_TC != "simt" and _ext.load().mtd_conv_fwd_tc_supported(B, H, W, C1, C2, N, kh, kw, stride, pad) == 1
 
 
+# Scratch for the stream-K wave of the tensor-core kernels (include/mtdgan_b200.h): one per (device, stream),
+# contents undefined between calls.  32 MB cover every layer of the model at any batch size (the stream-K wave holds
+# fewer tiles than there are SMs).
+_TC_WS_FLOATS = 8 << 20
+_tc_ws_cache: dict = {}
+
+
+def _tc_workspace(device) -> torch.Tensor:
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    ws = _tc_ws_cache.get(key)
+    if ws is None:
+        ws = torch.empty(_TC_WS_FLOATS, dtype=torch.float32, device=device)
+        _tc_ws_cache[key] = ws
+    return ws
+
+
 def _conv_forward_launch(x1, x2, weight, bias, scale, y, aux, add1, add2, cfg: ConvCfg):
     B, H, W, C1 = x1.shape
     C2 = 0 if x2 is None else x2.shape[3]
@@ -225,7 +241,8 @@ def _conv_forward_launch(x1, x2, weight, bias, scale, y, aux, add1, add2, cfg: C
     if tc:
         global tc_launches
         tc_launches += 1
-        call("mtd_conv_fwd_tc", *args, _TC_PASSES, stream())
+        ws = _tc_workspace(y.device)
+        call("mtd_conv_fwd_tc", *args, _TC_PASSES, fptr(ws), ws.numel(), stream())
     else:
         call("mtd_conv_fwd", *args, stream())
 
@@ -259,8 +276,10 @@ def _conv_dgrad_launch(dz, weight, dx, scale, add1, B, H, W, cin_sub, cin_off, c
         global tc_launches
         tc_launches += 1
         wpd = _packed(weight, _tc_kind("dgrad"), cfg)
+        ws = _tc_workspace(dx.device)
         call("mtd_conv_dgrad_tc", fptr(dz), wpd.data_ptr() + 4 * cin_off * T * cfg.cout, fptr(dx), fptr(scale), fptr(add1), None,
-             None, 0, cfg.slope, B, H, W, cin_sub, cfg.cout, cfg.kh, cfg.kw, cfg.stride, cfg.pad, _TC_PASSES, cfg.cin, st)
+             None, 0, cfg.slope, B, H, W, cin_sub, cfg.cout, cfg.kh, cfg.kw, cfg.stride, cfg.pad, _TC_PASSES, cfg.cin,
+             fptr(ws), ws.numel(), st)
     else:
         wpd = _packed(weight, "dgrad", cfg)
         call("mtd_conv_dgrad", fptr(dz), wpd.data_ptr() + 4 * cin_off * T * cfg.cout, fptr(dx), fptr(scale), fptr(add1), None,

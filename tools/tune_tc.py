@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Tile / split-K sweep of the tcgen05 conv kernels over the layer shapes of one MTD-GAN train step (B = 20).
 
-Every (kernel version, Cout tile, split-K) candidate is forced through `mtd_tc_set_tuning`, captured as a CUDA graph
+Every (kernel version, Cout tile, stream-K piece length) candidate is forced through `mtd_tc_set_tuning`, captured as a CUDA graph
 of `reps` launches (so host launch cost is out of the picture) that cycle through enough weight copies to defeat
 the L2 (in the real step the discriminator's 250 MB of weights never stay resident), and timed with CUDA events.
 Prints, per shape, the measured time of every candidate, the best one, and what the built-in cost model picks —
@@ -61,12 +61,13 @@ def main():
         x2 = torch.randn(B, H, H, C2, device=dev) if C2 else None
         bias = torch.zeros(N, device=dev)
         y = torch.empty(B, H, H, N, device=dev)
+        ws = torch.empty(8 << 20, device=dev)
         reps = ncopy * (2 if ncopy >= 8 else 8)
         flop = 2.0 * B * H * H * N * C * k * k
 
         def launch(i, st):
             call("mtd_conv_fwd_tc", fptr(x1), fptr(x2), fptr(wps[i % ncopy]), fptr(bias), None, fptr(y), None, None, None,
-                 B, H, H, C1, C2, N, k, k, 1, k // 2, ops.ACT_LEAKY, 0, 0.2, args.passes, st)
+                 B, H, H, C1, C2, N, k, k, 1, k // 2, ops.ACT_LEAKY, 0, 0.2, args.passes, fptr(ws), ws.numel(), st)
 
         def measure():
             s = torch.cuda.Stream()
@@ -94,33 +95,39 @@ def main():
         for ver in versions:
             ops.set_tc_version(ver)
             call("mtd_tc_set_tuning", 0, 0)
-            results[(ver, 0, 0)] = measure()
+            results[(ver, -1, 0)] = measure()
             for bn in (128, 64, 32):
                 if N % bn:
                     continue
-                for ks in (1, 2, 3, 4, 6, 8, 12, 16, 24, 36):
-                    if ks > max(1, kiters // 2):
+                mn = ((m + 127) // 128) * (N // bn)
+                rem = mn % 148
+                call("mtd_tc_set_tuning", bn, -1)             # whole tiles only
+                results[(ver, bn, 0)] = measure()
+                if rem == 0 or ver != 1:
+                    continue
+                per_min = -(-rem * kiters // 148)
+                seen = set()
+                for mult in (1.0, 1.25, 1.5, 2.0, 3.0, 4.0, 6.0, 8.0):
+                    per = max(2, int(per_min * mult + 0.5))
+                    if per in seen or (per >= kiters and mn < 148):
                         continue
-                    # skip splits that would only add rounds (tiles already over a wave)
-                    tiles = (m // 128) * (N // bn)
-                    if ks > 1 and tiles * ks > 148 * 2:
-                        continue
-                    call("mtd_tc_set_tuning", bn, ks)
-                    results[(ver, bn, ks)] = measure()
+                    seen.add(per)
+                    call("mtd_tc_set_tuning", bn, per)        # stream-K wave with `per` k-steps per CTA
+                    results[(ver, bn, per)] = measure()
         call("mtd_tc_set_tuning", 0, 0)
-        best = min((v, kk) for kk, v in results.items() if kk[1])
+        best = min((v, kk) for kk, v in results.items() if kk[1] > 0)
         line = f"shape H={H} C={C1}+{C2} N={N} k={k} (M={m}, kiters={kiters}, {ncopy} weight copies)  {flop / 1e9:.2f} GFLOP"
         print(line)
         for ver in versions:
-            auto = results[(ver, 0, 0)]
-            vbest = min((v, kk) for kk, v in results.items() if kk[0] == ver and kk[1])
-            print(f"  v{ver}: auto {auto:7.1f} us ({flop / auto / 1e6:6.1f} TF/s)   best {vbest[0]:7.1f} us @ bn={vbest[1][1]} ks={vbest[1][2]}"
+            auto = results[(ver, -1, 0)]
+            vbest = min((v, kk) for kk, v in results.items() if kk[0] == ver and kk[1] > 0)
+            print(f"  v{ver}: auto {auto:7.1f} us ({flop / auto / 1e6:6.1f} TF/s)   best {vbest[0]:7.1f} us @ bn={vbest[1][1]} per={vbest[1][2]}"
                   f"   auto/best = {auto / vbest[0]:.2f}")
             for bn in (128, 64, 32):
                 row = [(kk[2], v) for kk, v in sorted(results.items()) if kk[0] == ver and kk[1] == bn]
                 if row:
-                    print(f"      bn={bn:3d}: " + "  ".join(f"ks{ks}={v:.1f}" for ks, v in row))
-        print(f"  overall best: {best[0]:.1f} us  v{best[1][0]} bn={best[1][1]} ks={best[1][2]}", flush=True)
+                    print(f"      bn={bn:3d}: " + "  ".join((f"per{ks}={v:.1f}" if ks else f"whole={v:.1f}") for ks, v in row))
+        print(f"  overall best: {best[0]:.1f} us  v{best[1][0]} bn={best[1][1]} per={best[1][2]}", flush=True)
     ops.set_tc_version(1)
 
 
