@@ -213,6 +213,10 @@ def run_own(args):
     breakdown, roof = None, None
     torch.cuda.synchronize()
     if rank == 0:
+        # The eager step is enqueued from Python at ~10 us per call -- slower than the GPU executes it, so an event pair
+        # around a call would also time the host gap in front of it.  A 0.3 s device-side spin gives the host a head
+        # start: the whole step is queued behind it and then runs back to back, and the events time kernels only.
+        torch.cuda._sleep(int(0.3 * 1.9e9))
         _ext.start_profile()
     eager_step(xd, yd)                      # every rank runs it (the step contains collectives at N > 1)
     rec = _ext.stop_profile() if rank == 0 else None
@@ -237,10 +241,37 @@ def run_own(args):
         conv_ms = sum(by[n]["ms"] for n in GROUPS["conv"] if n in by)
         conv_flop = sum(by[n]["flop"] for n in GROUPS["conv"] if n in by)
         conv_calls = sum(by[n]["calls"] for n in GROUPS["conv"] if n in by)
+        timing = "CUDA events around every call of one eager step (includes host launch gaps)"
+        if use_graph and getattr(runner, "trace", None):
+            # Kernel-only times: re-issue each stateless kernel family of the CAPTURED step (same calls, same buffers,
+            # same order) as its own CUDA graph and time its replay with events -- no host gaps, no event overhead.
+            fam_ms = {}
+            for gname in ("conv", "conv_aux", "fft"):
+                fg, ncalls = runner.family_graph(set(GROUPS[gname]))
+                fg.replay()
+                torch.cuda.synchronize()
+                evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(5)]
+                for s_, e_ in evs:
+                    flush.zero_()
+                    s_.record(); fg.replay(); e_.record()
+                torch.cuda.synchronize()
+                fam_ms[gname] = (statistics.mean(s_.elapsed_time(e_) for s_, e_ in evs), ncalls)
+                breakdown[gname] = {"ms": round(fam_ms[gname][0], 3), "calls": ncalls,
+                                    "eager_event_ms": breakdown[gname]["ms"]}
+                del fg
+            conv_ms, conv_calls = fam_ms["conv"]
+            total_ms = t_dev / args.steps
+            breakdown["timing"] = ("conv / conv_aux / fft: replay of that family's calls of the captured step as its own CUDA "
+                                   "graph (kernel-only); other rows: events around the calls of one eager step")
+            timing = "replay of the captured step's conv-family calls as one CUDA graph, CUDA events, mean of 5"
         ach = conv_flop / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
         roof = {"kernel": "implicit-GEMM conv family (fwd + dgrad + wgrad)", "bound": "tensor", "achieved": round(ach, 3),
                 "peak": pk["tflops_sustained"], "unit": "TFLOP/s", "frac": round(ach / pk["tflops_sustained"], 5),
                 "traffic": None, "peak_source": pk["source"] + ", sustained bf16 dense (kernel timed inside a long step)",
+                # fp32-grade results need 3 TF32 MMAs per product and TF32 runs at half the bf16 rate: the same peak
+                # expressed in useful fp32-equivalent FLOP/s is peak / 6
+                "peak_3xtf32_equiv": round(pk["tflops_sustained"] / 6, 1), "frac_of_3xtf32_peak": round(ach / (pk["tflops_sustained"] / 6), 4),
+                "timing": timing,
                 "algorithmic_flop_per_launch": round(conv_flop / max(conv_calls, 1)), "launches_per_step": conv_calls,
                 "avg_launch_ms": round(conv_ms / max(conv_calls, 1), 5), "share_of_step": round(conv_ms / total_ms, 4),
                 "pcgrad": {"bound": "hbm", "achieved": round(7 * N_SHARED * 4 / (by["mtd_pcgrad_project"]["ms"] * 1e-3) / 1e9, 1),

@@ -96,6 +96,23 @@ def kernel_launch_count() -> int:
     return int((_lib if _lib is not None else load()).mtd_kernel_launch_count())
 
 
+_trace = None             # when a list: (entry point, args) per call, no events (legal during CUDA-graph capture)
+
+
+def start_trace():
+    """Record (entry point, args) of every C-ABI call.  Taken while a step is being captured into a CUDA graph, the
+    pointers belong to the graph's private pool and stay valid for the life of the graph, so bench.py can re-issue
+    one kernel family of the step as its own graph and time it in isolation."""
+    global _trace
+    _trace = []
+
+
+def stop_trace():
+    global _trace
+    rec, _trace = _trace, None
+    return rec
+
+
 def start_profile():
     """Bracket every C-ABI call with CUDA events on the launching stream (for bench.py's per-kernel times;
     adds two event records per call, so never enabled inside a timed region)."""
@@ -120,6 +137,8 @@ def call(name: str, *args):
         e.record()
         _profile.append((name, args, s, e))
     else:
+        if _trace is not None:
+            _trace.append((name, args))
         rc = getattr(lib, name)(*args)
     if rc != 0:
         if rc < 0:

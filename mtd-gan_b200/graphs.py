@@ -14,7 +14,7 @@ from __future__ import annotations
 
 import torch
 
-from . import ops
+from . import _ext, ops
 
 
 class GraphedTrainStep:
@@ -62,9 +62,28 @@ class GraphedTrainStep:
         torch.cuda.synchronize()
         ops.clear_pack_cache()            # every weight-packing kernel must be part of the captured step
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
-            self.out = self.eager_step(self.x, self.y)
+        _ext.start_trace()
+        try:
+            with torch.cuda.graph(self.graph):
+                self.out = self.eager_step(self.x, self.y)
+        finally:
+            self.trace = _ext.stop_trace()        # (entry point, args) of every library call in the captured step
         return self
+
+    def family_graph(self, names):
+        """A CUDA graph that re-issues, in order, the captured step's calls to the given entry points on the captured
+        step's own buffers (graph-private pool).  For timing one kernel family in isolation; only for stateless
+        families (convolutions, FFT passes) -- replaying optimizer or power-iteration calls would change the model."""
+        lib = _ext.load()
+        calls = [(n, a) for n, a in self.trace if n in names]
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            st = torch.cuda.current_stream().cuda_stream
+            for n, a in calls:
+                rc = getattr(lib, n)(*a[:-1], st)         # the stream is the last argument of every entry point
+                if rc != 0:
+                    raise _ext.MtdError(f"{n}: status {rc} while building a family graph")
+        return g, len(calls)
 
     def __call__(self, x, y):
         if self.graph is None:

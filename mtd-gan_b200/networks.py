@@ -336,10 +336,37 @@ class MTD_GAN_Method(nn.Module):
         self.pixel_loss = L.CharbonnierLoss()
         self.edge_loss = L.EdgeLoss()
 
+    # The reference evaluates G(x) twice per iteration on the same x and the same generator weights: detached in
+    # d_loss (:1958) and with autograd in g_loss (:1995) -- engine.py:40-55 steps only the discriminator in between.
+    # Both evaluations are the same deterministic kernels on the same inputs, so d_loss keeps its (autograd-enabled)
+    # result and g_loss takes it over when x and every generator parameter are unchanged (object identity + version
+    # counters); anything else falls back to a fresh forward.  Bit-identical to recomputing, one forward cheaper.
+    reuse_generator_forward = True
+
+    def _g_cache_key(self, x):
+        return (id(x), x._version, x.data_ptr(), self.Generator.training,
+                tuple(p._version for p in self.Generator.parameters()))
+
+    def _generate_for_d(self, x):
+        want_graph = (self.reuse_generator_forward and torch.is_grad_enabled()
+                      and any(p.requires_grad for p in self.Generator.parameters()))
+        if not want_graph:
+            self._g_cache = None
+            with torch.no_grad():
+                return self.Generator(x)
+        fake = self.Generator(x)
+        self._g_cache = (self._g_cache_key(x), x, fake)
+        return fake.detach()
+
+    def _generate_for_g(self, x):
+        cache, self._g_cache = getattr(self, "_g_cache", None), None         # an autograd graph backs one backward only
+        if cache is not None and torch.is_grad_enabled() and cache[0] == self._g_cache_key(x) and cache[1] is x:
+            return cache[2]
+        return self.Generator(x)
+
     def d_loss(self, x, y):
         x, y = check_input(x, "d_loss"), check_input(y, "d_loss")
-        with torch.no_grad():                                               # == G(x).detach()  (:1958)
-            fake = self.Generator(x)
+        fake = self._generate_for_d(x)                                      # == G(x).detach()  (:1958)
         D = self.Discriminator
         real_enc, real_dec, real_rec = D(y)                                 # :1959
         fake_enc, fake_dec, fake_rec = D(fake)                              # :1960
@@ -356,7 +383,7 @@ class MTD_GAN_Method(nn.Module):
 
     def g_loss(self, x, y):
         x, y = check_input(x, "g_loss"), check_input(y, "g_loss")
-        fake = self.Generator(x)                                            # :1995
+        fake = self._generate_for_g(x)                                      # :1995
         gen_enc, gen_dec, _ = self.Discriminator(fake, weight_grads=False, need_rec=False)   # :1996
         gt = L.g_terms(gen_enc, gen_dec, fake, x, y, eps=self.pixel_loss.eps)                # :1998-2002
         details = {'G/gen_enc': gt[1], 'G/gen_dec': gt[2], 'G/pix_loss': gt[3], 'G/edge_loss': gt[4]}
