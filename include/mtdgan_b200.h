@@ -80,7 +80,9 @@ int mtd_conv_wgrad_finish(const float* gp, float* dw_ref, int transposed, int Co
  * inv_sigma, Cout, kh*kw, Cin, sN, sC, flip, sn_cols, dot slot, next segment of the same weight or -1, 0 }
  * (Conv2d: sN = Cin*T, sC = T, flip 0; ConvTranspose2d: sN = T, sC = Cout*T, flip 1).  dot_chunks lists every
  * spectral-normed segment, head_chunks only the first segment of each weight.                              */
-int mtd_wgrad_finish_chunk_elems(void);
+/* elements per chunk-table entry of a segment with kh*kw = taps and Cin = cin: a whole number of packed rows when a
+ * row fits the kernels' shared-memory staging (coalesced transposition), else a fixed block                     */
+int mtd_wgrad_finish_chunk_elems(int taps, int cin);
 int mtd_wgrad_finish_batched(const void* seg_tab, int n_segs, const void* dot_chunks, int n_dot_chunks, const void* head_chunks,
                              int n_head_chunks, double* dots, void* stream);
 /* dz = dy * act'(y) (F.relu / nn.LeakyReLU(0.2) backward); dbias[N] = column sums of dz (optional)  */

@@ -129,7 +129,7 @@ class deferred_wgrad_finish:
 def _flush_finish(groups):
     first = next(iter(groups.values()))
     dev = first[0].device
-    rows, dot_numels, head_numels, heads = [], [], [], []
+    rows, dot_numels, head_numels, heads, rowdims = [], [], [], [], []
     for dw, insts in groups.values():
         base = len(rows)
         heads.append(base)
@@ -142,12 +142,13 @@ def _flush_finish(groups):
                          v.data_ptr() if sn else 0, inv.data_ptr() if sn else 0, cfg.cout, T, cfg.cin, sN, sC, flip,
                          cfg.cin * T, base + k, base + k + 1 if k + 1 < len(insts) else -1, 0])
             dot_numels.append(gp.numel() if sn else 0)
-    key = (tuple(dot_numels), tuple(heads), str(dev))
+            rowdims.append((T, cfg.cin))
+    key = (tuple(dot_numels), tuple(heads), tuple(rowdims), str(dev))
     ent = _fin_chunk_cache.get(key)
     if ent is None:
-        ck = _ext.load().mtd_wgrad_finish_chunk_elems()
-        dchunks = [[s_, off] for s_, n in enumerate(dot_numels) for off in range(0, n, ck)]
-        hchunks = [[h, off] for h, n in zip(heads, head_numels) for off in range(0, n, ck)]
+        ck = [_ext.load().mtd_wgrad_finish_chunk_elems(t, c) for t, c in rowdims]     # whole packed rows per chunk
+        dchunks = [[s_, off] for s_, n in enumerate(dot_numels) for off in range(0, n, ck[s_])]
+        hchunks = [[h, off] for h, n in zip(heads, head_numels) for off in range(0, n, ck[h])]
         ent = (_ext.device_table(dchunks, torch.int32, dev) if dchunks else None, len(dchunks),
                _ext.device_table(hchunks, torch.int32, dev), len(hchunks))
         _fin_chunk_cache[key] = ent

@@ -23,6 +23,7 @@ def main():
     ap.add_argument("--passes", type=int, default=3)
     ap.add_argument("--quick", action="store_true")
     ap.add_argument("--only", type=int, default=-1, help="index of a single shape to sweep")
+    ap.add_argument("--auto-only", action="store_true", help="only time the cost model's choice (for profiling)")
     ap.add_argument("--versions", default="1,2", help="kernel generations to sweep")
     args = ap.parse_args()
     from mtdgan_b200 import ops, _ext
@@ -96,6 +97,9 @@ def main():
             ops.set_tc_version(ver)
             call("mtd_tc_set_tuning", 0, 0)
             results[(ver, -1, 0)] = measure()
+            if args.auto_only:
+                print(f"v{ver} auto: {results[(ver, -1, 0)]:.1f} us", flush=True)
+                continue
             for bn in (128, 64, 32):
                 if N % bn:
                     continue
@@ -103,7 +107,7 @@ def main():
                 rem = mn % 148
                 call("mtd_tc_set_tuning", bn, -1)             # whole tiles only
                 results[(ver, bn, 0)] = measure()
-                if rem == 0 or ver != 1:
+                if rem == 0 or ver == 2:
                     continue
                 per_min = -(-rem * kiters // 148)
                 seen = set()
@@ -115,6 +119,8 @@ def main():
                     call("mtd_tc_set_tuning", bn, per)        # stream-K wave with `per` k-steps per CTA
                     results[(ver, bn, per)] = measure()
         call("mtd_tc_set_tuning", 0, 0)
+        if args.auto_only:
+            continue
         best = min((v, kk) for kk, v in results.items() if kk[1] > 0)
         line = f"shape H={H} C={C1}+{C2} N={N} k={k} (M={m}, kiters={kiters}, {ncopy} weight copies)  {flop / 1e9:.2f} GFLOP"
         print(line)
