@@ -30,6 +30,7 @@
 #include <unordered_map>
 #include <string>
 #include <string.h>
+#include <stdlib.h>
 #include "common.cuh"
 #include "mtdgan_b200.h"
 
@@ -735,244 +736,6 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant
   }
 }
 
-// =====================================================================================================
-// v3 forward / dgrad kernel: v1's work decomposition (whole-tile waves + stream-K wave, two accumulators, shared
-// epilogue) with the A operand fed to the tensor core from TENSOR MEMORY.
-//
-// Why: with both operands in shared memory a 128 x BN x 8 tf32 MMA reads (4 KB + BN*32 B) of smem in the 64*BN/128
-// clocks it computes, i.e. the MMA alone saturates the 128 B/clk shared-memory port, and the TMA writes and the
-// operand-conversion warps share that port.  v1's measured k-step times (0.52 / 0.57 / 0.78 us for BN = 32 / 64 / 128)
-// equal its shared-memory bytes per k-step (132 / 152 / 192 KB) at 128 B/clk: v1 is shared-memory-bandwidth bound at
-// ~50 % tensor-pipe utilisation.  Here the conversion warps read the raw fp32 A tile once (16 KB), write a_hi / a_lo
-// with tcgen05.st into a 4-slot ring in TMEM, and tcgen05.mma takes A from TMEM: 52 / 72 / 112 KB per k-step.
-//
-// Warp roles (448 threads): 0 TMA producer | 1 MMA issuer | 2-9 operand conversion, two warps per TMEM lane quadrant
-// taking alternate k-steps | 10-13 epilogue.
-// TMEM columns: [0, 2*BN) two accumulators | 4 x (a_hi 32 | a_lo 32).
-// =====================================================================================================
-constexpr int kThreads3 = 448;
-constexpr int kASlots = 4;
-
-template <int BN, int NPASS>
-__global__ void __launch_bounds__(kThreads3, 1)
-conv_tc3_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUtensorMap mapA2,
-                const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapBlo,
-                const __grid_constant__ TcArgs a) {
-  extern __shared__ __align__(1024) unsigned char smem_raw[];
-  constexpr int kNB = NPASS == 3 ? 2 : 1;
-  constexpr int kBBytes = kNB * BN * 128;                        // B_hi (| B_lo) per k-step
-  constexpr uint32_t kACols = kNB * 32;                          // a_hi (| a_lo) columns per TMEM A slot
-  constexpr uint32_t kAccCols = 2 * BN;
-  constexpr uint32_t kTmemCols = next_pow2_cols(kAccCols + kASlots * kACols);
-  static_assert(kAccCols + kASlots * kACols <= 512, "TMEM budget exceeded");
-
-  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const int RA = a.ra, RB = a.rb;
-  const uint32_t b_base = base + (uint32_t)RA * kABytes;
-  const uint32_t bar_base = b_base + (uint32_t)RB * kBBytes;
-  auto rfull = [&](int s) { return bar_base + 8u * s; };
-  auto rempty = [&](int s) { return bar_base + 8u * (RA + s); };
-  auto bfull = [&](int s) { return bar_base + 8u * (2 * RA + s); };
-  auto bempty = [&](int s) { return bar_base + 8u * (2 * RA + RB + s); };
-  auto afull = [&](int s) { return bar_base + 8u * (2 * RA + 2 * RB + s); };
-  auto aempty = [&](int s) { return bar_base + 8u * (2 * RA + 2 * RB + kASlots + s); };
-  auto tfull_bar = [&](int i) { return bar_base + 8u * (2 * RA + 2 * RB + 2 * kASlots + i); };
-  auto tempty_bar = [&](int i) { return bar_base + 8u * (2 * RA + 2 * RB + 2 * kASlots + 2 + i); };
-  const uint32_t tmem_slot = bar_base + 8u * (2 * RA + 2 * RB + 2 * kASlots + 4);
-  unsigned char* gen_base = smem_raw + (base - smem_u32(smem_raw));
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int kchunks = a.kc1 + a.kc2;
-  const int kiters = a.T * kchunks;
-
-  if (warp == 0 && lane == 0) {
-    prefetch_tmap(&mapA1);
-    if (a.kc2) prefetch_tmap(&mapA2);
-    prefetch_tmap(&mapB);
-    if (NPASS == 3) prefetch_tmap(&mapBlo);
-    for (int s = 0; s < RA; ++s) { mbar_init(rfull(s), 1); mbar_init(rempty(s), 4); }
-    for (int s = 0; s < RB; ++s) { mbar_init(bfull(s), 1); mbar_init(bempty(s), 1); }
-    for (int s = 0; s < kASlots; ++s) { mbar_init(afull(s), 4); mbar_init(aempty(s), 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(tfull_bar(i), 1); mbar_init(tempty_bar(i), 4); }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(kTmemCols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gen_base + (tmem_slot - base));
-  mtd_pdl_prologue();
-  const uint32_t tmem_a0 = tmem_base + kAccCols;
-
-  auto decode_tile = [&](int tile, int& b0, int& h0, int& w0, int& n0) {
-    int nt = tile % a.n_nt, m = tile / a.n_nt;
-    int mw = m % a.n_wt;
-    m /= a.n_wt;
-    int mh = m % a.n_ht, mb = m / a.n_ht;
-    b0 = mb * a.TB; h0 = mh * a.TH; w0 = mw * a.TW; n0 = nt * BN;
-  };
-
-  if (warp == 0) {
-    // ===== TMA producer: raw fp32 A tiles and weight tiles in separate rings =====
-    if (lane == 0) {
-      PipeState sr, sb;
-      WorkIter wi(a, kiters);
-      Work wk;
-      while (wi.next(a, kiters, wk)) {
-        int b0, h0, w0, n0;
-        decode_tile(wk.tile, b0, h0, w0, n0);
-        for (int it = wk.kb; it < wk.ke; ++it) {
-          const int t = it / kchunks, cc = it - t * kchunks;
-          mbar_wait(rempty(sr.stage), sr.phase ^ 1u);
-          mbar_expect_tx(rfull(sr.stage), kABytes);
-          const uint32_t sam = base + (uint32_t)sr.stage * kABytes;
-          if (cc < a.kc1) tma_load_4d(&mapA1, sam, rfull(sr.stage), cc * 32, w0 * a.es + a.dx[t], h0 * a.es + a.dy[t], b0);
-          else tma_load_4d(&mapA2, sam, rfull(sr.stage), (cc - a.kc1) * 32, w0 * a.es + a.dx[t], h0 * a.es + a.dy[t], b0);
-          sr.advance(RA);
-          mbar_wait(bempty(sb.stage), sb.phase ^ 1u);
-          mbar_expect_tx(bfull(sb.stage), kBBytes);
-          const uint32_t sbm = b_base + (uint32_t)sb.stage * kBBytes;
-          tma_load_4d(&mapB, sbm, bfull(sb.stage), 0, 0, it, n0 >> 5);
-          if (NPASS == 3) tma_load_4d(&mapBlo, sbm + BN * 128, bfull(sb.stage), 0, 0, it, n0 >> 5);
-          sb.advance(RB);
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // ===== MMA issuer: A from TMEM, B from shared memory =====
-    if (lane == 0) {
-      PipeState sb, sa;
-      constexpr uint32_t idesc = make_idesc(BN);
-      WorkIter wi(a, kiters);
-      Work wk;
-      for (int lt = 0; wi.next(a, kiters, wk); ++lt) {
-        const int acc = lt & 1;
-        mbar_wait(tempty_bar(acc), ((uint32_t)(lt >> 1) & 1u) ^ 1u);
-        tc_fence_after();
-        const uint32_t d = tmem_base + (uint32_t)(acc * BN);
-        for (int it = wk.kb; it < wk.ke; ++it) {
-          mbar_wait(bfull(sb.stage), sb.phase);
-          mbar_wait(afull(sa.stage), sa.phase);
-          tc_fence_after();
-          const uint32_t sbm = b_base + (uint32_t)sb.stage * kBBytes;
-          const uint64_t db = make_sw128_desc(sbm), dbl = make_sw128_desc(sbm + BN * 128);
-          const uint32_t a_hi = tmem_a0 + (uint32_t)sa.stage * kACols, a_lo = a_hi + 32;
-#pragma unroll
-          for (int kk = 0; kk < 4; ++kk) {
-            const uint32_t accum = (it > wk.kb || kk > 0) ? 1u : 0u;
-            if (NPASS == 3) {                   // small cross terms first, then the main product
-              umma_tf32_ts(d, a_lo + 8u * kk, db + 2u * kk, idesc, accum);
-              umma_tf32_ts(d, a_hi + 8u * kk, dbl + 2u * kk, idesc, 1u);
-              umma_tf32_ts(d, a_hi + 8u * kk, db + 2u * kk, idesc, 1u);
-            } else {
-              umma_tf32_ts(d, a_hi + 8u * kk, db + 2u * kk, idesc, accum);
-            }
-          }
-          umma_commit(aempty(sa.stage));
-          umma_commit(bempty(sb.stage));
-          sa.advance(kASlots);
-          sb.advance(RB);
-        }
-        umma_commit(tfull_bar(acc));
-      }
-    }
-  } else if (warp < 10) {
-    // ===== operand conversion: own row of the raw A tile -> tf32 hi / lo -> TMEM (alternate k-steps per warp pair) =====
-    const int q = warp & 3;                        // TMEM lane quadrant this warp may access
-    const int half = (warp - 2) >> 2;              // warps 2-5 take even steps, 6-9 odd steps
-    const int row = q * 32 + lane;
-    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-    const unsigned char* row0 = gen_base + (size_t)row * 128;
-    const int sw = row & 7;
-    long long n = 0;                               // k-steps issued so far (all work items)
-    WorkIter wi(a, kiters);
-    Work wk;
-    while (wi.next(a, kiters, wk)) {
-      for (int it = wk.kb; it < wk.ke; ++it, ++n) {
-        if ((int)(n & 1) != half) continue;
-        const int rs = (int)(n % RA), as = (int)(n % kASlots);
-        const uint32_t rphase = (uint32_t)((n / RA) & 1), aphase = (uint32_t)((n / kASlots) & 1);
-        mbar_wait(rfull(rs), rphase);
-        const unsigned char* rowp = row0 + (size_t)rs * kABytes;
-        uint32_t hi[32], lo[32];
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {               // logical 16-byte chunk c lives at physical chunk c ^ (row & 7)
-          const uint4 v = *reinterpret_cast<const uint4*>(rowp + ((c ^ sw) << 4));
-          const uint32_t f[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const uint32_t h = (f[e] + 0x1000u) & 0xffffe000u;          // == cvt.rna.tf32.f32 at full integer rate
-            hi[c * 4 + e] = h;
-            if (NPASS == 3)
-              lo[c * 4 + e] = (__float_as_uint(__uint_as_float(f[e]) - __uint_as_float(h)) + 0x1000u) & 0xffffe000u;
-          }
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(rempty(rs));       // raw slot may be refilled by TMA (one arrival per quadrant)
-        mbar_wait(aempty(as), aphase ^ 1u);           // the MMAs that read this TMEM slot have completed
-        tc_fence_after();
-        const uint32_t ta = tmem_a0 + lane_addr + (uint32_t)as * kACols;
-        tmem_st32(ta, hi);
-        if (NPASS == 3) tmem_st32(ta + 32, lo);
-        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(afull(as));
-      }
-    }
-  } else {
-    // ===== epilogue (as v1) =====
-    const int q = warp & 3;
-    const int r = q * 32 + lane;
-    const int bl = r / (a.TH * a.TW), rem = r - bl * (a.TH * a.TW);
-    const int hl = rem / a.TW, wl = rem - hl * a.TW;
-    const float scale = a.scale ? __ldg(a.scale) : 1.f;
-    WorkIter wi(a, kiters);
-    Work wk;
-    for (int lt = 0; wi.next(a, kiters, wk); ++lt) {
-      int b0, h0, w0, n0;
-      decode_tile(wk.tile, b0, h0, w0, n0);
-      const int acc = lt & 1;
-      mbar_wait(tfull_bar(acc), (uint32_t)(lt >> 1) & 1u);
-      tc_fence_after();
-      const int b = b0 + bl;
-      const bool valid = b < a.B;
-      const size_t rowoff =
-          (((size_t)b * a.outH + ((h0 + hl) * a.omy + a.ooy)) * a.outW + ((w0 + wl) * a.omx + a.oox)) * a.N + n0;
-#pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0), v);
-        if (wk.slot >= 0) {
-          float* wrow = a.ws + ((size_t)wk.slot * kBM + r) * BN + c0;
-#pragma unroll
-          for (int j = 0; j < 32; j += 4)
-            *reinterpret_cast<float4*>(wrow + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
-                                                               __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
-        } else if (valid) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4)
-            tc_store4(a, rowoff + c0 + j, n0 + c0 + j, scale, __uint_as_float(v[j]), __uint_as_float(v[j + 1]),
-                      __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
-        }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(acc));
-    }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
-  }
-}
-
 // second phase of a split-K launch: `out` holds raw sums over a dense (B,outH,outW,N) tensor
 __global__ void tc_finish_kernel(const __grid_constant__ TcArgs a, size_t total) {
   mtd_pdl_prologue();
@@ -1152,24 +915,6 @@ int launch_bn(const CUtensorMap& mA1, const CUtensorMap& mA2, const CUtensorMap&
   return MTD_OK;
 }
 
-template <int BN, int NPASS>
-int launch_v3(const CUtensorMap& mA1, const CUtensorMap& mA2, const CUtensorMap& mB, const CUtensorMap& mBlo, TcArgs& a,
-              cudaStream_t st) {
-  const int b_bytes = (NPASS == 3 ? 2 : 1) * BN * 128;
-  a.ra = BN == 128 ? 4 : 6;
-  int rb = (200 * 1024 - a.ra * kABytes) / b_bytes;
-  a.rb = rb > 6 ? 6 : rb;
-  size_t smem = 1024 + (size_t)a.ra * kABytes + (size_t)a.rb * b_bytes + 8 * (2 * a.ra + 2 * a.rb + 2 * kASlots + 6);
-  static bool attr_set = false;
-  if (!attr_set) {
-    MTD_CUDA(cudaFuncSetAttribute(conv_tc3_kernel<BN, NPASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
-  }
-  mtd_launch(conv_tc3_kernel<BN, NPASS>, a.grid, kThreads3, smem, st, mA1, mA2, mB, mBlo, a);
-  MTD_CHECK_LAUNCH();
-  return MTD_OK;
-}
-
 // Tile width / work decomposition of the v1 kernel by a cost model (microseconds) fitted to the sweeps of
 // tools/tune_tc.py over the layer shapes of the B = 20 train step (profiles/r01_tune_tc_*.txt):
 //   T = F0 + waves * (Ft + K * ts[BN]) + [stream-K wave] * (Ft + per * ts[BN] + finish)
@@ -1177,7 +922,6 @@ int launch_v3(const CUtensorMap& mA1, const CUtensorMap& mA2, const CUtensorMap&
 // (L2 -> SM ingest of the A tile and the hi|lo weight tile, ~32 B/clk/SM), finish = the reduction launch reading the
 // pieces of every stream-K tile from L2.  See "work decomposition" above WorkIter.
 int g_tune_bn = 0, g_tune_per = 0;      // tools/tune_tc.py overrides: Cout tile; stream-K piece length (-1: none)
-extern int g_tc_version;
 
 struct Schedule { int bn, n_dp, sk_tiles, sk_per, sk_P, grid; double cost; };
 
@@ -1188,8 +932,7 @@ Schedule choose_schedule(int m_tiles, int N, int K, int passes, long long ws_flo
   for (int bn = 128; bn >= 32; bn >>= 1) {
     if (N % bn) continue;
     if (g_tune_bn > 0 && bn != g_tune_bn && N % g_tune_bn == 0) continue;
-    const double ts = (g_tc_version == 3 ? (bn == 128 ? 0.48 : bn == 64 ? 0.34 : 0.30)
-                                         : (bn == 128 ? 0.78 : bn == 64 ? 0.57 : 0.52)) * (passes == 3 ? 1.0 : 0.7);
+    const double ts = (bn == 128 ? 0.78 : bn == 64 ? 0.57 : 0.52) * (passes == 3 ? 1.0 : 0.7);
     const double F0 = 6.0, Ft = 2.2;
     const int mn = m_tiles * (N / bn);
     // (a) whole tiles only
@@ -1224,7 +967,7 @@ Schedule choose_schedule(int m_tiles, int N, int K, int passes, long long ws_flo
 }
 
 // ---- v2 host side -------------------------------------------------------------------------------------
-int g_tc_version = 1;      // 3: v1 scheduling with A through TMEM (conv_tc3_kernel); 1 (default): A through shared memory (conv_tc_kernel); 2: A through TMEM, MT pixel tiles per CTA
+int g_tc_version = 1;      // 1 (default): A through shared memory (conv_tc_kernel); 2: A through TMEM, MT pixel tiles per CTA
                            // (slower on every measured layer shape -- kept selectable for experiments)
 
 struct V2Cfg { int bn, mt; };
@@ -1308,10 +1051,8 @@ int launch_tc_v1(const float* x1, const float* x2, const float* wp, int passes, 
     rc = make_w_map(&mBlo, wp + (size_t)a.wrows_total * K, K, a.N, BN);
     if (rc) return rc;
   }
-#define TC_DISPATCH(BN_)                                                                                        \
-  rc = g_tc_version == 3                                                                                        \
-           ? (passes == 3 ? launch_v3<BN_, 3>(mA1, mA2, mB, mBlo, a, st) : launch_v3<BN_, 1>(mA1, mA2, mB, mBlo, a, st)) \
-           : (passes == 3 ? launch_bn<BN_, 3>(mA1, mA2, mB, mBlo, a, st) : launch_bn<BN_, 1>(mA1, mA2, mB, mBlo, a, st))
+#define TC_DISPATCH(BN_)                                                           \
+  rc = passes == 3 ? launch_bn<BN_, 3>(mA1, mA2, mB, mBlo, a, st) : launch_bn<BN_, 1>(mA1, mA2, mB, mBlo, a, st)
   if (BN == 128) { TC_DISPATCH(128); }
   else if (BN == 64) { TC_DISPATCH(64); }
   else { TC_DISPATCH(32); }
@@ -1704,7 +1445,7 @@ extern "C" {
 // (conv_tc2_kernel).  Process-wide; returns the previous value.
 int mtd_tc_set_version(int version) {
   int prev = g_tc_version;
-  if (version >= 1 && version <= 3) g_tc_version = version;
+  if (version == 1 || version == 2) g_tc_version = version;
   return prev;
 }
 
@@ -1863,11 +1604,25 @@ int mtd_conv_wgrad_tc(const float* x1, const float* x2, const float* dz, float* 
   if (N % BN) return MTD_EINVAL;
   a.n_nt = N / BN;
   const int mn = a.m_tiles * a.n_nt;
+  // split over pixels by a cost model (us): a k-step streams 4 units x 64 px x 32 ch of x plus 64 px x BN of dz from L2
+  // (~32 B/clk/SM); every split adds one fp32 atomic per output element (0.33 us per 64 K, measured on the
+  // forward kernel) -- layers with few pixels and large weights (the deep discriminator layers) must NOT be split.
   int ksplit = 1;
-  if (mn < 2 * sms) {
-    ksplit = (2 * sms + mn - 1) / mn;
-    if (ksplit > a.ptiles / 4) ksplit = a.ptiles / 4;
-    if (ksplit < 1) ksplit = 1;
+  {
+    static const int forced = getenv("MTD_WG_KSPLIT") ? atoi(getenv("MTD_WG_KSPLIT")) : 0;     // tuning override
+    const double ts = (128.0 + BN) * kp * 4.0 * (passes == 3 ? 2 : 1) / 61000.0;     // (x rows + dz rows) x pixels x 4 B
+    const double outputs = (double)a.m_tiles * 128.0 * N;
+    double best = 1e30;
+    const int ks_max = a.ptiles / 2 > 1 ? a.ptiles / 2 : 1;
+    for (int ks0 = 1; ks0 <= ks_max && ks0 <= 512; ++ks0) {
+      const int kper = (a.ptiles + ks0 - 1) / ks0;
+      const int ks = (a.ptiles + kper - 1) / kper;
+      const int waves = (mn * ks + sms - 1) / sms;
+      double cost = 6.0 + waves * (2.5 + kper * ts);
+      if (ks > 1) cost += 3.0 + 0.33 * ks * outputs / 65536.0;
+      if (cost < best) { best = cost; ksplit = ks; }
+    }
+    if (forced > 0) ksplit = forced < ks_max ? forced : ks_max;
   }
   a.kper = (a.ptiles + ksplit - 1) / ksplit;
   ksplit = (a.ptiles + a.kper - 1) / a.kper;

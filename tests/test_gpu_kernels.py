@@ -112,11 +112,10 @@ TC_CASES = [
 ]
 
 
-@pytest.fixture(params=[1, 2, 3], ids=["v1_smemA", "v2_tmemA", "v3_tmemA_streamK"])
+@pytest.fixture(params=[1, 2], ids=["v1_smemA", "v2_tmemA"])
 def tc_version(request):
-    """All generations of the forward/dgrad tensor-core kernel: v1 keeps the rounded A tile in shared memory, v2
-    writes it to TMEM (tcgen05.st) and shares every weight stage among several pixel tiles, v3 = v1's work
-    decomposition (whole-tile waves + stream-K wave) with A through TMEM."""
+    """Both generations of the forward/dgrad tensor-core kernel: v1 keeps the rounded A tile in shared memory (whole-tile
+    waves + stream-K wave), v2 writes it to TMEM (tcgen05.st) and shares every weight stage among several pixel tiles."""
     from mtdgan_b200 import ops
     prev = ops.set_tc_version(request.param)
     yield request.param
