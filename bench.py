@@ -259,6 +259,22 @@ def run_own(args):
                 breakdown[gname] = {"ms": round(fam_ms[gname][0], 3), "calls": ncalls,
                                     "eager_event_ms": breakdown[gname]["ms"]}
                 del fg
+            if os.environ.get("MTD_BENCH_PER_ENTRY"):      # kernel-only time of every stateless entry point (analysis aid)
+                per = {}
+                safe = set(GROUPS["conv"]) | set(GROUPS["conv_aux"]) | set(GROUPS["fft"]) | {
+                    "mtd_upsample2x_fwd", "mtd_upsample2x_bwd", "mtd_pixel_shuffle2", "mtd_clip01_fwd", "mtd_clip01_bwd",
+                    "mtd_mul", "mtd_add3", "mtd_layout_transpose"}
+                for nm in sorted({n for n, _ in runner.trace} & safe):
+                    fg, ncalls = runner.family_graph({nm})
+                    fg.replay(); torch.cuda.synchronize()
+                    s_, e_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    s_.record()
+                    for _ in range(3):
+                        fg.replay()
+                    e_.record(); torch.cuda.synchronize()
+                    per[nm] = {"ms": round(s_.elapsed_time(e_) / 3, 3), "calls": ncalls}
+                    del fg
+                breakdown["per_entry"] = per
             conv_ms, conv_calls = fam_ms["conv"]
             total_ms = t_dev / args.steps
             breakdown["timing"] = ("conv / conv_aux / fft: replay of that family's calls of the captured step as its own CUDA "

@@ -86,7 +86,7 @@ int mtd_wgrad_finish_chunk_elems(int taps, int cin);
 int mtd_wgrad_finish_batched(const void* seg_tab, int n_segs, const void* dot_chunks, int n_dot_chunks, const void* head_chunks,
                              int n_head_chunks, double* dots, void* stream);
 /* dz = dy * act'(y) (F.relu / nn.LeakyReLU(0.2) backward); dbias[N] = column sums of dz (optional)  */
-int mtd_act_bwd(const float* dy, const float* y, float* dz, float* dbias, long long M, int N, int act, float slope,
+int mtd_act_bwd(const float* dy, const float* y, float* dz, float* dbias, int dbias_zeroed, long long M, int N, int act, float slope,
                 void* stream);
 
 /* tcgen05 / TMEM TF32 implicit-GEMM forward for C % 32 == 0 layers (conv_tc.cu).  Same contract as

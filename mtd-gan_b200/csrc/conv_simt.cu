@@ -943,6 +943,51 @@ __global__ void act_bwd_kernel(const float* __restrict__ dy, const float* __rest
   }
 }
 
+// float4 version (N % 4 == 0, 16-byte aligned pointers): 4 channels per thread; dy and y are read for the last
+// time here (streaming loads), dz is re-read at once by dgrad / wgrad and stays in L2.
+__global__ void __launch_bounds__(256) act_bwd_v4_kernel(const float4* __restrict__ dy, const float4* __restrict__ y,
+                                                         float4* __restrict__ dz, float* __restrict__ dbias, size_t total4,
+                                                         int N4, int act, float slope) {
+  mtd_pdl_prologue();
+  extern __shared__ float colsum[];   // 4 * N4 floats when dbias != null
+  if (dbias) {
+    for (int i = threadIdx.x; i < 4 * N4; i += blockDim.x) colsum[i] = 0.f;
+    __syncthreads();
+  }
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  const bool fixed = dbias && (stride % (size_t)N4 == 0);   // channel group of this thread never changes
+  float4 priv = make_float4(0.f, 0.f, 0.f, 0.f);
+  const size_t first = i;
+  for (; i < total4; i += stride) {
+    float4 g = __ldcs(dy + i);
+    if (act != MTD_ACT_NONE) {
+      const float4 t = __ldcs(y + i);
+      g.x *= mtd_act_grad(t.x, act, slope); g.y *= mtd_act_grad(t.y, act, slope);
+      g.z *= mtd_act_grad(t.z, act, slope); g.w *= mtd_act_grad(t.w, act, slope);
+    }
+    if (dz) dz[i] = g;
+    if (dbias) {
+      if (fixed) { priv.x += g.x; priv.y += g.y; priv.z += g.z; priv.w += g.w; }
+      else {
+        float* cs = colsum + 4 * (i % N4);
+        atomicAdd(cs, g.x); atomicAdd(cs + 1, g.y); atomicAdd(cs + 2, g.z); atomicAdd(cs + 3, g.w);
+      }
+    }
+  }
+  if (dbias) {
+    if (fixed && first < total4) {
+      float* cs = colsum + 4 * (first % N4);
+      atomicAdd(cs, priv.x); atomicAdd(cs + 1, priv.y); atomicAdd(cs + 2, priv.z); atomicAdd(cs + 3, priv.w);
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < 4 * N4; c += blockDim.x) {
+      float v = colsum[c];
+      if (v != 0.f) atomicAdd(dbias + c, v);
+    }
+  }
+}
+
 void tap_table_fwd(int* dy, int* dx, int kh, int kw, int pad) {
   for (int ky = 0; ky < kh; ++ky)
     for (int kx = 0; kx < kw; ++kx) {
@@ -1161,16 +1206,38 @@ int mtd_conv_wgrad_finish(const float* gp, float* dw_ref, int transposed, int Co
 }
 
 // dz = dy * act'(y); dbias[N] (optional) = column sums of dz.  dz may be null (colsum only) and may
-// alias dy.
-int mtd_act_bwd(const float* dy, const float* y, float* dz, float* dbias, long long M, int N, int act, float slope,
-                void* stream) {
+// alias dy.  dbias_zeroed != 0: the caller guarantees dbias is already all zero (e.g. carved from one zeroed slab
+// per backward pass), which saves a memset node per layer.
+int mtd_act_bwd(const float* dy, const float* y, float* dz, float* dbias, int dbias_zeroed, long long M, int N, int act,
+                float slope, void* stream) {
   MTD_REQUIRE(dy && M > 0 && N > 0 && (act == MTD_ACT_NONE || y));
   cudaStream_t st = (cudaStream_t)stream;
   size_t total = (size_t)M * N;
+  if (N % 4 == 0 && mtd_aligned16(dy) && (!y || mtd_aligned16(y)) && (!dz || mtd_aligned16(dz))) {
+    const size_t total4 = total / 4;
+    const int N4 = N / 4;
+    int blocks = (int)std::min<size_t>((total4 + 255) / 256, (size_t)mtd_sm_count() * 4);
+    if (dbias) {
+      MTD_REQUIRE(N <= 8192);
+      if (!dbias_zeroed) MTD_CUDA(cudaMemsetAsync(dbias, 0, (size_t)N * sizeof(float), st));
+      // grid stride a multiple of the channel groups when possible (N is a power of two for every layer here)
+      size_t stride = (size_t)blocks * 256;
+      if (stride % N4 != 0 && (size_t)N4 <= stride) {
+        size_t s2 = stride / N4 * N4;
+        if (s2 % 256 == 0 && s2 > 0) blocks = (int)(s2 / 256);
+      } else if ((size_t)N4 > stride) {
+        blocks = (N4 + 255) / 256;
+      }
+    }
+    mtd_launch(act_bwd_v4_kernel, blocks, 256, dbias ? N * sizeof(float) : 0, st, reinterpret_cast<const float4*>(dy),
+               reinterpret_cast<const float4*>(y), reinterpret_cast<float4*>(dz), dbias, total4, N4, act, slope);
+    MTD_CHECK_LAUNCH();
+    return MTD_OK;
+  }
   int blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)mtd_sm_count() * 8);
   if (dbias) {
     MTD_REQUIRE(N <= 8192);
-    MTD_CUDA(cudaMemsetAsync(dbias, 0, (size_t)N * sizeof(float), st));
+    if (!dbias_zeroed) MTD_CUDA(cudaMemsetAsync(dbias, 0, (size_t)N * sizeof(float), st));
     // make the grid stride a multiple of N when possible (N is a power of two for every layer here)
     size_t stride = (size_t)blocks * 256;
     if (stride % N != 0 && (size_t)N <= stride) {

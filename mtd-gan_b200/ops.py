@@ -114,16 +114,39 @@ _fin_chunk_cache: dict = {}
 
 class deferred_wgrad_finish:
     def __enter__(self):
-        global _finish_queue
+        global _finish_queue, _bias_slab
         self.prev, _finish_queue = _finish_queue, {}
+        self.prev_slab, _bias_slab = _bias_slab, None
         return self
 
     def __exit__(self, *exc):
-        global _finish_queue
+        global _finish_queue, _bias_slab
+        _bias_slab = self.prev_slab
         q, _finish_queue = _finish_queue, self.prev
         if q and exc[0] is None:
             _flush_finish(q)
         return False
+
+
+# Bias gradients are column sums accumulated with atomics, i.e. they need zeroed memory.  Inside a deferred-finishing
+# context (one per PCGrad autograd.grad call, ~250 layers) they are carved from ONE zeroed slab instead of one memset
+# node per layer.
+_BIAS_SLAB_FLOATS = 1 << 18
+_bias_slab = None             # [tensor, next free offset] of the active context
+
+
+def _dbias_alloc(n: int, like):
+    """-> (dbias tensor, 1 if it is known to be all zero else 0)"""
+    global _bias_slab
+    if _finish_queue is not None:
+        if _bias_slab is None:
+            _bias_slab = [torch.zeros(_BIAS_SLAB_FLOATS, dtype=torch.float32, device=like.device), 0]
+        t, off = _bias_slab
+        step = (n + 63) // 64 * 64                      # keep every slice 256-byte aligned
+        if off + step <= t.numel():
+            _bias_slab[1] = off + step
+            return t[off:off + n], 1
+    return _empty((n,), like), 0
 
 
 def _flush_finish(groups):
@@ -330,17 +353,17 @@ class ConvFn(Function):
         g1 = dy
         if cfg.post_act != ACT_NONE:
             g1 = _empty(dy.shape, dy)
-            call("mtd_act_bwd", fptr(dy), fptr(y), fptr(g1), None, M, cfg.cout, cfg.post_act, cfg.slope, st)
+            call("mtd_act_bwd", fptr(dy), fptr(y), fptr(g1), None, 0, M, cfg.cout, cfg.post_act, cfg.slope, st)
         d_add = g1 if ctx.has_add else None
-        dbias = _empty((cfg.cout,), dy) if need[3] else None
+        dbias, dbz = _dbias_alloc(cfg.cout, dy) if need[3] else (None, 0)
         if cfg.pre_act != ACT_NONE:
             pre_out = aux if aux is not None else y
             dz = _empty(dy.shape, dy)
-            call("mtd_act_bwd", fptr(g1), fptr(pre_out), fptr(dz), fptr(dbias), M, cfg.cout, cfg.pre_act, cfg.slope, st)
+            call("mtd_act_bwd", fptr(g1), fptr(pre_out), fptr(dz), fptr(dbias), dbz, M, cfg.cout, cfg.pre_act, cfg.slope, st)
         else:
             dz = g1
             if dbias is not None:
-                call("mtd_act_bwd", fptr(g1), None, None, fptr(dbias), M, cfg.cout, ACT_NONE, cfg.slope, st)
+                call("mtd_act_bwd", fptr(g1), None, None, fptr(dbias), dbz, M, cfg.cout, ACT_NONE, cfg.slope, st)
         # 2) data gradients
         dx1 = dx2 = None
         if need[0]:
@@ -434,7 +457,7 @@ class FFTConvBlockFn(Function):
         M = B * H * W
         dz = _empty(x.shape, x)
         dib = _empty((C,), x)
-        call("mtd_act_bwd", fptr(dout), fptr(img), fptr(dz), fptr(dib), M, C, ACT_RELU, LEAK, st)
+        call("mtd_act_bwd", fptr(dout), fptr(img), fptr(dz), fptr(dib), 0, M, C, ACT_RELU, LEAK, st)
         dx = None
         if need[0]:
             dxc = _empty(x.shape, x)      # dgrad(dz) + dout   (residual path fused)
