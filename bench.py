@@ -157,12 +157,18 @@ def run_own(args):
         dl, _, gl, _ = runner.eager_step(x, y)
         return dl, gl
 
-    use_graph = not args.no_graph and world == 1      # NCCL collectives are left out of graph capture for now
+    use_graph = not args.no_graph
     l0 = _ext.kernel_launch_count()
     eager_step(xd, yd)
     launches = _ext.kernel_launch_count() - l0          # kernels of this library per step (replays run the same ones)
     if use_graph:
-        runner.capture(xd, yd, warmup=2)
+        # At N > 1 the step contains NCCL collectives (reduce-scatter / all-reduce / all-gather of the PCGrad path, the
+        # generator-gradient all-reduce); NCCL kernels are capturable, every rank captures and replays the same graph.
+        # MTD_BENCH_NCCL_GRAPH=0 falls back to eager launches at N > 1.
+        if world > 1 and os.environ.get("MTD_BENCH_NCCL_GRAPH", "1") == "0":
+            use_graph = False
+        else:
+            runner.capture(xd, yd, warmup=2)
 
     def step(x, y):
         dl, _, gl, _ = runner(x, y)
