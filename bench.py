@@ -99,14 +99,14 @@ def dist_env():
 def flops_of(name, a):
     """Algorithmic FLOPs (2*MAC) of one conv entry-point call from its argument list."""
     if name in ("mtd_conv_fwd", "mtd_conv_fwd_tc"):
-        B, H, W, C1, C2, N, kh, kw, s, p = a[9:19]
+        B, H, W, C1, C2, N, kh, kw, s, p = a[10:20]
         Ho, Wo = (H + 2 * p - kh) // s + 1, (W + 2 * p - kw) // s + 1
         return 2.0 * B * Ho * Wo * N * (C1 + C2) * kh * kw
     if name in ("mtd_conv_dgrad", "mtd_conv_dgrad_tc"):
-        B, H, W, Cin, Cout, kh, kw, s, p = a[9:18]
+        B, H, W, Cin, Cout, kh, kw, s, p = a[10:19]
         Ho, Wo = (H + 2 * p - kh) // s + 1, (W + 2 * p - kw) // s + 1
         return 2.0 * B * Ho * Wo * Cout * Cin * kh * kw
-    if name == "mtd_conv_wgrad":
+    if name in ("mtd_conv_wgrad", "mtd_conv_wgrad_tc"):
         B, H, W, C1, C2, N, kh, kw, s, p = a[4:14]
         Ho, Wo = (H + 2 * p - kh) // s + 1, (W + 2 * p - kw) // s + 1
         return 2.0 * B * Ho * Wo * N * (C1 + C2) * kh * kw

@@ -59,12 +59,16 @@ int mtd_conv_pack_dgrad_blocked(const float* w_ref, int transposed, int Cout, in
                                 float* out, void* stream);
 /* y = post_act( pre_act( scale * conv(cat[x1,x2]) + bias ) + add1 + add2 );  aux (optional) receives the
  * value after pre_act.  x2/C2 = second source concatenated along channels (torch.cat at
- * networks.py:421-466) or null/0.  scale = device scalar 1/sigma of spectral norm, or null.       */
-int mtd_conv_fwd(const float* x1, const float* x2, const float* wp, const float* bias, const float* scale, float* y,
+ * networks.py:421-466) or null/0.  scale = device scalar 1/sigma of spectral norm, or null.  scale_group > 0 (all four
+ * conv entry points): the batch holds several independent reference calls of scale_group samples each (e.g. D(real)
+ * and D(fake) evaluated as one batch), every group with its own power-iteration result: scale is then an array with
+ * one 1/sigma per group, applied by sample index / scale_group.  0 = one scalar.                              */
+int mtd_conv_fwd(const float* x1, const float* x2, const float* wp, const float* bias, const float* scale, int scale_group,
+                 float* y,
                  float* aux, const float* add1, const float* add2, int B, int H, int W, int C1, int C2, int N, int kh,
                  int kw, int stride, int pad, int pre_act, int post_act, float slope, void* stream);
 /* dx = (scale * dgrad(dz) + add1 + add2) * act'(mask_src);  (H, W) are the conv INPUT dims.        */
-int mtd_conv_dgrad(const float* dz, const float* wpd, float* dx, const float* scale, const float* add1,
+int mtd_conv_dgrad(const float* dz, const float* wpd, float* dx, const float* scale, int scale_group, const float* add1,
                    const float* add2, const float* mask_src, int mask_act, float slope, int B, int H, int W, int Cin,
                    int Cout, int kh, int kw, int stride, int pad, void* stream);
 /* gp[N][kh*kw][C1+C2] = sum over output pixels of dz (x) x   (dL/dW~ in packed forward layout)      */
@@ -107,14 +111,16 @@ int mtd_round_tf32(float* p, long long n, void* stream);
  * stream).  With it, layers whose tile count is not a multiple of the SM count run their remainder as a stream-K wave
  * (k-range pieces -> partial tiles in ws -> ordered reduction + epilogue): balanced SMs, deterministic, no atomics.
  * ws = NULL: whole output tiles only (correct, slower for skinny layers).  32 MB covers every layer of the model. */
-int mtd_conv_fwd_tc(const float* x1, const float* x2, const float* wp, const float* bias, const float* scale, float* y,
+int mtd_conv_fwd_tc(const float* x1, const float* x2, const float* wp, const float* bias, const float* scale, int scale_group,
+                    float* y,
                     float* aux, const float* add1, const float* add2, int B, int H, int W, int C1, int C2, int N, int kh,
                     int kw, int stride, int pad, int pre_act, int post_act, float slope, int passes, float* ws, long long ws_floats,
                     void* stream);
 /* dgrad on the tensor cores (stride 1, or stride 2 with 4x4/pad 1); same contract as mtd_conv_dgrad.
  * passes = 1: wpd tf32-rounded (mtd_round_tf32); passes = 3: wpd = [hi | lo] halves of the full dgrad pack
  * (mtd_split_tf32); for stride 1 wpd may point at a row slice of the hi half of [cin_total][T][Cout].  */
-int mtd_conv_dgrad_tc(const float* dz, const float* wpd, float* dx, const float* scale, const float* add1, const float* add2,
+int mtd_conv_dgrad_tc(const float* dz, const float* wpd, float* dx, const float* scale, int scale_group, const float* add1,
+                      const float* add2,
                       const float* mask_src, int mask_act, float slope, int B, int H, int W, int Cin, int Cout, int kh, int kw,
                       int stride, int pad, int passes, int cin_total, float* ws, long long ws_floats, void* stream);
 /* weight gradient on the tensor cores (stride-1 same convs, C % 32 == 0, N % 32 == 0): both operands are

@@ -29,7 +29,8 @@ struct ConvArgs {
   int outH, outW, omy, omx, ooy, oox;
   // epilogue: v = acc*scale + bias; v = pre_act(v); aux = v; v += add1 + add2; v = post_act(v);
   //           v *= act'(mask_src)
-  const float* scale;   // device scalar (1/sigma) or null
+  const float* scale;   // device scalar (1/sigma) or null; with scale_span > 0 an array indexed by output element / span
+  long long scale_span; // output elements per scale entry (samples per group x outH x outW x N), 0 = one scalar
   const float* bias;
   int pre_act;
   const float* add1;
@@ -45,7 +46,7 @@ struct ConvArgs {
 };
 
 __device__ __forceinline__ float conv_epilogue_one(const ConvArgs& a, float v, size_t idx, int n) {
-  if (a.scale) v *= __ldg(a.scale);
+  if (a.scale) v *= __ldg(a.scale + (a.scale_span > 0 ? (long long)idx / a.scale_span : 0));
   if (a.bias) v += __ldg(a.bias + n);
   v = mtd_act(v, a.pre_act, a.slope);
   if (a.aux) a.aux[idx] = v;
@@ -1071,7 +1072,8 @@ int mtd_conv_pack_dgrad_blocked(const float* w_ref, int transposed, int Cout, in
   return rc;
 }
 
-int mtd_conv_fwd(const float* x1, const float* x2, const float* wp, const float* bias, const float* scale, float* y,
+int mtd_conv_fwd(const float* x1, const float* x2, const float* wp, const float* bias, const float* scale, int scale_group,
+                 float* y,
                  float* aux, const float* add1, const float* add2, int B, int H, int W, int C1, int C2, int N, int kh,
                  int kw, int stride, int pad, int pre_act, int post_act, float slope, void* stream) {
   MTD_REQUIRE(x1 && wp && y && B > 0 && H > 0 && W > 0 && C1 > 0 && C2 >= 0 && N > 0);
@@ -1087,12 +1089,13 @@ int mtd_conv_fwd(const float* x1, const float* x2, const float* wp, const float*
   tap_table_fwd(a.dy, a.dx, kh, kw, pad);
   a.out = y; a.outH = a.Ho; a.outW = a.Wo; a.omy = a.omx = 1; a.ooy = a.oox = 0;
   a.scale = scale; a.bias = bias; a.pre_act = pre_act; a.add1 = add1; a.add2 = add2; a.post_act = post_act;
+  a.scale_span = (scale && scale_group > 0 && scale_group < B) ? (long long)scale_group * a.Ho * a.Wo * N : 0;
   a.mask_src = nullptr; a.mask_act = 0; a.slope = slope; a.aux = aux;
   return launch_conv(a, (cudaStream_t)stream);
 }
 
 // dx (B,H,W,Cin) = scale * dgrad(dz (B,Ho,Wo,Cout)) [+ add1 + add2] [* act'(mask_src)]
-int mtd_conv_dgrad(const float* dz, const float* wpd, float* dx, const float* scale, const float* add1,
+int mtd_conv_dgrad(const float* dz, const float* wpd, float* dx, const float* scale, int scale_group, const float* add1,
                    const float* add2, const float* mask_src, int mask_act, float slope, int B, int H, int W, int Cin,
                    int Cout, int kh, int kw, int stride, int pad, void* stream) {
   MTD_REQUIRE(dz && wpd && dx && B > 0 && Cin > 0 && Cout > 0 && kh * kw <= kMaxTaps);
@@ -1102,6 +1105,7 @@ int mtd_conv_dgrad(const float* dz, const float* wpd, float* dx, const float* sc
   a.N = Cin;
   a.out = dx; a.outH = H; a.outW = W;
   a.scale = scale; a.bias = nullptr; a.pre_act = 0; a.add1 = add1; a.add2 = add2; a.post_act = 0;
+  a.scale_span = (scale && scale_group > 0 && scale_group < B) ? (long long)scale_group * H * W * Cin : 0;
   a.mask_src = mask_src; a.mask_act = mask_act; a.slope = slope; a.aux = nullptr;
   if (stride == 1) {
     a.wp = wpd; a.T = kh * kw; a.Ho = H; a.Wo = W; a.sy = a.sx = 1;

@@ -54,7 +54,8 @@ struct TcArgs {
   int m_tiles, n_groups, ra, rb; // v2 kernel: pixel tiles, groups of MT pixel tiles, raw-A / B ring depths
   int outH, outW, omy, omx, ooy, oox;   // output pixel = (h*omy+ooy, w*omx+oox) in a (B,outH,outW,N) tensor
   float* out;
-  const float* scale;
+  const float* scale;           // 1/sigma: one scalar, or (scale_group > 0) one per group of scale_group samples
+  int scale_group;
   const float* bias;
   int pre_act;
   const float* add1;
@@ -153,6 +154,10 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
 // N>>3 at [17,23), M>>4 at [24,29)
 __host__ __device__ constexpr uint32_t make_idesc(int bn) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
+}
+
+__device__ __forceinline__ float tc_row_scale(const TcArgs& a, int b) {
+  return a.scale ? __ldg(a.scale + (a.scale_group > 0 ? b / a.scale_group : 0)) : 1.f;
 }
 
 // scale / bias / pre-activation / aux copy / residual adds / post-activation / gradient mask of 4 consecutive
@@ -384,7 +389,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
     const int r = q * 32 + lane;                   // accumulator row == pixel within the tile
     const int bl = r / (a.TH * a.TW), rem = r - bl * (a.TH * a.TW);
     const int hl = rem / a.TW, wl = rem - hl * a.TW;
-    const float scale = a.scale ? __ldg(a.scale) : 1.f;
     WorkIter wi(a, kiters);
     Work wk;
     for (int lt = 0; wi.next(a, kiters, wk); ++lt) {
@@ -396,6 +400,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
       tc_fence_after();
       const int b = b0 + bl;
       const bool valid = b < a.B;
+      const float scale = valid ? tc_row_scale(a, b) : 1.f;
       const size_t rowoff =
           (((size_t)b * a.outH + ((h0 + hl) * a.omy + a.ooy)) * a.outW + ((w0 + wl) * a.omx + a.oox)) * a.N + n0;
 #pragma unroll 1
@@ -698,7 +703,6 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant
     const int r = q * 32 + lane;
     const int bl = r / (a.TH * a.TW), rem = r - bl * (a.TH * a.TW);
     const int hl = rem / a.TW, wl = rem - hl * a.TW;
-    const float scale = a.scale ? __ldg(a.scale) : 1.f;
     int lt = 0;
     for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++lt) {
       int g, n0, k_begin, k_end;
@@ -713,6 +717,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant
         decode_mtile(mt, b0, h0, w0);
         const int b = b0 + bl;
         const bool valid = b < a.B;
+        const float scale = valid ? tc_row_scale(a, b) : 1.f;
         const size_t rowoff =
             (((size_t)b * a.outH + ((h0 + hl) * a.omy + a.ooy)) * a.outW + ((w0 + wl) * a.omx + a.oox)) * a.N + n0;
 #pragma unroll 1
@@ -740,10 +745,10 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant
 __global__ void tc_finish_kernel(const __grid_constant__ TcArgs a, size_t total) {
   mtd_pdl_prologue();
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
-  const float scale = a.scale ? __ldg(a.scale) : 1.f;
+  const size_t per_sample = (size_t)a.outH * a.outW * a.N;
   for (; i < total; i += stride) {
     int n = (int)(i % a.N);
-    float x = a.out[i] * scale;
+    float x = a.out[i] * tc_row_scale(a, (int)(i / per_sample));
     if (a.bias) x += __ldg(a.bias + n);
     x = mtd_act(x, a.pre_act, a.slope);
     if (a.aux) a.aux[i] = x;
@@ -762,7 +767,6 @@ __global__ void __launch_bounds__(256) tc_sk_finish_kernel(const __grid_constant
   mtd_pdl_prologue();
   const int c4n = BN >> 2;
   const long long total = (long long)a.sk_tiles * kBM * c4n;
-  const float scale = a.scale ? __ldg(a.scale) : 1.f;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int c = (int)(i % c4n) * 4;
     const int r = (int)((i / c4n) % kBM);
@@ -786,7 +790,7 @@ __global__ void __launch_bounds__(256) tc_sk_finish_kernel(const __grid_constant
     }
     const size_t rowoff = (((size_t)b * a.outH + ((mh * a.TH + hl) * a.omy + a.ooy)) * a.outW +
                            ((mw * a.TW + wl) * a.omx + a.oox)) * a.N + nt * BN;
-    tc_store4(a, rowoff + c, nt * BN + c, scale, sum.x, sum.y, sum.z, sum.w);
+    tc_store4(a, rowoff + c, nt * BN + c, tc_row_scale(a, b), sum.x, sum.y, sum.z, sum.w);
   }
 }
 
@@ -1483,7 +1487,8 @@ int mtd_split_tf32(float* hi, float* lo, long long n, void* stream) {
   return MTD_OK;
 }
 
-int mtd_conv_fwd_tc(const float* x1, const float* x2, const float* wp, const float* bias, const float* scale, float* y,
+int mtd_conv_fwd_tc(const float* x1, const float* x2, const float* wp, const float* bias, const float* scale, int scale_group,
+                    float* y,
                     float* aux, const float* add1, const float* add2, int B, int H, int W, int C1, int C2, int N, int kh,
                     int kw, int stride, int pad, int pre_act, int post_act, float slope, int passes, float* ws, long long ws_floats,
                     void* stream) {
@@ -1496,7 +1501,8 @@ int mtd_conv_fwd_tc(const float* x1, const float* x2, const float* wp, const flo
   a.inH = H; a.inW = W; a.es = stride;
   for (int ky = 0; ky < kh; ++ky)
     for (int kx = 0; kx < kw; ++kx) { a.dy[ky * kw + kx] = ky - pad; a.dx[ky * kw + kx] = kx - pad; }
-  a.out = y; a.scale = scale; a.bias = bias; a.pre_act = pre_act; a.add1 = add1; a.add2 = add2; a.post_act = post_act;
+  a.out = y; a.scale = scale; a.scale_group = (scale && scale_group > 0 && scale_group < B) ? scale_group : 0;
+  a.bias = bias; a.pre_act = pre_act; a.add1 = add1; a.add2 = add2; a.post_act = post_act;
   a.mask_src = nullptr; a.mask_act = 0; a.slope = slope; a.aux = aux;
   a.wrows_total = N;
   a.outH = Ho; a.outW = Wo; a.omy = a.omx = 1; a.ooy = a.oox = 0;
@@ -1508,7 +1514,8 @@ int mtd_conv_fwd_tc(const float* x1, const float* x2, const float* wp, const flo
 // stride 1: dz (B,H,W,Cout), wpd[Cin][kh*kw][Cout].  stride 2 (4x4, pad 1): dz (B,H/2,W/2,Cout),
 // wpd[4][Cin][4][Cout]: four output-parity classes, each a 2x2-tap stride-1 conv over dz scattered to
 // (2i+py, 2j+px).  (H, W) are the conv INPUT dims = dx dims.
-int mtd_conv_dgrad_tc(const float* dz, const float* wpd, float* dx, const float* scale, const float* add1, const float* add2,
+int mtd_conv_dgrad_tc(const float* dz, const float* wpd, float* dx, const float* scale, int scale_group, const float* add1,
+                      const float* add2,
                       const float* mask_src, int mask_act, float slope, int B, int H, int W, int Cin, int Cout, int kh, int kw,
                       int stride, int pad, int passes, int cin_total, float* ws, long long ws_floats, void* stream) {
   MTD_REQUIRE(dz && wpd && dx);
@@ -1517,7 +1524,8 @@ int mtd_conv_dgrad_tc(const float* dz, const float* wpd, float* dx, const float*
   TcArgs a{};
   a.ws = ws; a.ws_floats = ws ? ws_floats : 0;
   a.B = B; a.C1 = Cout; a.C2 = 0; a.N = Cin;
-  a.out = dx; a.scale = scale; a.bias = nullptr; a.pre_act = 0; a.add1 = add1; a.add2 = add2; a.post_act = 0;
+  a.out = dx; a.scale = scale; a.scale_group = (scale && scale_group > 0 && scale_group < B) ? scale_group : 0;
+  a.bias = nullptr; a.pre_act = 0; a.add1 = add1; a.add2 = add2; a.post_act = 0;
   a.mask_src = mask_src; a.mask_act = mask_act; a.slope = slope; a.aux = nullptr;
   a.outH = H; a.outW = W;
   if (stride == 1) {

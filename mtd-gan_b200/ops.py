@@ -252,6 +252,15 @@ def _tc_workspace(device) -> torch.Tensor:
     return ws
 
 
+def _scale_group(scale, B: int) -> int:
+    """Samples per 1/sigma entry: `scale` holds one entry per independent reference call batched together."""
+    if scale is None or scale.numel() == 1:
+        return 0
+    g = scale.numel()
+    assert B % g == 0, (B, g)
+    return B // g
+
+
 def _conv_forward_launch(x1, x2, weight, bias, scale, y, aux, add1, add2, cfg: ConvCfg):
     B, H, W, C1 = x1.shape
     C2 = 0 if x2 is None else x2.shape[3]
@@ -260,7 +269,8 @@ def _conv_forward_launch(x1, x2, weight, bias, scale, y, aux, add1, add2, cfg: C
         wp = _packed(weight, _tc_kind("fwd"), cfg)
     else:
         wp = _packed(weight, "fwd", cfg) if cfg.kh * cfg.kw > 1 or cfg.transposed else weight.detach()
-    args = (fptr(x1), fptr(x2), fptr(wp), fptr(bias), fptr(scale), fptr(y), fptr(aux), fptr(add1), fptr(add2), B, H, W, C1,
+    args = (fptr(x1), fptr(x2), fptr(wp), fptr(bias), fptr(scale), _scale_group(scale, B), fptr(y), fptr(aux), fptr(add1),
+            fptr(add2), B, H, W, C1,
             C2, cfg.cout, cfg.kh, cfg.kw, cfg.stride, cfg.pad, cfg.pre_act, cfg.post_act, cfg.slope)
     if tc:
         global tc_launches
@@ -301,12 +311,14 @@ def _conv_dgrad_launch(dz, weight, dx, scale, add1, B, H, W, cin_sub, cin_off, c
         tc_launches += 1
         wpd = _packed(weight, _tc_kind("dgrad"), cfg)
         ws = _tc_workspace(dx.device)
-        call("mtd_conv_dgrad_tc", fptr(dz), wpd.data_ptr() + 4 * cin_off * T * cfg.cout, fptr(dx), fptr(scale), fptr(add1), None,
+        call("mtd_conv_dgrad_tc", fptr(dz), wpd.data_ptr() + 4 * cin_off * T * cfg.cout, fptr(dx), fptr(scale),
+             _scale_group(scale, B), fptr(add1), None,
              None, 0, cfg.slope, B, H, W, cin_sub, cfg.cout, cfg.kh, cfg.kw, cfg.stride, cfg.pad, _TC_PASSES, cfg.cin,
              fptr(ws), ws.numel(), st)
     else:
         wpd = _packed(weight, "dgrad", cfg)
-        call("mtd_conv_dgrad", fptr(dz), wpd.data_ptr() + 4 * cin_off * T * cfg.cout, fptr(dx), fptr(scale), fptr(add1), None,
+        call("mtd_conv_dgrad", fptr(dz), wpd.data_ptr() + 4 * cin_off * T * cfg.cout, fptr(dx), fptr(scale),
+             _scale_group(scale, B), fptr(add1), None,
              None, 0, cfg.slope, B, H, W, cin_sub, cfg.cout, cfg.kh, cfg.kw, cfg.stride, cfg.pad, st)
 
 
@@ -314,8 +326,9 @@ class ConvFn(Function):
     """y = post_act( pre_act( scale * conv(cat[x1, x2], W) + b ) + add1 + add2 ).
 
     `weight` is the reference-layout parameter (Conv2d / ConvTranspose2d / Linear).  For spectrally
-    normalised layers `inv_sigma` (1-element), `u`, `v` are this call's power-iteration results and the
-    backward applies dW_orig = (G - <G,W~> u v^T)/sigma.
+    normalised layers `inv_sigma` (G,), `u` (G, rows), `v` (G, cols) are the power-iteration results of the G
+    independent reference calls batched in x1 (G = 1: one call; G = 2: e.g. D(real) and D(fake) as one batch, each
+    half scaled by its own 1/sigma) and the backward applies dW_orig = sum_g (G_g - <G_g,W~_g> u_g v_g^T)/sigma_g.
     """
 
     @staticmethod
@@ -376,22 +389,33 @@ class ConvFn(Function):
         # 3) weight gradient (packed), then to reference layout (+ spectral-norm correction)
         dw = None
         if need[2] and _wgrad_wanted(weight):
-            gp = _empty((weight.numel(),), dy)
-            _conv_wgrad_launch(x1, x2, dz, gp, B, H, W, C1, C2, cfg)
+            G = 1 if inv_sigma is None else inv_sigma.numel()
+            Bg = B // G
+            insts = []
+            for g in range(G):              # one packed weight gradient per batched reference call (own u, v, sigma)
+                gp = _empty((weight.numel(),), dy)
+                if G == 1:
+                    _conv_wgrad_launch(x1, x2, dz, gp, B, H, W, C1, C2, cfg)
+                    insts.append((gp, weight.detach(), None if u is None else u.reshape(-1), None if v is None else v.reshape(-1),
+                                  inv_sigma, cfg))
+                else:
+                    sl = slice(g * Bg, (g + 1) * Bg)
+                    _conv_wgrad_launch(x1[sl], None if x2 is None else x2[sl], dz[sl], gp, Bg, H, W, C1, C2, cfg)
+                    insts.append((gp, weight.detach(), u[g], v[g], inv_sigma[g:g + 1], cfg))
             if _finish_queue is not None:
                 grp = _finish_queue.get(weight.data_ptr())
-                inst = (gp, weight.detach(), u, v, inv_sigma, cfg)
                 if grp is None:
                     dw = torch.empty_like(weight)
-                    _finish_queue[weight.data_ptr()] = (dw, [inst])
+                    _finish_queue[weight.data_ptr()] = (dw, insts)
                 else:
-                    grp[1].append(inst)            # summed into the first instance's dw by the batched unpack
+                    grp[1].extend(insts)           # summed into the first instance's dw by the batched unpack
             else:
-                dw = torch.empty_like(weight)
-                scratch = torch.empty(4, dtype=torch.float32, device=dy.device) if inv_sigma is not None else None
-                call("mtd_conv_wgrad_finish", fptr(gp), fptr(dw), cfg.transposed, cfg.cout, cfg.cin, cfg.kh, cfg.kw,
-                     fptr(weight.detach()) if inv_sigma is not None else None, fptr(u), fptr(v), fptr(inv_sigma),
-                     ptr(scratch), st)
+                for k, (gp, wd, ug, vg, inv_g, _) in enumerate(insts):
+                    part = torch.empty_like(weight)
+                    scratch = torch.empty(4, dtype=torch.float32, device=dy.device) if inv_g is not None else None
+                    call("mtd_conv_wgrad_finish", fptr(gp), fptr(part), cfg.transposed, cfg.cout, cfg.cin, cfg.kh, cfg.kw,
+                         fptr(wd) if inv_g is not None else None, fptr(ug), fptr(vg), fptr(inv_g), ptr(scratch), st)
+                    dw = part if k == 0 else dw + part
         d_add1 = d_add if (need[7] and not cfg.fuse_add1_is_input) else None
         d_add2 = d_add if need[8] else None
         return dx1, dx2, dw, dbias, None, None, None, d_add1, d_add2, None

@@ -253,3 +253,47 @@ def test_cuda_graph_step_matches_eager():
     assert errs[len(errs) // 2] <= 1e-4 and errs[int(len(errs) * 0.9)] <= 5e-2, (errs[len(errs) // 2], errs[-1])
     worst_abs = max(float((sd_g[k].double() - sd_e[k].double()).abs().max()) for k in sd_e if not k.endswith(("weight_u", "weight_v")))
     assert worst_abs <= 3 * 2 * 1e-4 + 1e-6, worst_abs          # <= 2*lr per step per element
+
+
+@pytest.mark.parametrize("mode", ["simt", "tc3"])
+def test_discriminator_grouped_pass_equals_separate_calls(masks, mode):
+    """D(cat[a, b], groups=2) == (D(a), D(b)) called one after the other: outputs, spectral-norm buffers and the
+    parameter gradients of a loss over both (d_loss batches the reference's call pairs this way).  In exact-fp32 mode
+    the two evaluations differ only by summation order; in the default tensor-core mode the weight gradients are
+    plain TF32 (2e-3 class) and the GEMMs are tiled differently (3 vs 6 samples per launch)."""
+    import copy
+    from mtdgan_b200 import ops
+    ops.set_conv_mode("simt" if mode == "simt" else "auto", 3)
+    try:
+        m1 = seeded_model().train()
+        D1 = m1.Discriminator
+        D2 = copy.deepcopy(D1)
+        a, b = (t.to(DEV) for t in O.synthetic_pair(3, 64, seed=77))
+        mk = [drop_mask(3, 31), drop_mask(3, 32)]
+        masks.extend([mk[0], mk[1]])
+        e1, d1, r1 = D1(a)
+        e2, d2, r2 = D1(b)
+        masks.extend([mk[0], mk[1]])
+        e, d, r = D2(torch.cat([a, b], 0), groups=2)
+        for got, ref in ((e, torch.cat([e1, e2])), (d, torch.cat([d1, d2])), (r, torch.cat([r1, r2]))):
+            assert rel_err(got, ref) <= 1e-4          # x_enc is ~1e-6 at initialisation: fp32 noise of the last layer
+        for (k, v1), (_, v2) in zip(D1.named_buffers(), D2.named_buffers()):
+            assert rel_err(v2, v1) <= 1e-6, k
+        g = torch.Generator().manual_seed(3)
+        we, wd, wr = (torch.randn(s, generator=g).to(DEV) for s in (e.shape, d.shape, r.shape))
+        ((torch.cat([e1, e2]) * we).sum() + (torch.cat([d1, d2]) * wd).sum() / 64 + (torch.cat([r1, r2]) * wr).sum() / 64).backward()
+        ((e * we).sum() + (d * wd).sum() / 64 + (r * wr).sum() / 64).backward()
+        tally = GradTally()
+        for (k, p1), (_, p2) in zip(D1.named_parameters(), D2.named_parameters()):
+            if p1.grad is None:
+                assert p2.grad is None, k
+            else:
+                tally.add(k, rel_err(p2.grad, p1.grad), 2e-3 if mode == "simt" else 2e-2)
+        # Forward values differ in the last fp32 bits between the two evaluations, so individual LeakyReLU decisions flip:
+        # per-tensor agreement is statistical (GradTally); a wrong per-group sigma / u / v would shift EVERY
+        # spectrally-normalised weight gradient by O(1).
+        errs = tally.finish(1e-4 if mode == "simt" else 5e-3)
+        print("grouped-vs-separate gradient errors (%s): median %.2e, p90 %.2e, max %.2e"
+              % (mode, errs[len(errs) // 2], errs[int(len(errs) * 0.9)], errs[-1]))
+    finally:
+        ops.set_conv_mode("auto", 3)

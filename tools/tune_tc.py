@@ -67,7 +67,7 @@ def main():
         flop = 2.0 * B * H * H * N * C * k * k
 
         def launch(i, st):
-            call("mtd_conv_fwd_tc", fptr(x1), fptr(x2), fptr(wps[i % ncopy]), fptr(bias), None, fptr(y), None, None, None,
+            call("mtd_conv_fwd_tc", fptr(x1), fptr(x2), fptr(wps[i % ncopy]), fptr(bias), None, 0, fptr(y), None, None, None,
                  B, H, H, C1, C2, N, k, k, 1, k // 2, ops.ACT_LEAKY, 0, 0.2, args.passes, fptr(ws), ws.numel(), st)
 
         def measure():
