@@ -669,13 +669,42 @@ __global__ void __launch_bounds__(256) finish_unpack_kernel(const FinSeg* __rest
   const FinSeg head = segs[ck.x];
   const size_t total = (size_t)head.N * head.T * head.C;
   const size_t end = min(total, (size_t)ck.y + (size_t)fin_chunk_elems(head.T, head.C));
-  const bool rowmajor = fin_row_major(head);
-  const int T = (int)head.T, C = (int)head.C, row = T * C;
+  if (fin_row_major(head)) {
+    // Conv2d / Linear layout, whole packed rows: 32-bit index arithmetic only, per-instance constants hoisted out of
+    // the element loop, sums accumulated in shared memory at the element's REFERENCE position, one coalesced store.
+    const int cnt = (int)(end - ck.y), T = (int)head.T, C = (int)head.C, row = T * C;
+    const int n0 = (int)(ck.y / (size_t)row);
+    for (int j = threadIdx.x; j < cnt; j += blockDim.x) sm[fin_pad(j)] = 0.f;      // each thread owns its j's throughout
+    long long si = ck.x;
+    while (si >= 0) {                                   // every forward instance (and batched group) that used this weight
+      const FinSeg& s = segs[si];
+      const float* gp = s.gp + ck.y;
+      if (s.inv_sigma) {
+        const float alpha = __ldg(s.inv_sigma);
+        const float beta = (float)dots[s.slot] * alpha;
+        for (int j = threadIdx.x; j < cnt; j += blockDim.x) {
+          const int c = j % C, r = j / C, t = r % T, nl = r / T;
+          const int col = c * T + t;                    // reference (Cout, Cin*kh*kw) matrix view: row = n, col = c*T + t
+          const float g = alpha * (gp[j] - beta * __ldg(s.u + n0 + nl) * __ldg(s.v + col));
+          sm[fin_pad(nl * row + col)] += g;
+        }
+      } else {
+        for (int j = threadIdx.x; j < cnt; j += blockDim.x) {
+          const int c = j % C, r = j / C, t = r % T, nl = r / T;
+          sm[fin_pad(nl * row + c * T + t)] += gp[j];
+        }
+      }
+      si = s.next;
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < cnt; j += blockDim.x) head.dw[ck.y + j] = sm[fin_pad(j)];
+    return;
+  }
   for (size_t i = (size_t)ck.y + threadIdx.x; i < end; i += blockDim.x) {
     const size_t ref = fin_ref_index(head, i);
     float sum = 0.f;
     long long si = ck.x;
-    while (si >= 0) {                                   // every forward instance that used this weight
+    while (si >= 0) {
       const FinSeg& s = segs[si];
       float g = s.gp[i];
       if (s.inv_sigma) {
@@ -687,18 +716,7 @@ __global__ void __launch_bounds__(256) finish_unpack_kernel(const FinSeg* __rest
       sum += g;
       si = s.next;
     }
-    if (rowmajor) {
-      const int j = (int)(i - ck.y);
-      const int c = j % C, r = j / C, t = r % T, nl = r / T;
-      sm[fin_pad(nl * row + c * T + t)] = sum;
-    } else {
-      head.dw[ref] = sum;
-    }
-  }
-  if (rowmajor) {                                       // the chunk's reference-layout image is contiguous from ck.y
-    __syncthreads();
-    const int cnt = (int)(end - ck.y);
-    for (int j = threadIdx.x; j < cnt; j += blockDim.x) head.dw[ck.y + j] = sm[fin_pad(j)];
+    head.dw[ref] = sum;
   }
 }
 
