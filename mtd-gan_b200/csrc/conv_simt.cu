@@ -607,7 +607,8 @@ struct FinSeg {
   const float* u;
   const float* v;
   const float* inv_sigma;
-  long long N, T, C, sN, sC, flip, sn_cols, slot, next, pad1;
+  long long N, T, C, sN, sC, flip, sn_cols, slot, next;
+  const double* dot_zw;     // optional: sum over this instance's pixels of dz . (W (*) x), computed by mtd_act_bwd_sn (then no dot pass)
 };
 static_assert(sizeof(FinSeg) == 128, "finish segment must be 16 x int64");
 
@@ -681,7 +682,8 @@ __global__ void __launch_bounds__(256) finish_unpack_kernel(const FinSeg* __rest
       const float* gp = s.gp + ck.y;
       if (s.inv_sigma) {
         const float alpha = __ldg(s.inv_sigma);
-        const float beta = (float)dots[s.slot] * alpha;
+        // <G, W~> = <G, W_orig> / sigma; from the activations it is alpha^-1 * sum dz.(y_pre - b) * alpha = that sum itself
+        const float beta = s.dot_zw ? (float)(*s.dot_zw) : (float)dots[s.slot] * alpha;
         for (int j = threadIdx.x; j < cnt; j += blockDim.x) {
           const int c = j % C, r = j / C, t = r % T, nl = r / T;
           const int col = c * T + t;                    // reference (Cout, Cin*kh*kw) matrix view: row = n, col = c*T + t
@@ -709,7 +711,7 @@ __global__ void __launch_bounds__(256) finish_unpack_kernel(const FinSeg* __rest
       float g = s.gp[i];
       if (s.inv_sigma) {
         const float alpha = __ldg(s.inv_sigma);
-        const float beta = (float)dots[s.slot] * alpha;
+        const float beta = s.dot_zw ? (float)(*s.dot_zw) : (float)dots[s.slot] * alpha;
         const size_t srow = ref / (size_t)s.sn_cols, col = ref - srow * (size_t)s.sn_cols;
         g = alpha * (g - beta * __ldg(s.u + srow) * __ldg(s.v + col));
       }
@@ -1007,6 +1009,61 @@ __global__ void __launch_bounds__(256) act_bwd_v4_kernel(const float4* __restric
   }
 }
 
+// act_bwd for spectrally-normalised layers: additionally accumulates, per batched reference call g (a contiguous
+// block of `group4` float4 elements), zw[g] = sum dz . (y_pre - bias): with y_pre = conv(x, W_orig)/sigma + bias this is
+// <G_g, W_orig>/sigma_g = <G_g, W~_g>, the coefficient of the spectral-norm weight-gradient correction -- taken from data
+// this pass reads anyway instead of a separate pass over the packed gradient and the weight.  LeakyReLU is inverted
+// exactly (y_pre = y > 0 ? y : y / slope); not available for ReLU (y = 0 loses y_pre).  zw and dbias pre-zeroed.
+__global__ void __launch_bounds__(256) act_bwd_sn_kernel(const float4* __restrict__ dy, const float4* __restrict__ y,
+                                                         float4* __restrict__ dz, float* __restrict__ dbias,
+                                                         const float4* __restrict__ bias, double* __restrict__ zw, size_t total4,
+                                                         size_t group4, int N4, int act, float slope) {
+  mtd_pdl_prologue();
+  extern __shared__ float colsum[];   // 4 * N4 floats when dbias != null
+  __shared__ double red[32];
+  if (dbias) {
+    for (int i = threadIdx.x; i < 4 * N4; i += blockDim.x) colsum[i] = 0.f;
+    __syncthreads();
+  }
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;      // a multiple of N4 (host guarantees it): channels are fixed
+  const size_t first = i;
+  const float4 b4 = (bias && first < total4) ? __ldg(bias + first % N4) : make_float4(0.f, 0.f, 0.f, 0.f);
+  const float inv_slope = 1.f / slope;
+  float4 priv = make_float4(0.f, 0.f, 0.f, 0.f);
+  double part[4] = {0.0, 0.0, 0.0, 0.0};                     // up to 4 batched calls
+  for (; i < total4; i += stride) {
+    float4 g = __ldcs(dy + i);
+    const float4 t = __ldcs(y + i);
+    float4 yp = t;
+    if (act == MTD_ACT_LEAKY) {
+      g.x *= t.x > 0.f ? 1.f : slope; g.y *= t.y > 0.f ? 1.f : slope; g.z *= t.z > 0.f ? 1.f : slope; g.w *= t.w > 0.f ? 1.f : slope;
+      yp.x = t.x > 0.f ? t.x : t.x * inv_slope; yp.y = t.y > 0.f ? t.y : t.y * inv_slope;
+      yp.z = t.z > 0.f ? t.z : t.z * inv_slope; yp.w = t.w > 0.f ? t.w : t.w * inv_slope;
+    }
+    if (dz) dz[i] = g;
+    priv.x += g.x; priv.y += g.y; priv.z += g.z; priv.w += g.w;
+    const float d = g.x * (yp.x - b4.x) + g.y * (yp.y - b4.y) + g.z * (yp.z - b4.z) + g.w * (yp.w - b4.w);
+    part[(i >= group4) + (i >= 2 * group4) + (i >= 3 * group4)] += (double)d;      // groups <= 4
+  }
+  if (dbias) {
+    if (first < total4) {
+      float* cs = colsum + 4 * (first % N4);
+      atomicAdd(cs, priv.x); atomicAdd(cs + 1, priv.y); atomicAdd(cs + 2, priv.z); atomicAdd(cs + 3, priv.w);
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < 4 * N4; c += blockDim.x) {
+      float v = colsum[c];
+      if (v != 0.f) atomicAdd(dbias + c, v);
+    }
+  }
+  const int ngroups = (int)((total4 + group4 - 1) / group4);
+  for (int gi = 0; gi < ngroups && gi < 4; ++gi) {
+    const double r = block_sum(part[gi], red);
+    if (threadIdx.x == 0 && r != 0.0) atomicAdd(zw + gi, r);
+  }
+}
+
 void tap_table_fwd(int* dy, int* dx, int kh, int kw, int pad) {
   for (int ky = 0; ky < kh; ++ky)
     for (int kx = 0; kx < kw; ++kx) {
@@ -1270,6 +1327,34 @@ int mtd_act_bwd(const float* dy, const float* y, float* dz, float* dbias, int db
     }
   }
   mtd_launch(act_bwd_kernel, blocks, 256, dbias ? N * sizeof(float) : 0, st, dy, y, dz, dbias, total, N, act, slope);
+  MTD_CHECK_LAUNCH();
+  return MTD_OK;
+}
+
+// mtd_act_bwd for a spectrally-normalised layer whose batch holds `groups` (<= 4) reference calls of M/groups rows:
+// also accumulates zw[g] += sum over group g of dz . (y_pre - bias) (see act_bwd_sn_kernel).  dbias (optional) and zw
+// must be all zero on entry.  act: MTD_ACT_NONE or MTD_ACT_LEAKY.  Requires N % 4 == 0 and a power-of-two N <= 8192.
+int mtd_act_bwd_sn(const float* dy, const float* y, float* dz, float* dbias, const float* bias, double* zw, int groups,
+                   long long M, int N, int act, float slope, void* stream) {
+  MTD_REQUIRE(dy && y && zw && M > 0 && N > 0 && N % 4 == 0 && N <= 8192 && groups >= 1 && groups <= 4 && M % groups == 0);
+  MTD_REQUIRE(act == MTD_ACT_NONE || act == MTD_ACT_LEAKY);
+  MTD_REQUIRE(mtd_aligned16(dy) && mtd_aligned16(y) && (!dz || mtd_aligned16(dz)) && (!bias || mtd_aligned16(bias)));
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t total4 = (size_t)M * N / 4;
+  const int N4 = N / 4;
+  int blocks = (int)std::min<size_t>((total4 + 255) / 256, (size_t)mtd_sm_count() * 4);
+  size_t stride = (size_t)blocks * 256;
+  if ((size_t)N4 > stride) blocks = (N4 + 255) / 256;
+  else if (stride % N4 != 0) {
+    size_t s2 = stride / N4 * N4;
+    while (s2 > 0 && s2 % 256 != 0) s2 -= N4;
+    MTD_REQUIRE(s2 > 0);
+    blocks = (int)(s2 / 256);
+  }
+  MTD_REQUIRE(((size_t)blocks * 256) % N4 == 0);
+  mtd_launch(act_bwd_sn_kernel, blocks, 256, dbias ? N * sizeof(float) : 0, st, reinterpret_cast<const float4*>(dy),
+             reinterpret_cast<const float4*>(y), reinterpret_cast<float4*>(dz), dbias, reinterpret_cast<const float4*>(bias), zw,
+             total4, total4 / groups, N4, act, slope);
   MTD_CHECK_LAUNCH();
   return MTD_OK;
 }

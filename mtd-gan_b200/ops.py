@@ -114,17 +114,21 @@ _fin_chunk_cache: dict = {}
 
 class deferred_wgrad_finish:
     def __enter__(self):
-        global _finish_queue, _bias_slab
+        global _finish_queue, _bias_slab, _zw_slab
         self.prev, _finish_queue = _finish_queue, {}
         self.prev_slab, _bias_slab = _bias_slab, None
+        self.prev_zw, _zw_slab = _zw_slab, None
         return self
 
     def __exit__(self, *exc):
-        global _finish_queue, _bias_slab
-        _bias_slab = self.prev_slab
+        global _finish_queue, _bias_slab, _zw_slab
         q, _finish_queue = _finish_queue, self.prev
+        zw_keepalive = _zw_slab               # the finishing kernels read the <G, W~> accumulators through raw pointers
+        _bias_slab = self.prev_slab
+        _zw_slab = self.prev_zw
         if q and exc[0] is None:
             _flush_finish(q)
+        del zw_keepalive
         return False
 
 
@@ -133,6 +137,21 @@ class deferred_wgrad_finish:
 # node per layer.
 _BIAS_SLAB_FLOATS = 1 << 18
 _bias_slab = None             # [tensor, next free offset] of the active context
+
+
+_zw_slab = None               # [float64 tensor, next free offset]: <G, W~> accumulators of the active context
+
+
+def _zw_alloc(n: int, like):
+    """n zeroed doubles for mtd_act_bwd_sn (only inside a deferred-finishing context)."""
+    global _zw_slab
+    if _zw_slab is None:
+        _zw_slab = [torch.zeros(8192, dtype=torch.float64, device=like.device), 0]
+    t, off = _zw_slab
+    if off + n > t.numel():
+        return None                          # slab exhausted: the caller falls back to the dot pass
+    _zw_slab[1] = off + n
+    return t[off:off + n]
 
 
 def _dbias_alloc(n: int, like):
@@ -157,14 +176,14 @@ def _flush_finish(groups):
         base = len(rows)
         heads.append(base)
         head_numels.append(dw.numel())
-        for k, (gp, w, u, v, inv, cfg) in enumerate(insts):
+        for k, (gp, w, u, v, inv, cfg, zwp) in enumerate(insts):
             T = cfg.kh * cfg.kw
             sN, sC, flip = (T, cfg.cout * T, 1) if cfg.transposed else (cfg.cin * T, T, 0)
             sn = inv is not None
             rows.append([gp.data_ptr(), dw.data_ptr(), w.data_ptr() if sn else 0, u.data_ptr() if sn else 0,
                          v.data_ptr() if sn else 0, inv.data_ptr() if sn else 0, cfg.cout, T, cfg.cin, sN, sC, flip,
-                         cfg.cin * T, base + k, base + k + 1 if k + 1 < len(insts) else -1, 0])
-            dot_numels.append(gp.numel() if sn else 0)
+                         cfg.cin * T, base + k, base + k + 1 if k + 1 < len(insts) else -1, zwp])
+            dot_numels.append(gp.numel() if (sn and not zwp) else 0)
             rowdims.append((T, cfg.cin))
     key = (tuple(dot_numels), tuple(heads), tuple(rowdims), str(dev))
     ent = _fin_chunk_cache.get(key)
@@ -347,13 +366,13 @@ class ConvFn(Function):
         ctx.has_add = has_add
         ctx.weight_obj = weight          # identity key of the packed-weight cache
         ctx.shapes = (B, H, W, C1, C2)
-        ctx.save_for_backward(x1, x2, weight, inv_sigma, u, v, y, aux)
+        ctx.save_for_backward(x1, x2, weight, inv_sigma, u, v, y, aux, bias)
         return y
 
     @staticmethod
     def backward(ctx, dy):
         cfg: ConvCfg = ctx.cfg
-        x1, x2, weight, inv_sigma, u, v, y, aux = ctx.saved_tensors
+        x1, x2, weight, inv_sigma, u, v, y, aux, bias = ctx.saved_tensors
         weight = ctx.weight_obj
         B, H, W, C1, C2 = ctx.shapes
         need = list(ctx.needs_input_grad)
@@ -369,7 +388,21 @@ class ConvFn(Function):
             call("mtd_act_bwd", fptr(dy), fptr(y), fptr(g1), None, 0, M, cfg.cout, cfg.post_act, cfg.slope, st)
         d_add = g1 if ctx.has_add else None
         dbias, dbz = _dbias_alloc(cfg.cout, dy) if need[3] else (None, 0)
-        if cfg.pre_act != ACT_NONE:
+        want_w = need[2] and _wgrad_wanted(weight)
+        G = 1 if inv_sigma is None else inv_sigma.numel()
+        # spectrally-normalised layer inside a deferred-finishing pass: the correction coefficient <G_g, W~_g> of every
+        # batched call g comes out of the activation-backward pass itself (mtd_act_bwd_sn) -- no dot pass later
+        zw = None
+        if (want_w and inv_sigma is not None and _finish_queue is not None and cfg.post_act == ACT_NONE and not ctx.has_add
+                and cfg.pre_act in (ACT_NONE, ACT_LEAKY) and cfg.cout % 4 == 0 and G <= 4):
+            zw = _zw_alloc(G, dy)
+        if zw is not None:
+            if dbias is not None and not dbz:
+                dbias.zero_()
+            dz = _empty(dy.shape, dy) if cfg.pre_act != ACT_NONE else g1
+            call("mtd_act_bwd_sn", fptr(g1), fptr(y), fptr(dz) if cfg.pre_act != ACT_NONE else None, fptr(dbias), fptr(bias),
+                 zw.data_ptr(), G, M, cfg.cout, cfg.pre_act, cfg.slope, st)
+        elif cfg.pre_act != ACT_NONE:
             pre_out = aux if aux is not None else y
             dz = _empty(dy.shape, dy)
             call("mtd_act_bwd", fptr(g1), fptr(pre_out), fptr(dz), fptr(dbias), dbz, M, cfg.cout, cfg.pre_act, cfg.slope, st)
@@ -388,8 +421,7 @@ class ConvFn(Function):
             _conv_dgrad_launch(dz, weight, dx2, inv_sigma, None, B, H, W, C2, C1, cfg)
         # 3) weight gradient (packed), then to reference layout (+ spectral-norm correction)
         dw = None
-        if need[2] and _wgrad_wanted(weight):
-            G = 1 if inv_sigma is None else inv_sigma.numel()
+        if want_w:
             Bg = B // G
             insts = []
             for g in range(G):              # one packed weight gradient per batched reference call (own u, v, sigma)
@@ -397,11 +429,11 @@ class ConvFn(Function):
                 if G == 1:
                     _conv_wgrad_launch(x1, x2, dz, gp, B, H, W, C1, C2, cfg)
                     insts.append((gp, weight.detach(), None if u is None else u.reshape(-1), None if v is None else v.reshape(-1),
-                                  inv_sigma, cfg))
+                                  inv_sigma, cfg, 0 if zw is None else zw.data_ptr()))
                 else:
                     sl = slice(g * Bg, (g + 1) * Bg)
                     _conv_wgrad_launch(x1[sl], None if x2 is None else x2[sl], dz[sl], gp, Bg, H, W, C1, C2, cfg)
-                    insts.append((gp, weight.detach(), u[g], v[g], inv_sigma[g:g + 1], cfg))
+                    insts.append((gp, weight.detach(), u[g], v[g], inv_sigma[g:g + 1], cfg, 0 if zw is None else zw.data_ptr() + 8 * g))
             if _finish_queue is not None:
                 grp = _finish_queue.get(weight.data_ptr())
                 if grp is None:
@@ -410,7 +442,7 @@ class ConvFn(Function):
                 else:
                     grp[1].extend(insts)           # summed into the first instance's dw by the batched unpack
             else:
-                for k, (gp, wd, ug, vg, inv_g, _) in enumerate(insts):
+                for k, (gp, wd, ug, vg, inv_g, _, _zw) in enumerate(insts):
                     part = torch.empty_like(weight)
                     scratch = torch.empty(4, dtype=torch.float32, device=dy.device) if inv_g is not None else None
                     call("mtd_conv_wgrad_finish", fptr(gp), fptr(part), cfg.transposed, cfg.cout, cfg.cin, cfg.kh, cfg.kw,

@@ -422,3 +422,73 @@ def test_adamw_step_matches_torch():
         ob.step()
     for pa, pb in zip(a, b):
         assert rel_err(pb, pa) <= 1e-6
+
+
+@pytest.mark.parametrize("M,N,groups,act", [(16, 512, 1, 2), (40, 512, 2, 2), (2 * 3 * 64 * 64, 64, 2, 2), (8, 2048, 2, 0), (6 * 17, 24, 2, 2)])
+def test_act_bwd_sn_matches_reference(M, N, groups, act):
+    """mtd_act_bwd_sn: dz, bias gradient and the per-call spectral-norm coefficients sum dz.(y_pre - b)."""
+    from mtdgan_b200._ext import call, fptr, stream
+    g = torch.Generator().manual_seed(M + N)
+    ypre = torch.randn(M, N, generator=g, dtype=torch.float64)
+    bias = torch.randn(N, generator=g, dtype=torch.float64) * 0.1
+    dy = torch.randn(M, N, generator=g, dtype=torch.float64)
+    y = torch.where(ypre > 0, ypre, 0.2 * ypre) if act == 2 else ypre
+    dz_ref = dy * torch.where(y > 0, 1.0, 0.2) if act == 2 else dy
+    zw_ref = (dz_ref * (ypre - bias)).reshape(groups, -1).sum(1)
+    dyc, yc, bc = dy.float().to(DEV), y.float().to(DEV), bias.float().to(DEV)
+    dz = torch.empty_like(dyc)
+    db = torch.zeros(N, device=DEV)
+    zw = torch.zeros(groups, dtype=torch.float64, device=DEV)
+    call("mtd_act_bwd_sn", fptr(dyc), fptr(yc), fptr(dz), fptr(db), fptr(bc), zw.data_ptr(), groups, M, N, act, 0.2, stream())
+    torch.cuda.synchronize()
+    assert rel_err(dz, dz_ref) <= 1e-6
+    assert rel_err(db, dz_ref.sum(0)) <= 1e-5
+    scale = float((dz_ref * (ypre - bias)).abs().reshape(groups, -1).sum(1).max())      # cancellation-free magnitude
+    assert float((zw.cpu() - zw_ref).abs().max()) <= 2e-6 * scale
+
+
+def test_spectral_norm_grouped_deferred_matches_two_calls():
+    """Two batched reference calls through one SN conv (per-group 1/sigma, per-group weight-gradient correction with
+    the coefficients from mtd_act_bwd_sn, deferred batched finishing) == two separate torch spectral-norm calls."""
+    import torch.nn as nn
+    from mtdgan_b200 import networks as NW, ops
+    from mtdgan_b200._ext import call, fptr, ptr, stream
+    torch.manual_seed(5)
+    ref = nn.utils.spectral_norm(nn.Conv2d(32, 64, 3, 1, 1)).double().train()
+    sd0 = {k: v.clone() for k, v in ref.state_dict().items()}
+    xa, xb = _rand(3, 32, 8, 8, seed=6), _rand(3, 32, 8, 8, seed=7)
+    ga, gb = _rand(3, 64, 8, 8, seed=8), _rand(3, 64, 8, 8, seed=9)
+    ya = F.leaky_relu(ref(xa), 0.2)
+    yb = F.leaky_relu(ref(xb), 0.2)                  # second call: second power iteration
+    ((ya * ga).sum() + (yb * gb).sum()).backward()
+    holder = nn.Module()
+    holder.conv = nn.utils.spectral_norm(nn.Conv2d(32, 64, 3, 1, 1))
+    holder.conv.load_state_dict({k: v.float() for k, v in sd0.items()})
+    holder.to(DEV)
+    st = NW._SNState([holder.conv], torch.device(DEV))
+    u_snap = torch.empty(2, st.u_total, device=DEV)
+    v_snap = torch.empty(2, st.v_total, device=DEV)
+    inv = torch.empty(2, 1, device=DEV)
+    for g in range(2):
+        call("mtd_sn_power_iter", ptr(st.tab), 1, ptr(st.wtu), st.n_wtu, ptr(st.wv), st.n_wv, fptr(st.t_ws), st.v_total,
+             fptr(st.s_ws), fptr(u_snap[g]), fptr(v_snap[g]), fptr(inv[g]), 1, 1e-12, stream())
+    xc = nhwc(torch.cat([xa, xb]).float()).to(DEV)
+    cfg = ops.ConvCfg(cin=32, cout=64, pre_act=ops.ACT_LEAKY)
+    w, b = holder.conv.weight_orig, holder.conv.bias
+    y = ops.conv(xc, w, b, cfg, inv_sigma=inv.reshape(2), u=u_snap, v=v_snap)
+    assert rel_err(nchw(y), torch.cat([ya, yb])) <= TOL
+    loss = (y * nhwc(torch.cat([ga, gb]).float()).to(DEV)).sum()
+    with ops.deferred_wgrad_finish():
+        dw, db = torch.autograd.grad(loss, [w, b])
+    torch.cuda.synchronize()
+    assert rel_err(db, ref.bias.grad) <= TOL
+    assert rel_err(dw, ref.weight_orig.grad) <= 2e-3        # weight gradient GEMM runs in plain TF32 on this shape
+    ops.set_conv_mode("simt")
+    try:
+        y = ops.conv(xc, w, b, cfg, inv_sigma=inv.reshape(2), u=u_snap, v=v_snap)
+        loss = (y * nhwc(torch.cat([ga, gb]).float()).to(DEV)).sum()
+        with ops.deferred_wgrad_finish():
+            dw, db = torch.autograd.grad(loss, [w, b])
+        assert rel_err(dw, ref.weight_orig.grad) <= 2e-5    # exact-fp32 kernels
+    finally:
+        ops.set_conv_mode("auto", 3)

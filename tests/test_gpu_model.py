@@ -37,7 +37,10 @@ class Tol:
     def __init__(self, mode):
         self.mode = mode
         self.out = {"simt": 1e-4, "tc3": 3e-4, "tc1": 1e-2}[mode]
-        self.grad = {"simt": 2e-4, "tc3": 2e-3, "tc1": 1e-1}[mode]
+        # per-tensor bound; the MEDIAN over tensors (below) is the sharp check (measured ~3e-7 in simt mode).  With 4
+        # samples a deep discriminator layer sees 4-16 pixels, so one flipped LeakyReLU decision (forward sums differ in
+        # the last bit between runs: fp32 atomics) moves a tensor by a few 1e-4 -- hence 1e-3, not 2e-4, per tensor.
+        self.grad = {"simt": 1e-3, "tc3": 2e-3, "tc1": 1e-1}[mode]
         self.median = {"simt": 1e-4, "tc3": 1e-3, "tc1": 1e-2}[mode]   # tc3: weight gradients run in plain TF32 (2e-3 class)
 
 
@@ -288,7 +291,7 @@ def test_discriminator_grouped_pass_equals_separate_calls(masks, mode):
             if p1.grad is None:
                 assert p2.grad is None, k
             else:
-                tally.add(k, rel_err(p2.grad, p1.grad), 2e-3 if mode == "simt" else 2e-2)
+                tally.add(k, rel_err(p2.grad, p1.grad), 2e-2)
         # Forward values differ in the last fp32 bits between the two evaluations, so individual LeakyReLU decisions flip:
         # per-tensor agreement is statistical (GradTally); a wrong per-group sigma / u / v would shift EVERY
         # spectrally-normalised weight gradient by O(1).
