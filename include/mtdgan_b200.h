@@ -83,14 +83,17 @@ int mtd_conv_wgrad_finish(const float* gp, float* dw_ref, int transposed, int Co
  * instances that share a weight are summed into one dw.  Segment table int64[n][16] = { gp, dw, w_ref, u, v,
  * inv_sigma, Cout, kh*kw, Cin, sN, sC, flip, sn_cols, dot slot, next segment of the same weight or -1,
  * pointer to a precomputed <G,W~> (mtd_act_bwd_sn) or 0 }
- * (Conv2d: sN = Cin*T, sC = T, flip 0; ConvTranspose2d: sN = T, sC = Cout*T, flip 1).  dot_chunks lists every
+ * (Conv2d: sN = Cin*T, sC = T, flip 0; ConvTranspose2d: sN = T, sC = Cout*T, flip 1; flip bits 2 / 4: see
+ * mtd_act_bwd_sn).  dot_chunks lists every
  * spectral-normed segment, head_chunks only the first segment of each weight.                              */
 /* mtd_act_bwd for spectrally-normalised layers: also accumulates zw[g] += sum over the rows of batched call g of
  * dz . (y_pre - bias) = <G_g, W_orig>/sigma_g, the coefficient of the spectral-norm weight-gradient correction
  * (replaces the dot pass of the finishing step: segment field 15 = pointer to zw[g]).  dbias and zw pre-zeroed;
- * act = none or leaky.                                                                                    */
-int mtd_act_bwd_sn(const float* dy, const float* y, float* dz, float* dbias, const float* bias, double* zw, int groups,
-                   long long M, int N, int act, float slope, void* stream);
+ * act = none or leaky.  dz_scale (optional, one 1/sigma per call): the dz written is pre-scaled, so dgrad needs no
+ * scale and one weight-gradient GEMM over the whole batch gives sum_g G_g/sigma_g (segment flag bits: 2 = gp is
+ * pre-scaled, 4 = correction-only instance without a gp).                                                  */
+int mtd_act_bwd_sn(const float* dy, const float* y, float* dz, float* dbias, const float* bias, double* zw,
+                   const float* dz_scale, int groups, long long M, int N, int act, float slope, void* stream);
 /* elements per chunk-table entry of a segment with kh*kw = taps and Cin = cin: a whole number of packed rows when a
  * row fits the kernels' shared-memory staging (coalesced transposition), else a fixed block                     */
 int mtd_wgrad_finish_chunk_elems(int taps, int cin);

@@ -617,7 +617,7 @@ __device__ __forceinline__ size_t fin_ref_index(const FinSeg& s, size_t i) {
   const size_t r = i / s.C;
   const int t = (int)(r % s.T);
   const size_t n = r / s.T;
-  const long long toff = s.flip ? (s.T - 1 - t) : t;
+  const long long toff = (s.flip & 1) ? (s.T - 1 - t) : t;
   return n * (size_t)s.sN + (size_t)c * s.sC + toff;
 }
 
@@ -629,8 +629,9 @@ __host__ __device__ inline long long fin_chunk_elems(long long T, long long C) {
   const long long row = T * C;
   return row <= kFinChunk ? (kFinChunk / row) * row : kFinChunk;
 }
+constexpr long long kFinFlip = 1, kFinPrescaled = 2, kFinNoGp = 4;     // bits of FinSeg::flip
 __device__ __forceinline__ bool fin_row_major(const FinSeg& s) {
-  return !s.flip && s.sC == s.T && s.sN == s.T * s.C && s.T * s.C <= kFinChunk;
+  return !(s.flip & kFinFlip) && s.sC == s.T && s.sN == s.T * s.C && s.T * s.C <= kFinChunk;
 }
 __device__ __forceinline__ int fin_pad(int i) { return i + (i >> 5); }      // keeps stride-T (T = 16) accesses conflict-free
 constexpr int kFinSmem = kFinChunk + kFinChunk / 32 + 1;
@@ -684,10 +685,13 @@ __global__ void __launch_bounds__(256) finish_unpack_kernel(const FinSeg* __rest
         const float alpha = __ldg(s.inv_sigma);
         // <G, W~> = <G, W_orig> / sigma; from the activations it is alpha^-1 * sum dz.(y_pre - b) * alpha = that sum itself
         const float beta = s.dot_zw ? (float)(*s.dot_zw) : (float)dots[s.slot] * alpha;
+        const float coef = alpha * beta;                // dW = a_gp * gp - coef * u v^T
+        const bool nogp = (s.flip & kFinNoGp) != 0;     // correction-only instance (its gp is part of another instance's)
+        const float a_gp = (s.flip & kFinPrescaled) ? 1.f : alpha;
         for (int j = threadIdx.x; j < cnt; j += blockDim.x) {
           const int c = j % C, r = j / C, t = r % T, nl = r / T;
           const int col = c * T + t;                    // reference (Cout, Cin*kh*kw) matrix view: row = n, col = c*T + t
-          const float g = alpha * (gp[j] - beta * __ldg(s.u + n0 + nl) * __ldg(s.v + col));
+          const float g = (nogp ? 0.f : a_gp * gp[j]) - coef * __ldg(s.u + n0 + nl) * __ldg(s.v + col);
           sm[fin_pad(nl * row + col)] += g;
         }
       } else {
@@ -708,12 +712,12 @@ __global__ void __launch_bounds__(256) finish_unpack_kernel(const FinSeg* __rest
     long long si = ck.x;
     while (si >= 0) {
       const FinSeg& s = segs[si];
-      float g = s.gp[i];
+      float g = (s.flip & kFinNoGp) ? 0.f : s.gp[i];
       if (s.inv_sigma) {
         const float alpha = __ldg(s.inv_sigma);
         const float beta = s.dot_zw ? (float)(*s.dot_zw) : (float)dots[s.slot] * alpha;
         const size_t srow = ref / (size_t)s.sn_cols, col = ref - srow * (size_t)s.sn_cols;
-        g = alpha * (g - beta * __ldg(s.u + srow) * __ldg(s.v + col));
+        g = ((s.flip & kFinPrescaled) ? 1.f : alpha) * g - alpha * beta * __ldg(s.u + srow) * __ldg(s.v + col);
       }
       sum += g;
       si = s.next;
@@ -1016,8 +1020,9 @@ __global__ void __launch_bounds__(256) act_bwd_v4_kernel(const float4* __restric
 // exactly (y_pre = y > 0 ? y : y / slope); not available for ReLU (y = 0 loses y_pre).  zw and dbias pre-zeroed.
 __global__ void __launch_bounds__(256) act_bwd_sn_kernel(const float4* __restrict__ dy, const float4* __restrict__ y,
                                                          float4* __restrict__ dz, float* __restrict__ dbias,
-                                                         const float4* __restrict__ bias, double* __restrict__ zw, size_t total4,
-                                                         size_t group4, int N4, int act, float slope) {
+                                                         const float4* __restrict__ bias, double* __restrict__ zw,
+                                                         const float* __restrict__ dz_scale, size_t total4, size_t group4,
+                                                         int N4, int act, float slope) {
   mtd_pdl_prologue();
   extern __shared__ float colsum[];   // 4 * N4 floats when dbias != null
   __shared__ double red[32];
@@ -1041,10 +1046,16 @@ __global__ void __launch_bounds__(256) act_bwd_sn_kernel(const float4* __restric
       yp.x = t.x > 0.f ? t.x : t.x * inv_slope; yp.y = t.y > 0.f ? t.y : t.y * inv_slope;
       yp.z = t.z > 0.f ? t.z : t.z * inv_slope; yp.w = t.w > 0.f ? t.w : t.w * inv_slope;
     }
-    if (dz) dz[i] = g;
+    const int gi = (i >= group4) + (i >= 2 * group4) + (i >= 3 * group4);      // groups <= 4
+    if (dz) {
+      // dz_scale: write dz / sigma_g, so that dgrad needs no epilogue scale and ONE weight-gradient GEMM over the
+      // whole batch yields sum_g G_g / sigma_g; the bias gradient and zw use the unscaled dz
+      const float a = dz_scale ? __ldg(dz_scale + gi) : 1.f;
+      dz[i] = make_float4(g.x * a, g.y * a, g.z * a, g.w * a);
+    }
     priv.x += g.x; priv.y += g.y; priv.z += g.z; priv.w += g.w;
     const float d = g.x * (yp.x - b4.x) + g.y * (yp.y - b4.y) + g.z * (yp.z - b4.z) + g.w * (yp.w - b4.w);
-    part[(i >= group4) + (i >= 2 * group4) + (i >= 3 * group4)] += (double)d;      // groups <= 4
+    part[gi] += (double)d;
   }
   if (dbias) {
     if (first < total4) {
@@ -1058,9 +1069,9 @@ __global__ void __launch_bounds__(256) act_bwd_sn_kernel(const float4* __restric
     }
   }
   const int ngroups = (int)((total4 + group4 - 1) / group4);
-  for (int gi = 0; gi < ngroups && gi < 4; ++gi) {
-    const double r = block_sum(part[gi], red);
-    if (threadIdx.x == 0 && r != 0.0) atomicAdd(zw + gi, r);
+  for (int k = 0; k < ngroups && k < 4; ++k) {
+    const double r = block_sum(part[k], red);
+    if (threadIdx.x == 0 && r != 0.0) atomicAdd(zw + k, r);
   }
 }
 
@@ -1333,9 +1344,9 @@ int mtd_act_bwd(const float* dy, const float* y, float* dz, float* dbias, int db
 
 // mtd_act_bwd for a spectrally-normalised layer whose batch holds `groups` (<= 4) reference calls of M/groups rows:
 // also accumulates zw[g] += sum over group g of dz . (y_pre - bias) (see act_bwd_sn_kernel).  dbias (optional) and zw
-// must be all zero on entry.  act: MTD_ACT_NONE or MTD_ACT_LEAKY.  Requires N % 4 == 0 and a power-of-two N <= 8192.
-int mtd_act_bwd_sn(const float* dy, const float* y, float* dz, float* dbias, const float* bias, double* zw, int groups,
-                   long long M, int N, int act, float slope, void* stream) {
+// must be all zero on entry.  dz_scale (optional, `groups` floats = 1/sigma_g): the dz written is dz / sigma_g.  act: MTD_ACT_NONE or MTD_ACT_LEAKY.  Requires N % 4 == 0 and a power-of-two N <= 8192.
+int mtd_act_bwd_sn(const float* dy, const float* y, float* dz, float* dbias, const float* bias, double* zw,
+                   const float* dz_scale, int groups, long long M, int N, int act, float slope, void* stream) {
   MTD_REQUIRE(dy && y && zw && M > 0 && N > 0 && N % 4 == 0 && N <= 8192 && groups >= 1 && groups <= 4 && M % groups == 0);
   MTD_REQUIRE(act == MTD_ACT_NONE || act == MTD_ACT_LEAKY);
   MTD_REQUIRE(mtd_aligned16(dy) && mtd_aligned16(y) && (!dz || mtd_aligned16(dz)) && (!bias || mtd_aligned16(bias)));
@@ -1354,7 +1365,7 @@ int mtd_act_bwd_sn(const float* dy, const float* y, float* dz, float* dbias, con
   MTD_REQUIRE(((size_t)blocks * 256) % N4 == 0);
   mtd_launch(act_bwd_sn_kernel, blocks, 256, dbias ? N * sizeof(float) : 0, st, reinterpret_cast<const float4*>(dy),
              reinterpret_cast<const float4*>(y), reinterpret_cast<float4*>(dz), dbias, reinterpret_cast<const float4*>(bias), zw,
-             total4, total4 / groups, N4, act, slope);
+             dz_scale, total4, total4 / groups, N4, act, slope);
   MTD_CHECK_LAUNCH();
   return MTD_OK;
 }

@@ -176,14 +176,15 @@ def _flush_finish(groups):
         base = len(rows)
         heads.append(base)
         head_numels.append(dw.numel())
-        for k, (gp, w, u, v, inv, cfg, zwp) in enumerate(insts):
+        for k, (gp, w, u, v, inv, cfg, zwp, flags) in enumerate(insts):
             T = cfg.kh * cfg.kw
             sN, sC, flip = (T, cfg.cout * T, 1) if cfg.transposed else (cfg.cin * T, T, 0)
             sn = inv is not None
-            rows.append([gp.data_ptr(), dw.data_ptr(), w.data_ptr() if sn else 0, u.data_ptr() if sn else 0,
-                         v.data_ptr() if sn else 0, inv.data_ptr() if sn else 0, cfg.cout, T, cfg.cin, sN, sC, flip,
+            rows.append([gp.data_ptr() if gp is not None else 0, dw.data_ptr(), w.data_ptr() if sn else 0,
+                         u.data_ptr() if sn else 0, v.data_ptr() if sn else 0, inv.data_ptr() if sn else 0, cfg.cout, T, cfg.cin,
+                         sN, sC, flip | flags,
                          cfg.cin * T, base + k, base + k + 1 if k + 1 < len(insts) else -1, zwp])
-            dot_numels.append(gp.numel() if (sn and not zwp) else 0)
+            dot_numels.append(gp.numel() if (sn and not zwp and gp is not None) else 0)
             rowdims.append((T, cfg.cin))
     key = (tuple(dot_numels), tuple(heads), tuple(rowdims), str(dev))
     ent = _fin_chunk_cache.get(key)
@@ -399,9 +400,11 @@ class ConvFn(Function):
         if zw is not None:
             if dbias is not None and not dbz:
                 dbias.zero_()
-            dz = _empty(dy.shape, dy) if cfg.pre_act != ACT_NONE else g1
-            call("mtd_act_bwd_sn", fptr(g1), fptr(y), fptr(dz) if cfg.pre_act != ACT_NONE else None, fptr(dbias), fptr(bias),
-                 zw.data_ptr(), G, M, cfg.cout, cfg.pre_act, cfg.slope, st)
+            # dz is written pre-scaled by 1/sigma of its call: dgrad then needs no scale, and ONE weight-gradient GEMM over
+            # the whole batch yields sum_g G_g / sigma_g (the per-call corrections are separate rank-1 terms)
+            dz = _empty(dy.shape, dy)
+            call("mtd_act_bwd_sn", fptr(g1), fptr(y), fptr(dz), fptr(dbias), fptr(bias), zw.data_ptr(), fptr(inv_sigma), G, M,
+                 cfg.cout, cfg.pre_act, cfg.slope, st)
         elif cfg.pre_act != ACT_NONE:
             pre_out = aux if aux is not None else y
             dz = _empty(dy.shape, dy)
@@ -412,28 +415,36 @@ class ConvFn(Function):
                 call("mtd_act_bwd", fptr(g1), None, None, fptr(dbias), dbz, M, cfg.cout, ACT_NONE, cfg.slope, st)
         # 2) data gradients
         dx1 = dx2 = None
+        dscale = None if zw is not None else inv_sigma       # zw path: dz already carries 1/sigma
         if need[0]:
             dx1 = _empty((B, H, W, C1), dy)
             fuse = g1 if cfg.fuse_add1_is_input else None
-            _conv_dgrad_launch(dz, weight, dx1, inv_sigma, fuse, B, H, W, C1, 0, cfg)
+            _conv_dgrad_launch(dz, weight, dx1, dscale, fuse, B, H, W, C1, 0, cfg)
         if C2 and need[1]:
             dx2 = _empty((B, H, W, C2), dy)
-            _conv_dgrad_launch(dz, weight, dx2, inv_sigma, None, B, H, W, C2, C1, cfg)
+            _conv_dgrad_launch(dz, weight, dx2, dscale, None, B, H, W, C2, C1, cfg)
         # 3) weight gradient (packed), then to reference layout (+ spectral-norm correction)
         dw = None
         if want_w:
             Bg = B // G
-            insts = []
-            for g in range(G):              # one packed weight gradient per batched reference call (own u, v, sigma)
+            insts = []          # (gp, w, u, v, 1/sigma, cfg, pointer to <G,W~> or 0, flag bits: 2 gp pre-scaled, 4 no gp)
+            if zw is not None:
                 gp = _empty((weight.numel(),), dy)
-                if G == 1:
-                    _conv_wgrad_launch(x1, x2, dz, gp, B, H, W, C1, C2, cfg)
-                    insts.append((gp, weight.detach(), None if u is None else u.reshape(-1), None if v is None else v.reshape(-1),
-                                  inv_sigma, cfg, 0 if zw is None else zw.data_ptr()))
-                else:
-                    sl = slice(g * Bg, (g + 1) * Bg)
-                    _conv_wgrad_launch(x1[sl], None if x2 is None else x2[sl], dz[sl], gp, Bg, H, W, C1, C2, cfg)
-                    insts.append((gp, weight.detach(), u[g], v[g], inv_sigma[g:g + 1], cfg, 0 if zw is None else zw.data_ptr() + 8 * g))
+                _conv_wgrad_launch(x1, x2, dz, gp, B, H, W, C1, C2, cfg)          # sum_g G_g / sigma_g in one GEMM
+                for g in range(G):
+                    insts.append((gp if g == 0 else None, weight.detach(), u[g] if u.dim() == 2 else u, v[g] if v.dim() == 2 else v,
+                                  inv_sigma[g:g + 1], cfg, zw.data_ptr() + 8 * g, 2 if g == 0 else 4))
+            else:
+                for g in range(G):          # one packed weight gradient per batched reference call (own u, v, sigma)
+                    gp = _empty((weight.numel(),), dy)
+                    if G == 1:
+                        _conv_wgrad_launch(x1, x2, dz, gp, B, H, W, C1, C2, cfg)
+                        insts.append((gp, weight.detach(), None if u is None else u.reshape(-1),
+                                      None if v is None else v.reshape(-1), inv_sigma, cfg, 0, 0))
+                    else:
+                        sl = slice(g * Bg, (g + 1) * Bg)
+                        _conv_wgrad_launch(x1[sl], None if x2 is None else x2[sl], dz[sl], gp, Bg, H, W, C1, C2, cfg)
+                        insts.append((gp, weight.detach(), u[g], v[g], inv_sigma[g:g + 1], cfg, 0, 0))
             if _finish_queue is not None:
                 grp = _finish_queue.get(weight.data_ptr())
                 if grp is None:
@@ -442,7 +453,7 @@ class ConvFn(Function):
                 else:
                     grp[1].extend(insts)           # summed into the first instance's dw by the batched unpack
             else:
-                for k, (gp, wd, ug, vg, inv_g, _, _zw) in enumerate(insts):
+                for k, (gp, wd, ug, vg, inv_g, _, _zw, _fl) in enumerate(insts):
                     part = torch.empty_like(weight)
                     scratch = torch.empty(4, dtype=torch.float32, device=dy.device) if inv_g is not None else None
                     call("mtd_conv_wgrad_finish", fptr(gp), fptr(part), cfg.transposed, cfg.cout, cfg.cin, cfg.kh, cfg.kw,

@@ -439,9 +439,19 @@ def test_act_bwd_sn_matches_reference(M, N, groups, act):
     dz = torch.empty_like(dyc)
     db = torch.zeros(N, device=DEV)
     zw = torch.zeros(groups, dtype=torch.float64, device=DEV)
-    call("mtd_act_bwd_sn", fptr(dyc), fptr(yc), fptr(dz), fptr(db), fptr(bc), zw.data_ptr(), groups, M, N, act, 0.2, stream())
+    call("mtd_act_bwd_sn", fptr(dyc), fptr(yc), fptr(dz), fptr(db), fptr(bc), zw.data_ptr(), None, groups, M, N, act, 0.2, stream())
     torch.cuda.synchronize()
     assert rel_err(dz, dz_ref) <= 1e-6
+    # pre-scaled dz (1/sigma per batched call); bias gradient and coefficients stay unscaled
+    sc = torch.tensor([0.5 + 0.25 * g_ for g_ in range(groups)], device=DEV)
+    dz2, db2 = torch.empty_like(dyc), torch.zeros(N, device=DEV)
+    zw2 = torch.zeros(groups, dtype=torch.float64, device=DEV)
+    call("mtd_act_bwd_sn", fptr(dyc), fptr(yc), fptr(dz2), fptr(db2), fptr(bc), zw2.data_ptr(), fptr(sc), groups, M, N, act, 0.2,
+         stream())
+    torch.cuda.synchronize()
+    want = (dz_ref.reshape(groups, -1) * sc.double().cpu().reshape(groups, 1)).reshape(M, N)
+    assert rel_err(dz2, want) <= 1e-6 and rel_err(db2, dz_ref.sum(0)) <= 1e-5
+    assert float((zw2.cpu() - zw_ref).abs().max()) <= 2e-6 * float((dz_ref * (ypre - bias)).abs().reshape(groups, -1).sum(1).max())
     assert rel_err(db, dz_ref.sum(0)) <= 1e-5
     scale = float((dz_ref * (ypre - bias)).abs().reshape(groups, -1).sum(1).max())      # cancellation-free magnitude
     assert float((zw.cpu() - zw_ref).abs().max()) <= 2e-6 * scale
