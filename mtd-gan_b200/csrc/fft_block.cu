@@ -43,12 +43,14 @@ __device__ __forceinline__ void fill_twiddles(float2* tw, int N) {
 template <bool INV>
 __device__ __forceinline__ void fft_dif(float2* Z, const float2* tw, int N, int Q) {
   const int nb = (N >> 1) * Q;
+  const int lq = __ffs(Q) - 1;                     // N, Q, half are powers of two: shifts instead of integer division
   for (int half = N >> 1; half >= 1; half >>= 1) {
-    const int tstep = N / (2 * half);
+    const int lh = __ffs(half) - 1;
+    const int tstep = N >> (lh + 1);
     for (int idx = threadIdx.x; idx < nb; idx += blockDim.x) {
-      int q = idx % Q, j = idx / Q;
-      int pos = j & (half - 1), grp = j / half;
-      int i0 = (grp * 2 * half + pos) * Q + q, i1 = i0 + half * Q;
+      int q = idx & (Q - 1), j = idx >> lq;
+      int pos = j & (half - 1), grp = j >> lh;
+      int i0 = (((grp << (lh + 1)) + pos) << lq) + q, i1 = i0 + (half << lq);
       float2 a = Z[i0], b = Z[i1];
       float2 d = csub(a, b), w = tw[pos * tstep];
       Z[i0] = cadd(a, b);
@@ -62,12 +64,14 @@ __device__ __forceinline__ void fft_dif(float2* Z, const float2* tw, int N, int 
 template <bool INV>
 __device__ __forceinline__ void fft_dit(float2* Z, const float2* tw, int N, int Q) {
   const int nb = (N >> 1) * Q;
+  const int lq = __ffs(Q) - 1;
   for (int half = 1; half < N; half <<= 1) {
-    const int tstep = N / (2 * half);
+    const int lh = __ffs(half) - 1;
+    const int tstep = N >> (lh + 1);
     for (int idx = threadIdx.x; idx < nb; idx += blockDim.x) {
-      int q = idx % Q, j = idx / Q;
-      int pos = j & (half - 1), grp = j / half;
-      int i0 = (grp * 2 * half + pos) * Q + q, i1 = i0 + half * Q;
+      int q = idx & (Q - 1), j = idx >> lq;
+      int pos = j & (half - 1), grp = j >> lh;
+      int i0 = (((grp << (lh + 1)) + pos) << lq) + q, i1 = i0 + (half << lq);
       float2 w = tw[pos * tstep];
       float2 a = Z[i0], b = INV ? cmulc(Z[i1], w) : cmul(Z[i1], w);
       Z[i0] = cadd(a, b);
@@ -430,7 +434,7 @@ long long mtd_fft_bwd_part_elems(int B, int W) { return (long long)B * (W / 2 + 
 
 int mtd_fft_rows_fwd(const float* x, float* spec, int B, int H, int W, int C, void* stream) {
   int lw = ilog2_exact(W);
-  MTD_REQUIRE(x && spec && B > 0 && H > 0 && lw >= 3 && W <= 1024 && C > 0 && C % 4 == 0);
+  MTD_REQUIRE(x && spec && B > 0 && H > 0 && lw >= 3 && W <= 1024 && C >= 4 && (C & (C - 1)) == 0);    // C: power of two
   MTD_REQUIRE(mtd_aligned16(x) && mtd_aligned16(spec));
   size_t smem = (size_t)W * C * 4 + (size_t)(W / 2) * 8;
   int rc = set_smem(fft_rows_fwd_kernel, smem);
@@ -443,7 +447,7 @@ int mtd_fft_rows_fwd(const float* x, float* spec, int B, int H, int W, int C, vo
 int mtd_fft_rows_inv(const float* spec, const float* add1, const float* add2, float* out, int B, int H, int W, int C,
                      void* stream) {
   int lw = ilog2_exact(W);
-  MTD_REQUIRE(spec && out && B > 0 && H > 0 && lw >= 3 && W <= 1024 && C > 0 && C % 4 == 0);
+  MTD_REQUIRE(spec && out && B > 0 && H > 0 && lw >= 3 && W <= 1024 && C >= 4 && (C & (C - 1)) == 0);
   MTD_REQUIRE(mtd_aligned16(spec) && mtd_aligned16(out) && mtd_aligned16(add1) && mtd_aligned16(add2));
   size_t smem = (size_t)W * C * 4 + (size_t)(W / 2) * 8;
   int rc = set_smem(fft_rows_inv_kernel, smem);
