@@ -293,7 +293,12 @@ def run_own(args):
         ach = conv_flop / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
         roof = {"kernel": "implicit-GEMM conv family (fwd + dgrad + wgrad)", "bound": "tensor", "achieved": round(ach, 3),
                 "peak": pk["tflops_sustained"], "unit": "TFLOP/s", "frac": round(ach / pk["tflops_sustained"], 5),
-                "traffic": None, "peak_source": pk["source"] + ", sustained bf16 dense (kernel timed inside a long step)",
+                # DRAM bytes of ONE representative launch of the dominant kernel from an `ncu --set full` capture
+                # (profiles/r01_ncu_full_conv_tc_v1_v3.txt): conv_tc_kernel<128,3>, B=20 32x32 256->128 3x3 --
+                # 23.37 MB read + 2.6 KB written vs 23.3 MB compulsory (input + hi|lo weights; the output stays in L2)
+                "traffic": 23375104, "traffic_source": "ncu dram__bytes_read+write of one conv_tc_kernel<128,3> launch "
+                "(B=20 32x32 256->128 3x3; algorithmic input+weight bytes 23.3 MB, output L2-resident), not the family average",
+                "peak_source": pk["source"] + ", sustained bf16 dense (kernel timed inside a long step)",
                 # fp32-grade results need 3 TF32 MMAs per product and TF32 runs at half the bf16 rate: the same peak
                 # expressed in useful fp32-equivalent FLOP/s is peak / 6
                 "peak_3xtf32_equiv": round(pk["tflops_sustained"] / 6, 1), "frac_of_3xtf32_peak": round(ach / (pk["tflops_sustained"] / 6), 4),

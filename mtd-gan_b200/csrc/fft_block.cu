@@ -101,8 +101,9 @@ __global__ void __launch_bounds__(256) fft_rows_fwd_kernel(const float* __restri
   __syncthreads();
   fft_dif<false>(Z, tw, W, Q);
   const float sc = rsqrtf((float)W) * 0.5f;
+  const int lq = __ffs(Q) - 1;                      // Q is a power of two (checked by the entry point)
   for (int idx = threadIdx.x; idx < Wh * Q; idx += blockDim.x) {
-    int q = idx % Q, k = idx / Q;
+    int q = idx & (Q - 1), k = idx >> lq;
     float2 zk = Z[bitrev(k, logW) * Q + q];
     float2 zm = Z[bitrev((W - k) & (W - 1), logW) * Q + q];
     zm.y = -zm.y;
@@ -126,8 +127,9 @@ __global__ void __launch_bounds__(256) fft_rows_inv_kernel(const float2* __restr
   float2* tw = Z + (size_t)W * Q;
   const int bh = blockIdx.x, b = bh / H, h = bh - b * H;
   fill_twiddles(tw, W);
+  const int lq = __ffs(Q) - 1;
   for (int idx = threadIdx.x; idx < Wh * Q; idx += blockDim.x) {
-    int q = idx % Q, k = idx / Q;
+    int q = idx & (Q - 1), k = idx >> lq;
     size_t src = (((size_t)b * Wh + k) * H + h) * C + 2 * q;
     float4 v = __ldg(reinterpret_cast<const float4*>(spec + src));   // A = (v.x, v.y), B = (v.z, v.w)
     if (k == 0 || k == (W >> 1)) {
@@ -144,7 +146,7 @@ __global__ void __launch_bounds__(256) fft_rows_inv_kernel(const float2* __restr
   const float4* Z4 = reinterpret_cast<const float4*>(Z);
   const int C4 = C >> 2;
   for (int i = threadIdx.x; i < W * C4; i += blockDim.x) {
-    int n = i / C4, j = i - n * C4;
+    int n = i >> (lq - 1), j = i & (C4 - 1);         // C4 = Q / 2
     float4 v = Z4[bitrev(n, logW) * C4 + j];
     v.x *= sc; v.y *= sc; v.z *= sc; v.w *= sc;
     size_t o = base + (size_t)i * 4;
