@@ -128,11 +128,14 @@ int mtd_conv_fwd_tc(const float* x1, const float* x2, const float* wp, const flo
                     void* stream);
 /* dgrad on the tensor cores (stride 1, or stride 2 with 4x4/pad 1); same contract as mtd_conv_dgrad.
  * passes = 1: wpd tf32-rounded (mtd_round_tf32); passes = 3: wpd = [hi | lo] halves of the full dgrad pack
- * (mtd_split_tf32); for stride 1 wpd may point at a row slice of the hi half of [cin_total][T][Cout].  */
+ * (mtd_split_tf32); for stride 1 wpd may point at a row slice of the hi half of [cin_total][T][Cout].
+ * dx2 / c_split (stride 1, optional): the layer's input was torch.cat of two tensors -- input channels [0, c_split)
+ * are written to dx (B,H,W,c_split) and the rest to dx2 (B,H,W,Cin-c_split) by ONE launch (dz is streamed once).  */
 int mtd_conv_dgrad_tc(const float* dz, const float* wpd, float* dx, const float* scale, int scale_group, const float* add1,
                       const float* add2,
                       const float* mask_src, int mask_act, float slope, int B, int H, int W, int Cin, int Cout, int kh, int kw,
-                      int stride, int pad, int passes, int cin_total, float* ws, long long ws_floats, void* stream);
+                      int stride, int pad, int passes, int cin_total, float* dx2, int c_split, float* ws, long long ws_floats,
+                      void* stream);
 /* weight gradient on the tensor cores (stride-1 same convs, C % 32 == 0, N % 32 == 0): both operands are
  * MN-major TMA boxes, split-K over pixels, fp32 atomics into gp (zeroed here).  Same gp layout as
  * mtd_conv_wgrad.                                                                                    */

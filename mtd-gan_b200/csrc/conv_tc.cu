@@ -54,6 +54,8 @@ struct TcArgs {
   int m_tiles, n_groups, ra, rb; // v2 kernel: pixel tiles, groups of MT pixel tiles, raw-A / B ring depths
   int outH, outW, omy, omx, ooy, oox;   // output pixel = (h*omy+ooy, w*omx+oox) in a (B,outH,outW,N) tensor
   float* out;
+  float* out2;                  // split output (dgrad of a torch.cat layer): channels [n_split, N) go to out2, n_split | BN tiles
+  int n_split;                  // 0 = single output
   const float* scale;           // 1/sigma: one scalar, or (scale_group > 0) one per group of scale_group samples
   int scale_group;
   const float* bias;
@@ -162,7 +164,8 @@ __device__ __forceinline__ float tc_row_scale(const TcArgs& a, int b) {
 
 // scale / bias / pre-activation / aux copy / residual adds / post-activation / gradient mask of 4 consecutive
 // output channels, then the store (the one epilogue of every forward / dgrad path)
-__device__ __forceinline__ void tc_store4(const TcArgs& a, size_t idx, int n, float scale, float x0, float x1, float x2, float x3) {
+__device__ __forceinline__ void tc_store4(const TcArgs& a, float* out, size_t idx, int n, float scale, float x0, float x1, float x2,
+                                          float x3) {
   float o[4] = {x0 * scale, x1 * scale, x2 * scale, x3 * scale};
   if (a.bias) {
     const float4 b = __ldg(reinterpret_cast<const float4*>(a.bias + n));
@@ -180,7 +183,14 @@ __device__ __forceinline__ void tc_store4(const TcArgs& a, size_t idx, int n, fl
     o[0] *= mtd_act_grad(t.x, a.mask_act, a.slope); o[1] *= mtd_act_grad(t.y, a.mask_act, a.slope);
     o[2] *= mtd_act_grad(t.z, a.mask_act, a.slope); o[3] *= mtd_act_grad(t.w, a.mask_act, a.slope);
   }
-  *reinterpret_cast<float4*>(a.out + idx) = make_float4(o[0], o[1], o[2], o[3]);
+  *reinterpret_cast<float4*>(out + idx) = make_float4(o[0], o[1], o[2], o[3]);
+}
+
+// output tensor, row stride and first column of the tile starting at channel n0 (split outputs: see TcArgs::out2)
+__device__ __forceinline__ float* tc_out_of(const TcArgs& a, int n0, int& ncols, int& nloc) {
+  if (a.n_split > 0 && n0 >= a.n_split) { ncols = a.N - a.n_split; nloc = n0 - a.n_split; return a.out2; }
+  ncols = a.n_split > 0 ? a.n_split : a.N; nloc = n0;
+  return a.out;
 }
 
 // ---- work decomposition of the v1 kernel: data-parallel waves + one stream-K wave ---------------------------
@@ -401,8 +411,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
       const int b = b0 + bl;
       const bool valid = b < a.B;
       const float scale = valid ? tc_row_scale(a, b) : 1.f;
+      int ncols, nloc;
+      float* outp = tc_out_of(a, n0, ncols, nloc);
       const size_t rowoff =
-          (((size_t)b * a.outH + ((h0 + hl) * a.omy + a.ooy)) * a.outW + ((w0 + wl) * a.omx + a.oox)) * a.N + n0;
+          (((size_t)b * a.outH + ((h0 + hl) * a.omy + a.ooy)) * a.outW + ((w0 + wl) * a.omx + a.oox)) * ncols + nloc;
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
         uint32_t v[32];
@@ -417,7 +429,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
         } else if (valid) {
 #pragma unroll
           for (int j = 0; j < 32; j += 4)
-            tc_store4(a, rowoff + c0 + j, n0 + c0 + j, scale, __uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+            tc_store4(a, outp, rowoff + c0 + j, n0 + c0 + j, scale, __uint_as_float(v[j]), __uint_as_float(v[j + 1]),
                       __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
         }
       }
@@ -788,9 +800,11 @@ __global__ void __launch_bounds__(256) tc_sk_finish_kernel(const __grid_constant
       const float4 t = __ldcg(reinterpret_cast<const float4*>(wsp + (size_t)p * kBM * BN));
       sum.x += t.x; sum.y += t.y; sum.z += t.z; sum.w += t.w;
     }
+    int ncols, nloc;
+    float* outp = tc_out_of(a, nt * BN, ncols, nloc);
     const size_t rowoff = (((size_t)b * a.outH + ((mh * a.TH + hl) * a.omy + a.ooy)) * a.outW +
-                           ((mw * a.TW + wl) * a.omx + a.oox)) * a.N + nt * BN;
-    tc_store4(a, rowoff + c, nt * BN + c, tc_row_scale(a, b), sum.x, sum.y, sum.z, sum.w);
+                           ((mw * a.TW + wl) * a.omx + a.oox)) * ncols + nloc;
+    tc_store4(a, outp, rowoff + c, nt * BN + c, tc_row_scale(a, b), sum.x, sum.y, sum.z, sum.w);
   }
 }
 
@@ -929,13 +943,14 @@ int g_tune_bn = 0, g_tune_per = 0;      // tools/tune_tc.py overrides: Cout tile
 
 struct Schedule { int bn, n_dp, sk_tiles, sk_per, sk_P, grid; double cost; };
 
-Schedule choose_schedule(int m_tiles, int N, int K, int passes, long long ws_floats) {
+Schedule choose_schedule(int m_tiles, int N, int K, int passes, long long ws_floats, int n_align = 0) {
   const int sms = mtd_sm_count();
   Schedule best{};
   best.cost = 1e30;
   for (int bn = 128; bn >= 32; bn >>= 1) {
     if (N % bn) continue;
-    if (g_tune_bn > 0 && bn != g_tune_bn && N % g_tune_bn == 0) continue;
+    if (n_align > 0 && n_align % bn) continue;        // split outputs: no tile may straddle the split
+    if (g_tune_bn > 0 && bn != g_tune_bn && N % g_tune_bn == 0 && !(n_align > 0 && n_align % g_tune_bn)) continue;
     const double ts = (bn == 128 ? 0.78 : bn == 64 ? 0.57 : 0.52) * (passes == 3 ? 1.0 : 0.7);
     const double F0 = 6.0, Ft = 2.2;
     const int mn = m_tiles * (N / bn);
@@ -1033,7 +1048,7 @@ int launch_tc_v1(const float* x1, const float* x2, const float* wp, int passes, 
   const int m_tiles = a.n_wt * a.n_ht * a.n_bt;
   const int kiters = a.T * (a.kc1 + a.kc2);
   if (a.ws && !mtd_aligned16(a.ws)) return MTD_EALIGN;
-  const Schedule sc = choose_schedule(m_tiles, a.N, kiters, passes, a.ws ? a.ws_floats : 0);
+  const Schedule sc = choose_schedule(m_tiles, a.N, kiters, passes, a.ws ? a.ws_floats : 0, a.n_split);
   if (sc.cost >= 1e30) return MTD_EINVAL;
   const int BN = sc.bn;
   a.n_nt = a.N / BN;
@@ -1517,14 +1532,20 @@ int mtd_conv_fwd_tc(const float* x1, const float* x2, const float* wp, const flo
 int mtd_conv_dgrad_tc(const float* dz, const float* wpd, float* dx, const float* scale, int scale_group, const float* add1,
                       const float* add2,
                       const float* mask_src, int mask_act, float slope, int B, int H, int W, int Cin, int Cout, int kh, int kw,
-                      int stride, int pad, int passes, int cin_total, float* ws, long long ws_floats, void* stream) {
+                      int stride, int pad, int passes, int cin_total, float* dx2, int c_split, float* ws, long long ws_floats,
+                      void* stream) {
   MTD_REQUIRE(dz && wpd && dx);
+  if (dx2) {      // two outputs: dx gets input channels [0, c_split), dx2 the rest (the two sources of a torch.cat layer)
+    MTD_REQUIRE(g_tc_version == 1 && stride == 1 && c_split > 0 && c_split < Cin && c_split % 32 == 0 && (Cin - c_split) % 32 == 0 &&
+                cin_total == Cin && !add1 && !add2 && !mask_src && mtd_aligned16(dx2));
+  }
   cudaStream_t st = (cudaStream_t)stream;
   int tw, th, tb;
   TcArgs a{};
   a.ws = ws; a.ws_floats = ws ? ws_floats : 0;
   a.B = B; a.C1 = Cout; a.C2 = 0; a.N = Cin;
-  a.out = dx; a.scale = scale; a.scale_group = (scale && scale_group > 0 && scale_group < B) ? scale_group : 0;
+  a.out = dx; a.out2 = dx2; a.n_split = dx2 ? c_split : 0;
+  a.scale = scale; a.scale_group = (scale && scale_group > 0 && scale_group < B) ? scale_group : 0;
   a.bias = nullptr; a.pre_act = 0; a.add1 = add1; a.add2 = add2; a.post_act = 0;
   a.mask_src = mask_src; a.mask_act = mask_act; a.slope = slope; a.aux = nullptr;
   a.outH = H; a.outW = W;

@@ -224,9 +224,19 @@ _TC_PASSES = 1 if os.environ.get("MTDGAN_TF32", "x3") == "x1" else 3
 _WGRAD_PASSES = 3 if os.environ.get("MTDGAN_WGRAD_TF32", "x1") == "x3" else 1
 
 
+_TC_VERSION = 1
+
+
 def set_tc_version(version: int) -> int:
     """Forward/dgrad tensor-core kernel generation (1: A through shared memory, 2: A through TMEM, multi-tile)."""
-    return _ext.load().mtd_tc_set_version(int(version))
+    global _TC_VERSION
+    prev = _ext.load().mtd_tc_set_version(int(version))
+    _TC_VERSION = int(version)
+    return prev
+
+
+def _tc_version() -> int:
+    return _TC_VERSION
 
 
 def set_wgrad_passes(passes: int):
@@ -334,12 +344,27 @@ def _conv_dgrad_launch(dz, weight, dx, scale, add1, B, H, W, cin_sub, cin_off, c
         call("mtd_conv_dgrad_tc", fptr(dz), wpd.data_ptr() + 4 * cin_off * T * cfg.cout, fptr(dx), fptr(scale),
              _scale_group(scale, B), fptr(add1), None,
              None, 0, cfg.slope, B, H, W, cin_sub, cfg.cout, cfg.kh, cfg.kw, cfg.stride, cfg.pad, _TC_PASSES, cfg.cin,
-             fptr(ws), ws.numel(), st)
+             None, 0, fptr(ws), ws.numel(), st)
     else:
         wpd = _packed(weight, "dgrad", cfg)
         call("mtd_conv_dgrad", fptr(dz), wpd.data_ptr() + 4 * cin_off * T * cfg.cout, fptr(dx), fptr(scale),
              _scale_group(scale, B), fptr(add1), None,
              None, 0, cfg.slope, B, H, W, cin_sub, cfg.cout, cfg.kh, cfg.kw, cfg.stride, cfg.pad, st)
+
+
+def _conv_dgrad_launch_cat(dz, weight, dx1, dx2, scale, B, H, W, C1, C2, cfg: ConvCfg) -> bool:
+    """Both halves of a torch.cat layer's data gradient from ONE tensor-core launch (dz streamed once).  Returns False
+    when the shape is not eligible (the caller then issues one launch per source)."""
+    if (cfg.stride != 1 or C1 % 32 or C2 % 32 or _tc_version() != 1
+            or not _tc_ok(B, H, W, cfg.cout, 0, C1 + C2, cfg.kh, cfg.kw, 1, cfg.pad)):
+        return False
+    global tc_launches
+    tc_launches += 1
+    wpd = _packed(weight, _tc_kind("dgrad"), cfg)
+    ws = _tc_workspace(dx1.device)
+    call("mtd_conv_dgrad_tc", fptr(dz), fptr(wpd), fptr(dx1), fptr(scale), _scale_group(scale, B), None, None, None, 0, cfg.slope,
+         B, H, W, C1 + C2, cfg.cout, cfg.kh, cfg.kw, 1, cfg.pad, _TC_PASSES, cfg.cin, fptr(dx2), C1, fptr(ws), ws.numel(), stream())
+    return True
 
 
 class ConvFn(Function):
@@ -416,11 +441,15 @@ class ConvFn(Function):
         # 2) data gradients
         dx1 = dx2 = None
         dscale = None if zw is not None else inv_sigma       # zw path: dz already carries 1/sigma
-        if need[0]:
+        both = False
+        if C2 and need[0] and need[1] and not cfg.fuse_add1_is_input:
+            dx1, dx2 = _empty((B, H, W, C1), dy), _empty((B, H, W, C2), dy)
+            both = _conv_dgrad_launch_cat(dz, weight, dx1, dx2, dscale, B, H, W, C1, C2, cfg)
+        if need[0] and not both:
             dx1 = _empty((B, H, W, C1), dy)
             fuse = g1 if cfg.fuse_add1_is_input else None
             _conv_dgrad_launch(dz, weight, dx1, dscale, fuse, B, H, W, C1, 0, cfg)
-        if C2 and need[1]:
+        if C2 and need[1] and not both:
             dx2 = _empty((B, H, W, C2), dy)
             _conv_dgrad_launch(dz, weight, dx2, dscale, None, B, H, W, C2, C1, cfg)
         # 3) weight gradient (packed), then to reference layout (+ spectral-norm correction)

@@ -190,7 +190,8 @@ def test_conv_tcgen05_forward_backward(case, passes, tol, tc_version):
         y = ops.conv(x1, wc, bc, cfg, x2=x2, add1=sc)
         y.backward(nhwc(gout.float()).to(DEV))
         torch.cuda.synchronize()
-        assert ops.tc_launches - n0 == (4 if C2 else 3), "tcgen05 kernels (fwd, dgrad, wgrad) were not all selected"
+        # a torch.cat layer's two data gradients come from one launch on the v1 kernel, from two on v2
+        assert ops.tc_launches - n0 == (4 if (C2 and tc_version == 2) else 3), "tcgen05 kernels (fwd, dgrad, wgrad) were not all selected"
     finally:
         ops.set_conv_mode("auto", 3)
         ops.set_wgrad_passes(1)
