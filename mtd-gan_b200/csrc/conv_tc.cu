@@ -71,6 +71,9 @@ struct TcArgs {
   // CTAs; the k-steps of tiles [n_dp, n_dp + sk_tiles) form one flat range cut into equal pieces of sk_per steps,
   // piece c going to CTA c, partial sums to ws[slot][128][BN] with slot = sk_tile * sk_P + (c - first CTA of the tile)
   int n_dp, sk_tiles, sk_per, sk_P;
+  // stride-2 dgrad as ONE launch: n_cls = 4 output-parity classes; tile = cls * tiles_per_cls + (m, n) tile; class cls
+  // uses taps dy/dx[cls*T ..], weight rows [cls*N, (cls+1)*N) of the stacked pack and output offset (cls >> 1, cls & 1)
+  int n_cls, tiles_per_cls;
   float* ws;
   long long ws_floats;          // host side only: capacity of ws
   int grid;                     // host side only: CTAs to launch
@@ -291,7 +294,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
   // barriers initialised, TMEM allocated, descriptors prefetched: all of it overlapped the previous kernel's tail
   mtd_pdl_prologue();
 
-  auto decode_tile = [&](int tile, int& b0, int& h0, int& w0, int& n0) {
+  auto decode_tile = [&](int tile, int& b0, int& h0, int& w0, int& n0, int& cls) {
+    cls = 0;
+    if (a.n_cls > 1) { cls = tile / a.tiles_per_cls; tile -= cls * a.tiles_per_cls; }
     int nt = tile % a.n_nt, m = tile / a.n_nt;
     int mw = m % a.n_wt;
     m /= a.n_wt;
@@ -306,17 +311,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
       WorkIter wi(a, kiters);
       Work wk;
       while (wi.next(a, kiters, wk)) {
-        int b0, h0, w0, n0;
-        decode_tile(wk.tile, b0, h0, w0, n0);
+        int b0, h0, w0, n0, cls;
+        decode_tile(wk.tile, b0, h0, w0, n0, cls);
+        const int nblk = (n0 >> 5) + cls * (a.N >> 5);            // weight rows of this class in the stacked pack
         for (int it = wk.kb; it < wk.ke; ++it) {
           mbar_wait(empty_bar(st.stage), st.phase ^ 1u);
           mbar_expect_tx(full_bar(st.stage), kTxBytes);
-          const int t = it / kchunks, cc = it - t * kchunks;
+          const int t = it / kchunks, cc = it - t * kchunks, tt = cls * a.T + t;
           const uint32_t sa = base + (uint32_t)st.stage * kStageBytes, sb = sa + kOffB;
-          if (cc < a.kc1) tma_load_4d(&mapA1, sa, full_bar(st.stage), cc * 32, w0 * a.es + a.dx[t], h0 * a.es + a.dy[t], b0);
-          else tma_load_4d(&mapA2, sa, full_bar(st.stage), (cc - a.kc1) * 32, w0 * a.es + a.dx[t], h0 * a.es + a.dy[t], b0);
-          tma_load_4d(&mapB, sb, full_bar(st.stage), 0, 0, it, n0 >> 5);          // k-step `it` == (t*Ctot + cc*32)/32
-          if (NPASS == 3) tma_load_4d(&mapBlo, sa + kOffBlo, full_bar(st.stage), 0, 0, it, n0 >> 5);
+          if (cc < a.kc1) tma_load_4d(&mapA1, sa, full_bar(st.stage), cc * 32, w0 * a.es + a.dx[tt], h0 * a.es + a.dy[tt], b0);
+          else tma_load_4d(&mapA2, sa, full_bar(st.stage), (cc - a.kc1) * 32, w0 * a.es + a.dx[tt], h0 * a.es + a.dy[tt], b0);
+          tma_load_4d(&mapB, sb, full_bar(st.stage), 0, 0, it, nblk);             // k-step `it` == (t*Ctot + cc*32)/32
+          if (NPASS == 3) tma_load_4d(&mapBlo, sa + kOffBlo, full_bar(st.stage), 0, 0, it, nblk);
           st.advance(S);
         }
       }
@@ -402,8 +408,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
     WorkIter wi(a, kiters);
     Work wk;
     for (int lt = 0; wi.next(a, kiters, wk); ++lt) {
-      int b0, h0, w0, n0;
-      decode_tile(wk.tile, b0, h0, w0, n0);
+      int b0, h0, w0, n0, cls;
+      decode_tile(wk.tile, b0, h0, w0, n0, cls);
+      const int ooy = a.n_cls > 1 ? (cls >> 1) : a.ooy, oox = a.n_cls > 1 ? (cls & 1) : a.oox;
       const int acc = lt & 1;
       const uint32_t acc_phase = (uint32_t)(lt >> 1) & 1u;
       mbar_wait(tfull_bar(acc), acc_phase);
@@ -414,7 +421,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
       int ncols, nloc;
       float* outp = tc_out_of(a, n0, ncols, nloc);
       const size_t rowoff =
-          (((size_t)b * a.outH + ((h0 + hl) * a.omy + a.ooy)) * a.outW + ((w0 + wl) * a.omx + a.oox)) * ncols + nloc;
+          (((size_t)b * a.outH + ((h0 + hl) * a.omy + ooy)) * a.outW + ((w0 + wl) * a.omx + oox)) * ncols + nloc;
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
         uint32_t v[32];
@@ -784,7 +791,9 @@ __global__ void __launch_bounds__(256) tc_sk_finish_kernel(const __grid_constant
     const int r = (int)((i / c4n) % kBM);
     const int st = (int)(i / ((long long)c4n * kBM));
     const int first = (st * K) / a.sk_per, last = ((st + 1) * K - 1) / a.sk_per;
-    int tile = a.n_dp + st;
+    int tile = a.n_dp + st, cls = 0;
+    if (a.n_cls > 1) { cls = tile / a.tiles_per_cls; tile -= cls * a.tiles_per_cls; }
+    const int ooy = a.n_cls > 1 ? (cls >> 1) : a.ooy, oox = a.n_cls > 1 ? (cls & 1) : a.oox;
     const int nt = tile % a.n_nt;
     int m = tile / a.n_nt;
     const int mw = m % a.n_wt;
@@ -802,8 +811,8 @@ __global__ void __launch_bounds__(256) tc_sk_finish_kernel(const __grid_constant
     }
     int ncols, nloc;
     float* outp = tc_out_of(a, nt * BN, ncols, nloc);
-    const size_t rowoff = (((size_t)b * a.outH + ((mh * a.TH + hl) * a.omy + a.ooy)) * a.outW +
-                           ((mw * a.TW + wl) * a.omx + a.oox)) * ncols + nloc;
+    const size_t rowoff = (((size_t)b * a.outH + ((mh * a.TH + hl) * a.omy + ooy)) * a.outW +
+                           ((mw * a.TW + wl) * a.omx + oox)) * ncols + nloc;
     tc_store4(a, outp, rowoff + c, nt * BN + c, tc_row_scale(a, b), sum.x, sum.y, sum.z, sum.w);
   }
 }
@@ -1048,11 +1057,13 @@ int launch_tc_v1(const float* x1, const float* x2, const float* wp, int passes, 
   const int m_tiles = a.n_wt * a.n_ht * a.n_bt;
   const int kiters = a.T * (a.kc1 + a.kc2);
   if (a.ws && !mtd_aligned16(a.ws)) return MTD_EALIGN;
-  const Schedule sc = choose_schedule(m_tiles, a.N, kiters, passes, a.ws ? a.ws_floats : 0, a.n_split);
+  if (a.n_cls < 1) a.n_cls = 1;
+  const Schedule sc = choose_schedule(m_tiles * a.n_cls, a.N, kiters, passes, a.ws ? a.ws_floats : 0, a.n_split);
   if (sc.cost >= 1e30) return MTD_EINVAL;
   const int BN = sc.bn;
   a.n_nt = a.N / BN;
-  a.n_tiles = m_tiles * a.n_nt;
+  a.tiles_per_cls = m_tiles * a.n_nt;
+  a.n_tiles = a.tiles_per_cls * a.n_cls;
   a.n_dp = sc.n_dp; a.sk_tiles = sc.sk_tiles; a.sk_per = sc.sk_per; a.sk_P = sc.sk_P; a.grid = sc.grid;
   a.ksplit = 1; a.kper = kiters;
   CUtensorMap mA1, mA2, mB;
@@ -1062,12 +1073,12 @@ int launch_tc_v1(const float* x1, const float* x2, const float* wp, int passes, 
   if (a.C2) { rc = make_act_map(&mA2, x2, a.C2, a.inW, a.inH, a.B, a.TW, a.TH, a.TB, false, a.es); if (rc) return rc; }
   else mA2 = mA1;
   const long long K = (long long)a.T * (a.C1 + a.C2);
-  rc = make_w_map(&mB, wp, K, a.N, BN);
+  rc = make_w_map(&mB, wp, K, a.N * a.n_cls, BN);
   if (rc) return rc;
   CUtensorMap mBlo = mB;
   if (passes == 3) {
     // the lo half follows the hi half of the FULL packed weight (a.wrows_total rows), not of this row slice
-    rc = make_w_map(&mBlo, wp + (size_t)a.wrows_total * K, K, a.N, BN);
+    rc = make_w_map(&mBlo, wp + (size_t)a.wrows_total * K, K, a.N * a.n_cls, BN);
     if (rc) return rc;
   }
 #define TC_DISPATCH(BN_)                                                           \
@@ -1563,6 +1574,21 @@ int mtd_conv_dgrad_tc(const float* dz, const float* wpd, float* dx, const float*
   a.H = H / 2; a.W = W / 2; a.T = 4; a.omy = a.omx = 2;
   const size_t total = (size_t)B * H * W * Cin;
   const size_t cls_elems = (size_t)Cin * 4 * Cout;
+  if (g_tc_version != 2) {
+    // v1 kernel: the four output-parity classes are ONE launch (tile index carries the class); the classes own
+    // disjoint output pixels, so whole tiles and stream-K pieces are finished exactly as for a stride-1 layer
+    for (int py = 0; py < 2; ++py)
+      for (int px = 0; px < 2; ++px)
+        for (int aa = 0; aa < 2; ++aa)
+          for (int bb = 0; bb < 2; ++bb) {
+            const int ky = (1 - py) + 2 * aa, kx = (1 - px) + 2 * bb, i = (py * 2 + px) * 4 + aa * 2 + bb;
+            a.dy[i] = (py + 1 - ky) / 2;
+            a.dx[i] = (px + 1 - kx) / 2;
+          }
+    a.n_cls = 4;
+    a.wrows_total = 4 * Cin;          // packed layout [4 classes][Cin][4][Cout]; the lo copy follows all four classes
+    return launch_tc(dz, nullptr, wpd, passes, a, st);
+  }
   int ksplit = 0;
   for (int py = 0; py < 2; ++py)
     for (int px = 0; px < 2; ++px) {
@@ -1576,12 +1602,6 @@ int mtd_conv_dgrad_tc(const float* dz, const float* wpd, float* dx, const float*
       c.ooy = py; c.oox = px;
       // packed layout [4 classes][Cin][4][Cout]; for passes == 3 the lo half starts after all four classes
       c.wrows_total = 4 * Cin;                            // rows from this class's base to the lo copy of the same class
-      if (g_tc_version != 2) {
-        // v1 kernel: every class launch reduces its own stream-K pieces (the classes own disjoint output pixels)
-        int rc = launch_tc(dz, nullptr, wpd + (size_t)(py * 2 + px) * cls_elems, passes, c, st);
-        if (rc) return rc;
-        continue;
-      }
       if (py == 0 && px == 0) {
         // decide the split once so all classes agree; zero dx up front when partial sums will be accumulated
         TcArgs probe = c;
