@@ -57,6 +57,11 @@ int mtd_conv_pack_fwd_blocked(const float* w_ref, int transposed, int Cout, int 
                               void* stream);
 int mtd_conv_pack_dgrad_blocked(const float* w_ref, int transposed, int Cout, int Cin, int kh, int kw, int stride, int tf32,
                                 float* out, void* stream);
+/* Batched packing: between _begin and _end every pack entry point above records its work instead of launching; _end
+ * launches it all, 24 packs per kernel (descriptions travel in kernel-parameter space: no table upload, graph-safe).
+ * Host-side recording state: one batch at a time, not thread-safe.                                          */
+int mtd_conv_pack_batch_begin(void);
+int mtd_conv_pack_batch_end(void* stream);
 /* y = post_act( pre_act( scale * conv(cat[x1,x2]) + bias ) + add1 + add2 );  aux (optional) receives the
  * value after pre_act.  x2/C2 = second source concatenated along channels (torch.cat at
  * networks.py:421-466) or null/0.  scale = device scalar 1/sigma of spectral norm, or null.  scale_group > 0 (all four

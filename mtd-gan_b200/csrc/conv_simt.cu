@@ -8,6 +8,8 @@
 // Replaces: every nn.Conv2d / nn.ConvTranspose2d / nn.Linear call of arch/Ours/networks.py:18-19,
 // 41-46, 170, 181-306 and their autograd backward (ATen convolution_backward).
 #include <algorithm>
+#include <string.h>
+#include <vector>
 #include "common.cuh"
 #include "mtdgan_b200.h"
 
@@ -529,6 +531,52 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, float* __restri
   }
 }
 
+// Batched packing: up to kPackBatch packs per launch, described in kernel-parameter space (no table upload), so the
+// ~230 per-layer pack launches of a train step (every weight changes once per step) become ~10.
+constexpr int kPackBatch = 24;
+constexpr int kPackChunk = 8192;          // elements per block
+struct PackBatch {
+  const float* w[kPackBatch];
+  float* out[kPackBatch];
+  PackArgs p[kPackBatch];
+  int first_block[kPackBatch + 1];        // prefix sums of blocks per pack
+  int n;
+};
+static_assert(sizeof(PackBatch) <= 4000, "PackBatch must fit the kernel parameter space");
+
+__device__ __forceinline__ void pack_one(const float* __restrict__ w, float* __restrict__ out, const PackArgs& p, size_t i) {
+  int c = (int)(i % p.C);
+  size_t r = i / p.C;
+  int t = (int)(r % p.T);
+  int n = (int)(r / p.T);
+  size_t o = i;
+  if (p.blocked) {
+    const size_t k = (size_t)t * p.C + c, KS = (size_t)p.T * p.C / 32;
+    o = ((((size_t)(n >> 5) * KS + (k >> 5)) * 32 + (n & 31)) << 5) + (k & 31);
+  }
+  const float v = __ldg(w + (size_t)n * p.sN + (size_t)c * p.sC + p.toff[t]);
+  if (p.tf32 == 0) { out[o] = v; return; }
+  uint32_t h;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(v));
+  out[o] = __uint_as_float(h);
+  if (p.tf32 == 3) {
+    uint32_t l;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(v - __uint_as_float(h)));
+    out[o + p.lo_off] = __uint_as_float(l);
+  }
+}
+
+__global__ void __launch_bounds__(256) pack_batched_kernel(const __grid_constant__ PackBatch pb) {
+  mtd_pdl_prologue();
+  int s = 0;
+  while (s + 1 < pb.n && (int)blockIdx.x >= pb.first_block[s + 1]) ++s;
+  const PackArgs& p = pb.p[s];
+  const size_t total = (size_t)p.N * p.T * p.C;
+  const size_t begin = (size_t)((int)blockIdx.x - pb.first_block[s]) * kPackChunk;
+  const size_t end = min(total, begin + (size_t)kPackChunk);
+  for (size_t i = begin + threadIdx.x; i < end; i += blockDim.x) pack_one(pb.w[s], pb.out[s], p, i);
+}
+
 // dw_ref[n*sN + c*sC + toff[t]] = alpha * (gp[n][t][c] - beta * u[n_sn] * v[k_sn])
 // where for spectral-normed layers alpha = 1/sigma, beta = <G,W>/sigma and (u,v) index the
 // (Cout, Cin*kh*kw) matrix view of the REFERENCE layout.
@@ -742,7 +790,16 @@ void fwd_mapping(PackArgs& p, int transposed, int Cout, int Cin, int kh, int kw)
   }
 }
 
+// mtd_conv_pack_batch_begin / _end: between them every pack entry point RECORDS its work instead of launching it
+// (host-side list, one batch at a time, not thread-safe); _end launches ceil(n / kPackBatch) batched kernels.
+struct PackRec { const float* w; float* out; PackArgs p; };
+static std::vector<PackRec>* g_pack_batch = nullptr;
+
 int pack_launch(const float* w, float* out, const PackArgs& p, cudaStream_t st) {
+  if (g_pack_batch) {
+    g_pack_batch->push_back(PackRec{w, out, p});
+    return MTD_OK;
+  }
   size_t total = (size_t)p.N * p.T * p.C;
   int blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)mtd_sm_count() * 16);
   mtd_launch(pack_weights_kernel, blocks, 256, 0, st, w, out, p);
@@ -1155,6 +1212,41 @@ int mtd_conv_pack_dgrad_blocked(const float* w_ref, int transposed, int Cout, in
   g_pack_blocked = 1; g_pack_tf32 = tf32;
   int rc = mtd_conv_pack_dgrad(w_ref, transposed, Cout, Cin, kh, kw, stride, out, stream);
   g_pack_blocked = 0; g_pack_tf32 = 0;
+  return rc;
+}
+
+int mtd_conv_pack_batch_begin(void) {
+  MTD_REQUIRE(g_pack_batch == nullptr);
+  g_pack_batch = new std::vector<PackRec>();
+  return MTD_OK;
+}
+
+// Launches everything recorded since mtd_conv_pack_batch_begin: kPackBatch packs per kernel.
+int mtd_conv_pack_batch_end(void* stream) {
+  MTD_REQUIRE(g_pack_batch != nullptr);
+  std::vector<PackRec>* recs = g_pack_batch;
+  g_pack_batch = nullptr;
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = MTD_OK;
+  for (size_t i0 = 0; i0 < recs->size() && rc == MTD_OK; i0 += kPackBatch) {
+    PackBatch pb;
+    memset(&pb, 0, sizeof(pb));
+    pb.n = (int)std::min<size_t>(kPackBatch, recs->size() - i0);
+    int blocks = 0;
+    for (int k = 0; k < pb.n; ++k) {
+      const PackRec& r = (*recs)[i0 + k];
+      pb.w[k] = r.w; pb.out[k] = r.out; pb.p[k] = r.p;
+      pb.first_block[k] = blocks;
+      const size_t total = (size_t)r.p.N * r.p.T * r.p.C;
+      blocks += (int)((total + kPackChunk - 1) / kPackChunk);
+    }
+    pb.first_block[pb.n] = blocks;
+    mtd_launch(pack_batched_kernel, blocks, 256, 0, st, pb);
+    ++g_mtd_kernel_launches;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) rc = (int)e;
+  }
+  delete recs;
   return rc;
 }
 

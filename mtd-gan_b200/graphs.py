@@ -32,17 +32,20 @@ class GraphedTrainStep:
         self._ts = list(D.task_specific_parameters())
         self._last = list(D.last_shared_parameters())
         self._post_g_backward = post_g_backward      # e.g. the generator-gradient all-reduce at N > 1
+        self._d_params = list(D.parameters())
         self.graph = None
         self.x = self.y = None
         self.out = None
 
     def eager_step(self, x, y):
         m, D, G = self.model, self.model.Discriminator, self.model.Generator
+        ops.repack_stale()                    # all weights changed in the previous step: one batched re-pack
         self.opt_D.zero_grad(); D.zero_grad()
         d_losses, d_det = m.d_loss(x, y)
         self.wm.backward(losses=d_losses, shared_parameters=self._shared, task_specific_parameters=self._ts,
                          last_shared_parameters=self._last)
         self.opt_D.step()
+        ops.repack_stale(self._d_params)      # g_loss runs the updated discriminator
         self.opt_G.zero_grad(); G.zero_grad()
         g_loss, g_det = m.g_loss(x, y)
         g_loss.backward()

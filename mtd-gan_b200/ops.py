@@ -31,9 +31,11 @@ _pack_cache: dict = {}        # id(weight object) -> {(kind, transposed, stride)
 
 
 def clear_pack_cache():
-    """Drop every packed copy (used before CUDA-graph capture so the packing kernels are captured too)."""
+    """Invalidate every packed copy (used before CUDA-graph capture so the packing kernels are captured too).  The
+    registry of (weight, kind, cfg) stays, so `repack_stale()` can rebuild everything in a few batched launches."""
     for slot in _pack_cache.values():
-        slot.clear()
+        for key, ent in list(slot.items()):
+            slot[key] = (None,) + tuple(ent[1:])
 
 
 def _cache_slot(weight) -> dict:
@@ -46,18 +48,7 @@ def _cache_slot(weight) -> dict:
     return slot
 
 
-def _packed(weight: torch.Tensor, kind: str, cfg: "ConvCfg") -> torch.Tensor:
-    """K-major packed copy of a reference-layout weight.  Cached per weight OBJECT (weakly: entries die
-    with the parameter, so a recycled allocation can never alias a stale entry) and invalidated by the
-    tensor's version counter / storage pointer."""
-    slot = _cache_slot(weight)
-    key = (kind, cfg.transposed, cfg.stride)
-    tag = (weight._version, weight.data_ptr())
-    ent = slot.get(key)
-    if ent is not None and ent[0] == tag:
-        return ent[1]
-    w = weight.detach()
-    out = _empty((w.numel() * (2 if kind.endswith("_tf32x3") else 1),), w)
+def _pack_into(w: torch.Tensor, kind: str, cfg: "ConvCfg", out: torch.Tensor):
     if "_tf32" in kind:
         # tensor-core packs: tile-major (blocked) layout with the TF32 rounding ([hi | lo] split for 3xTF32) fused in
         mode = 3 if kind.endswith("_tf32x3") else 1
@@ -72,8 +63,58 @@ def _packed(weight: torch.Tensor, kind: str, cfg: "ConvCfg") -> torch.Tensor:
     else:
         call("mtd_conv_pack_dgrad", fptr(w), cfg.transposed, cfg.cout, cfg.cin, cfg.kh, cfg.kw, cfg.stride, fptr(out),
              stream())
-    slot[key] = (tag, out)
+
+
+def _packed(weight: torch.Tensor, kind: str, cfg: "ConvCfg") -> torch.Tensor:
+    """K-major packed copy of a reference-layout weight.  Cached per weight OBJECT (weakly: entries die
+    with the parameter, so a recycled allocation can never alias a stale entry) and invalidated by the
+    tensor's version counter / storage pointer.  Cache entry: (tag, packed, weakref(weight), kind, cfg)."""
+    slot = _cache_slot(weight)
+    key = (kind, cfg.transposed, cfg.stride)
+    tag = (weight._version, weight.data_ptr())
+    ent = slot.get(key)
+    if ent is not None and ent[0] == tag:
+        return ent[1]
+    w = weight.detach()
+    out = _empty((w.numel() * (2 if kind.endswith("_tf32x3") else 1),), w)
+    _pack_into(w, kind, cfg, out)
+    slot[key] = (tag, out, weakref.ref(weight), kind, cfg)
     return out
+
+
+def repack_stale(params=None) -> int:
+    """Rebuild, in a few BATCHED launches (24 packs per kernel), every registered packed copy whose weight has changed
+    since it was packed (optimizer step, load_state_dict, cache invalidation).  `params` restricts it to those
+    parameters.  Layers pack lazily on first use anyway; calling this once after each optimizer step replaces ~230
+    per-layer pack launches per train step by ~10.  Returns the number of packs rebuilt."""
+    want = None if params is None else {id(p) for p in params}
+    todo = []
+    for wid, slot in _pack_cache.items():
+        if want is not None and wid not in want:
+            continue
+        for key, ent in slot.items():
+            if len(ent) < 5:
+                continue
+            weight = ent[2]()
+            if weight is None or not weight.is_cuda:
+                continue
+            tag = (weight._version, weight.data_ptr())
+            if ent[0] != tag:
+                todo.append((slot, key, ent, weight, tag))
+    if not todo:
+        return 0
+    call("mtd_conv_pack_batch_begin")
+    try:
+        for slot, key, ent, weight, tag in todo:
+            kind, cfg = ent[3], ent[4]
+            w = weight.detach()
+            n = w.numel() * (2 if kind.endswith("_tf32x3") else 1)
+            out = ent[1] if (ent[1] is not None and ent[1].numel() == n and ent[1].device == w.device) else _empty((n,), w)
+            _pack_into(w, kind, cfg, out)
+            slot[key] = (tag, out, ent[2], kind, cfg)
+    finally:
+        call("mtd_conv_pack_batch_end", stream())
+    return len(todo)
 
 
 # Weight-gradient request filter.  torch.autograd.grad(l, inputs=...) prunes built-in ops' unused
