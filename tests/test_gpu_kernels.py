@@ -503,3 +503,41 @@ def test_spectral_norm_grouped_deferred_matches_two_calls():
         assert rel_err(dw, ref.weight_orig.grad) <= 2e-5    # exact-fp32 kernels
     finally:
         ops.set_conv_mode("auto", 3)
+
+
+def test_repack_stale_rebuilds_all_packs_in_batches():
+    """ops.repack_stale(): after in-place weight updates every registered packed copy (SIMT / tensor-core, forward /
+    dgrad, stride-2 class packs) is rebuilt by the batched pack kernel and gives the same results as lazy packing."""
+    from mtdgan_b200 import ops, _ext
+    torch.manual_seed(11)
+    layers = []
+    for (cin, cout, k, s, p) in [(32, 64, 3, 1, 1), (64, 64, 4, 2, 1), (1, 32, 3, 1, 1), (64, 32, 1, 1, 0)] * 8:     # 32 layers > one batch
+        w = (torch.randn(cout, cin, k, k, device=DEV) / (cin * k * k) ** 0.5).requires_grad_(True)
+        b = torch.zeros(cout, device=DEV, requires_grad=True)
+        layers.append((w, b, ops.ConvCfg(cin=cin, cout=cout, kh=k, kw=k, stride=s, pad=p, pre_act=ops.ACT_LEAKY)))
+
+    def run():
+        outs = []
+        for w, b, cfg in layers:
+            x = torch.randn(4, 16, 16, cfg.cin, device=DEV, generator=torch.Generator(device=DEV).manual_seed(cfg.cin)).requires_grad_(True)
+            y = ops.conv(x, w, b, cfg)
+            (gx,) = torch.autograd.grad(y.sum(), [x])
+            outs.append((y.detach(), gx))
+        return outs
+
+    run()                                                     # registers fwd + dgrad packs of every layer
+    with torch.no_grad():
+        for w, _, _ in layers:
+            w.mul_(1.5).add_(0.01)                            # bumps the version counters
+    l0 = _ext.kernel_launch_count()
+    n = ops.repack_stale()
+    launches = _ext.kernel_launch_count() - l0
+    recs = n + 3 * 8                                          # each of the 8 stride-2 dgrad packs is four class sub-packs
+    assert n == 2 * len(layers) and launches == -(-recs // 24), (n, launches)
+    l1 = _ext.kernel_launch_count()
+    got = run()
+    ops.clear_pack_cache()                                    # force lazy per-layer packing for the reference run
+    want = run()
+    for (y1, g1), (y2, g2) in zip(got, want):
+        assert torch.equal(y1, y2) and torch.equal(g1, g2)
+    assert ops.repack_stale() == 0
