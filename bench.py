@@ -25,9 +25,15 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-# stdout carries exactly one JSON line: keep NCCL's version banner (NCCL_DEBUG=VERSION prints it to stdout) out of it
-if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-    os.environ["NCCL_DEBUG"] = "WARN"
+# stdout carries exactly ONE JSON line.  Libraries print there too (NCCL's version banner at NCCL_DEBUG=VERSION or
+# WARN), so file descriptor 1 is pointed at stderr for the whole run and the JSON line goes to the saved descriptor.
+_JSON_FD = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line: dict):
+    os.write(_JSON_FD, (json.dumps(line) + "\n").encode())
+
 
 import torch  # noqa: E402
 
@@ -451,7 +457,7 @@ def main():
     if args.impl == "reference":
         line = run_reference(args)
         if line is not None:
-            print(json.dumps(line), flush=True)
+            emit(line)
         return
     line = run_own(args)
     rank, world, _ = dist_env()
@@ -462,7 +468,7 @@ def main():
             except Exception as ex:      # the baseline leg must never take the measurement down with it
                 line["cpu_baseline"] = {"value": None, "unit": "patches/s", "cores": os.cpu_count(), "kind": "port",
                                         "sample": f"failed: {type(ex).__name__}: {ex}"}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         torch.distributed.barrier()
         torch.distributed.destroy_process_group()
