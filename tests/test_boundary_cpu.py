@@ -135,3 +135,22 @@ def test_get_loss_and_module_surface(model):
     for attr in ("conv11", "relu11", "down6", "bconv2", "brelu2", "c_flatten", "c_fc", "c_relu", "c_drop", "s_up1",
                  "s_dconv62", "s_drelu62", "r_up6", "r_dconv62", "r_drelu62", "enc_out", "dec_out", "rec_out"):
         assert hasattr(model.Discriminator, attr), attr
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the reference's CPU path = oracle port on the host cores): exactly one stdout line,
+    a JSON object with the contract's keys (metric / unit / config shared with the GPU arm; impl, cpu_baseline, e2e)."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=600, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, r.stdout
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"].startswith("train patches/s") and d["unit"] == "patches/s"
+    assert d["higher_is_better"] is True and d["n_gpus"] == 1 and d["steps"] == 1 and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "patches/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
