@@ -153,6 +153,41 @@ _finish_queue = None          # None, or {weight data_ptr: (dw, [instance tuples
 _fin_chunk_cache: dict = {}
 
 
+# Weight-gradient GEMMs are off the critical path of a backward pass (nothing consumes them before the batched
+# finishing at the end of the autograd.grad call), so inside a deferred-finishing context they can be issued on a side
+# stream and overlap the act_bwd -> dgrad chain of the following layers (MTDGAN_WGRAD_STREAM=0 disables it; in a captured
+# step the side stream becomes a parallel branch of the graph; measured 43.1 -> 42.5 ms per step).  Their operands are kept alive until the join.
+_WGRAD_SIDE = os.environ.get("MTDGAN_WGRAD_STREAM", "1") == "1"
+_side_streams: dict = {}
+_side_keepalive: list = []
+_side_used = False
+
+
+def _on_side_stream(fn, *keep):
+    """Run fn() on the side stream after everything queued so far on the current stream."""
+    global _side_used
+    main = torch.cuda.current_stream()
+    key = (main.device.index, main.cuda_stream)
+    side = _side_streams.get(key)
+    if side is None:
+        side = _side_streams[key] = torch.cuda.Stream(device=main.device)
+    side.wait_stream(main)
+    with torch.cuda.stream(side):
+        fn()
+    _side_keepalive.extend(keep)
+    _side_used = True
+
+
+def _join_side_stream():
+    global _side_used
+    if _side_used:
+        main = torch.cuda.current_stream()
+        side = _side_streams.get((main.device.index, main.cuda_stream))
+        if side is not None:
+            main.wait_stream(side)
+        _side_used = False
+
+
 class deferred_wgrad_finish:
     def __enter__(self):
         global _finish_queue, _bias_slab, _zw_slab
@@ -167,9 +202,11 @@ class deferred_wgrad_finish:
         zw_keepalive = _zw_slab               # the finishing kernels read the <G, W~> accumulators through raw pointers
         _bias_slab = self.prev_slab
         _zw_slab = self.prev_zw
+        _join_side_stream()
         if q and exc[0] is None:
             _flush_finish(q)
         del zw_keepalive
+        _side_keepalive.clear()
         return False
 
 
@@ -479,28 +516,18 @@ class ConvFn(Function):
             dz = g1
             if dbias is not None:
                 call("mtd_act_bwd", fptr(g1), None, None, fptr(dbias), dbz, M, cfg.cout, ACT_NONE, cfg.slope, st)
-        # 2) data gradients
-        dx1 = dx2 = None
-        dscale = None if zw is not None else inv_sigma       # zw path: dz already carries 1/sigma
-        both = False
-        if C2 and need[0] and need[1] and not cfg.fuse_add1_is_input:
-            dx1, dx2 = _empty((B, H, W, C1), dy), _empty((B, H, W, C2), dy)
-            both = _conv_dgrad_launch_cat(dz, weight, dx1, dx2, dscale, B, H, W, C1, C2, cfg)
-        if need[0] and not both:
-            dx1 = _empty((B, H, W, C1), dy)
-            fuse = g1 if cfg.fuse_add1_is_input else None
-            _conv_dgrad_launch(dz, weight, dx1, dscale, fuse, B, H, W, C1, 0, cfg)
-        if C2 and need[1] and not both:
-            dx2 = _empty((B, H, W, C2), dy)
-            _conv_dgrad_launch(dz, weight, dx2, dscale, None, B, H, W, C2, C1, cfg)
-        # 3) weight gradient (packed), then to reference layout (+ spectral-norm correction)
+        # 2) weight gradient (packed), then to reference layout (+ spectral-norm correction).  Issued BEFORE the data
+        #    gradient: on the side stream it then runs concurrently with this layer's dgrad and the layers after it
         dw = None
         if want_w:
             Bg = B // G
             insts = []          # (gp, w, u, v, 1/sigma, cfg, pointer to <G,W~> or 0, flag bits: 2 gp pre-scaled, 4 no gp)
             if zw is not None:
                 gp = _empty((weight.numel(),), dy)
-                _conv_wgrad_launch(x1, x2, dz, gp, B, H, W, C1, C2, cfg)          # sum_g G_g / sigma_g in one GEMM
+                if _WGRAD_SIDE:
+                    _on_side_stream(lambda: _conv_wgrad_launch(x1, x2, dz, gp, B, H, W, C1, C2, cfg), x1, x2, dz, gp)
+                else:
+                    _conv_wgrad_launch(x1, x2, dz, gp, B, H, W, C1, C2, cfg)      # sum_g G_g / sigma_g in one GEMM
                 for g in range(G):
                     insts.append((gp if g == 0 else None, weight.detach(), u[g] if u.dim() == 2 else u, v[g] if v.dim() == 2 else v,
                                   inv_sigma[g:g + 1], cfg, zw.data_ptr() + 8 * g, 2 if g == 0 else 4))
@@ -508,7 +535,10 @@ class ConvFn(Function):
                 for g in range(G):          # one packed weight gradient per batched reference call (own u, v, sigma)
                     gp = _empty((weight.numel(),), dy)
                     if G == 1:
-                        _conv_wgrad_launch(x1, x2, dz, gp, B, H, W, C1, C2, cfg)
+                        if _WGRAD_SIDE and _finish_queue is not None:
+                            _on_side_stream(lambda gp=gp: _conv_wgrad_launch(x1, x2, dz, gp, B, H, W, C1, C2, cfg), x1, x2, dz, gp)
+                        else:
+                            _conv_wgrad_launch(x1, x2, dz, gp, B, H, W, C1, C2, cfg)
                         insts.append((gp, weight.detach(), None if u is None else u.reshape(-1),
                                       None if v is None else v.reshape(-1), inv_sigma, cfg, 0, 0))
                     else:
@@ -529,6 +559,20 @@ class ConvFn(Function):
                     call("mtd_conv_wgrad_finish", fptr(gp), fptr(part), cfg.transposed, cfg.cout, cfg.cin, cfg.kh, cfg.kw,
                          fptr(wd) if inv_g is not None else None, fptr(ug), fptr(vg), fptr(inv_g), ptr(scratch), st)
                     dw = part if k == 0 else dw + part
+        # 3) data gradients
+        dx1 = dx2 = None
+        dscale = None if zw is not None else inv_sigma       # zw path: dz already carries 1/sigma
+        both = False
+        if C2 and need[0] and need[1] and not cfg.fuse_add1_is_input:
+            dx1, dx2 = _empty((B, H, W, C1), dy), _empty((B, H, W, C2), dy)
+            both = _conv_dgrad_launch_cat(dz, weight, dx1, dx2, dscale, B, H, W, C1, C2, cfg)
+        if need[0] and not both:
+            dx1 = _empty((B, H, W, C1), dy)
+            fuse = g1 if cfg.fuse_add1_is_input else None
+            _conv_dgrad_launch(dz, weight, dx1, dscale, fuse, B, H, W, C1, 0, cfg)
+        if C2 and need[1] and not both:
+            dx2 = _empty((B, H, W, C2), dy)
+            _conv_dgrad_launch(dz, weight, dx2, dscale, None, B, H, W, C2, C1, cfg)
         d_add1 = d_add if (need[7] and not cfg.fuse_add1_is_input) else None
         d_add2 = d_add if need[8] else None
         return dx1, dx2, dw, dbias, None, None, None, d_add1, d_add2, None
