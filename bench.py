@@ -27,12 +27,23 @@ sys.path.insert(0, ROOT)
 
 # stdout carries exactly ONE JSON line.  Libraries print there too (NCCL's version banner at NCCL_DEBUG=VERSION or
 # WARN), so file descriptor 1 is pointed at stderr for the whole run and the JSON line goes to the saved descriptor.
-_JSON_FD = os.dup(1)
-os.dup2(2, 1)
+_JSON_FD = None
+
+
+def claim_stdout():
+    """Called by main() only (importing this module, e.g. from the cpu_baseline child process, must not touch fd 1)."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
 
 
 def emit(line: dict):
-    os.write(_JSON_FD, (json.dumps(line) + "\n").encode())
+    if _JSON_FD is None:
+        print(json.dumps(line), flush=True)
+    else:
+        os.write(_JSON_FD, (json.dumps(line) + "\n").encode())
 
 
 import torch  # noqa: E402
@@ -454,6 +465,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of the captured CUDA graph")
     args = ap.parse_args()
+    claim_stdout()
     if args.impl == "reference":
         line = run_reference(args)
         if line is not None:

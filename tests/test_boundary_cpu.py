@@ -154,3 +154,14 @@ def test_bench_reference_arm_contract():
     assert d["higher_is_better"] is True and d["n_gpus"] == 1 and d["steps"] == 1 and d["value"] > 0
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "patches/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_importing_bench_leaves_stdout_alone():
+    """bench.py points fd 1 at stderr only in main(); its cpu_baseline leg imports the module in a child process and
+    reads that child's stdout."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", "import bench; print('still-stdout')"], capture_output=True, text=True,
+                       timeout=300, cwd=root)
+    assert r.returncode == 0 and r.stdout.strip().splitlines()[-1] == "still-stdout", (r.stdout, r.stderr[-500:])
