@@ -15,7 +15,6 @@ so world_size-2 gloo tests on CPU exercise it with torch stand-ins.
 """
 from __future__ import annotations
 
-import os
 from typing import List, Optional, Sequence
 
 import torch

@@ -7,7 +7,7 @@ from __future__ import annotations
 import os
 import weakref
 from dataclasses import dataclass
-from typing import Optional
+
 
 import torch
 from torch.autograd import Function

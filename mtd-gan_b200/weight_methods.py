@@ -11,7 +11,7 @@ like the reference (one in-place `random.shuffle` of the task list per outer tas
 from __future__ import annotations
 
 import random
-from typing import Dict, List, Optional, Sequence, Tuple, Union
+from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
 
