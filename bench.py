@@ -308,9 +308,23 @@ def run_own(args):
             breakdown["timing"] = ("conv / conv_aux / fft: replay of that family's calls of the captured step as its own CUDA "
                                    "graph (kernel-only); other rows: events around the calls of one eager step")
             timing = "replay of the captured step's conv-family calls as one CUDA graph, CUDA events, mean of 5"
-        ach = conv_flop / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
+        # achieved = ALGORITHMIC FLOP (F_alg = 99.3 GF per patch per step, useful conv + linear work) over the
+        # conv family's kernel-only time; the FLOP the launches actually execute (redundant decoder traversals of the
+        # fourth backward pass, the generator forward that is NOT re-run, ...) are reported beside it
+        ach_exec = conv_flop / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
+        ach = F_ALG_TRAIN * BATCH / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
+        by_kind = {}
+        for name, a, t in rec:
+            fl = flops_of(name, a)
+            if fl:
+                kind = "wgrad" if "wgrad" in name else "dgrad" if "dgrad" in name else "fwd"
+                by_kind[kind] = by_kind.get(kind, 0.0) + fl
         roof = {"kernel": "implicit-GEMM conv family (fwd + dgrad + wgrad)", "bound": "tensor", "achieved": round(ach, 3),
                 "peak": pk["tflops_sustained"], "unit": "TFLOP/s", "frac": round(ach / pk["tflops_sustained"], 5),
+                "flop_basis": "algorithmic: F_alg 99.3 GF/patch x 20 patches per launch-set (SURVEY 8d)",
+                "executed_tflops": round(ach_exec, 3), "frac_executed": round(ach_exec / pk["tflops_sustained"], 5),
+                "executed_gflop_per_patch": {k: round(v / BATCH / 1e9, 2) for k, v in sorted(by_kind.items())},
+                "algorithmic_gflop_per_patch": F_ALG_TRAIN / 1e9,
                 # DRAM bytes of ONE representative launch of the dominant kernel from an `ncu --set full` capture
                 # (profiles/r01_ncu_full_conv_tc_v1_v3.txt): conv_tc_kernel<128,3>, B=20 32x32 256->128 3x3 --
                 # 23.37 MB read + 2.6 KB written vs 23.3 MB compulsory (input + hi|lo weights; the output stays in L2)
@@ -321,44 +335,28 @@ def run_own(args):
                 # expressed in useful fp32-equivalent FLOP/s is peak / 6
                 "peak_3xtf32_equiv": round(pk["tflops_sustained"] / 6, 1), "frac_of_3xtf32_peak": round(ach / (pk["tflops_sustained"] / 6), 4),
                 "timing": timing,
-                "algorithmic_flop_per_launch": round(conv_flop / max(conv_calls, 1)), "launches_per_step": conv_calls,
+                "algorithmic_flop_per_launch": round(F_ALG_TRAIN * BATCH / max(conv_calls, 1)), "launches_per_step": conv_calls,
                 "avg_launch_ms": round(conv_ms / max(conv_calls, 1), 5), "share_of_step": round(conv_ms / total_ms, 4),
                 "pcgrad": {"bound": "hbm", "achieved": round(7 * N_SHARED * 4 / (by["mtd_pcgrad_project"]["ms"] * 1e-3) / 1e9, 1),
                            "peak": pk["hbm_gbs"], "unit": "GB/s",
                            "frac": round(7 * N_SHARED * 4 / (by["mtd_pcgrad_project"]["ms"] * 1e-3) / 1e9 / pk["hbm_gbs"], 4)}
                 if "mtd_pcgrad_project" in by else None}
 
-    # ---- generator inference, 1 x 512 x 512 (configs[1]); slices are independent => ranks run replicas
-    infer = None
-    model.eval()
-    xs_h = synthetic_pair(1, 512, seed=4321, rank=rank, pin=True)[0]
-    xs = xs_h.to(dev)
-    with torch.no_grad():
-        for _ in range(3):
-            G(xs)
-        torch.cuda.synchronize()
-        n_inf = max(10, min(50, args.steps))
-        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_inf)]
-        for s, e in ev:
-            flush.zero_()
-            s.record(); G(xs); e.record()
-        torch.cuda.synchronize()
-        inf_ms = [s.elapsed_time(e) for s, e in ev]
-        out_h = torch.empty(1, 1, 512, 512).pin_memory()
-        ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_inf)]
-        for s, e in ev2:
-            flush.zero_()
-            s.record(); out_h.copy_(G(xs_h.to(dev, non_blocking=True)), non_blocking=True); e.record()
-        torch.cuda.synchronize()
-        inf_e2e = [s.elapsed_time(e) for s, e in ev2]
-    if rank == 0:
-        pk = peaks()
-        sl = 1e3 / statistics.mean(inf_ms)
-        infer = {"metric": "512x512 denoised slices/s (generator inference, batch 1)", "value": round(sl * world, 3),
-                 "ms_per_slice": round(statistics.mean(inf_ms), 4), "e2e_value": round(1e3 / statistics.mean(inf_e2e) * world, 3),
-                 "roofline": {"bound": "hbm", "achieved": round(B_ALG_INFER * sl / 1e9, 1), "peak": pk["hbm_gbs"], "unit": "GB/s",
-                              "frac": round(B_ALG_INFER * sl / 1e9 / pk["hbm_gbs"], 4), "traffic": None},
-                 "scaling": "replicas (slices are independent; no collective)"}
+    # ---- generator inference (configs[1]: one 1x512x512 slice; configs[4]: 64 slices per GPU, slices sharded by rank,
+    #      no collective).  The forward is replayed as a CUDA graph per micro-batch (mtdgan_b200.inference).
+    infer = run_inference(args, model, dev, rank, world, flush)
+
+    gpu_eager = None
+    if rank == 0 and world == 1 and not args.no_gpu_eager:
+        try:
+            gpu_eager = run_gpu_eager_baseline(dev, xd, yd)
+        except Exception as ex:       # a baseline leg must never take the measurement down with it
+            gpu_eager = {"failed": f"{type(ex).__name__}: {ex}"}
+    if rank == 0 and roof is not None and world == 1:
+        try:
+            roof["tf32_peak"] = measure_tf32_peak(dev)
+        except Exception as ex:
+            roof["tf32_peak"] = {"failed": f"{type(ex).__name__}: {ex}"}
 
     if rank != 0:
         return None
@@ -377,9 +375,224 @@ def run_own(args):
                 "h2d_bytes_per_step": 2 * BATCH * PATCH * PATCH * 4, "d2h_bytes_per_step": 16},
         "gpu_launches": int(launches) * args.steps, "gpu_launches_per_step": int(launches),
         "useful_tflops": round(F_ALG_TRAIN * patches * args.steps / (t_dev * 1e-3) / 1e12, 3),
-        "roofline": roof, "kernel_breakdown_ms": breakdown, "inference": infer, "clocks": clocks,
+        "roofline": roof, "kernel_breakdown_ms": breakdown, "inference": infer, "gpu_eager_baseline": gpu_eager, "clocks": clocks,
     }
     return line
+
+
+# Bytes of DRAM traffic per 512x512 slice measured by `ncu --set full` over one batch-1 generator forward (sum of
+# dram__bytes_read.sum + dram__bytes_write.sum over its kernels; profiles/r02_ncu_inference_512.txt); None until captured.
+INFER_TRAFFIC_BYTES = None
+
+
+def run_inference(args, model, dev, rank, world, flush):
+    from mtdgan_b200.data import synthetic_pair
+    from mtdgan_b200.inference import GraphedGenerator, shard_slices
+    from mtdgan_b200 import _ext
+    G = model.Generator
+    model.eval()
+    pk = peaks()
+    n_inf = max(10, min(30, args.steps))
+
+    def ev_pairs(n):
+        return [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n)]
+
+    with torch.no_grad():
+        # -- configs[1]: batch 1
+        xs_h = synthetic_pair(1, 512, seed=4321, rank=rank, pin=True)[0]
+        xs = xs_h.to(dev)
+        g1 = GraphedGenerator(G, 512, 512, micro_batch=1).capture()
+        for _ in range(3):
+            g1(xs)
+        torch.cuda.synchronize()
+        ev = ev_pairs(n_inf)
+        for s, e in ev:
+            flush.zero_()
+            s.record(); g1(xs); e.record()
+        torch.cuda.synchronize()
+        inf_ms = [s.elapsed_time(e) for s, e in ev]
+        out_h = torch.empty(1, 1, 512, 512).pin_memory()
+        ev2 = ev_pairs(n_inf)
+        for s, e in ev2:
+            flush.zero_()
+            s.record(); out_h.copy_(g1(xs_h.to(dev, non_blocking=True)), non_blocking=True); e.record()
+        torch.cuda.synchronize()
+        inf_e2e = [s.elapsed_time(e) for s, e in ev2]
+        # eager (ungraphed) for comparison + per-entry-point kernel times of one forward
+        ev3 = ev_pairs(5)
+        for s, e in ev3:
+            s.record(); G(xs); e.record()
+        torch.cuda.synchronize()
+        eager_ms = statistics.mean(s.elapsed_time(e) for s, e in ev3)
+        per_entry = None
+        if rank == 0:
+            torch.cuda._sleep(int(0.05 * 1.9e9))
+            _ext.start_profile()
+            G(xs)
+            rec = _ext.stop_profile()
+            per_entry = {}
+            for name, a, t in rec:
+                d = per_entry.setdefault(name, {"ms": 0.0, "calls": 0})
+                d["ms"] = round(d["ms"] + t, 4); d["calls"] += 1
+        del g1
+
+        # -- configs[4]: 64 slices per GPU; choose the micro-batch by a short sweep (1 / 2 / 4), keep the best
+        per_gpu = args.infer_batch
+        xb_h = synthetic_pair(per_gpu, 512, seed=777, rank=rank, pin=True)[0]
+        ob_h = torch.empty(per_gpu, 1, 512, 512).pin_memory()
+        xb = xb_h.to(dev)
+        ob = torch.empty_like(xb)
+        best = None
+        for mb in (1, 2, 4):
+            gb = GraphedGenerator(G, 512, 512, micro_batch=mb).capture()
+            gb(xb[:2 * mb], ob[:2 * mb])
+            torch.cuda.synchronize()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record(); gb(xb[:8], ob[:8]); e.record()
+            torch.cuda.synchronize()
+            t = s.elapsed_time(e) / 8
+            if best is None or t < best[1]:
+                best = (mb, t)
+            del gb
+        gb = GraphedGenerator(G, 512, 512, micro_batch=best[0]).capture()
+        gb(xb, ob)
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+        reps = 3
+        evb = ev_pairs(reps)
+        for s, e in evb:
+            flush.zero_()
+            s.record(); gb(xb, ob); e.record()
+        torch.cuda.synchronize()
+        tb = sum(s.elapsed_time(e) for s, e in evb)
+        evc = ev_pairs(reps)
+        for s, e in evc:
+            flush.zero_()
+            s.record()
+            gb(xb_h.to(dev, non_blocking=True), ob)
+            ob_h.copy_(ob, non_blocking=True)
+            e.record()
+        torch.cuda.synchronize()
+        tc = sum(s.elapsed_time(e) for s, e in evc)
+        if world > 1:
+            t = torch.tensor([tb, tc], device=dev, dtype=torch.float64)
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+            tb, tc = float(t[0]), float(t[1])
+        del gb
+    lo, hi = shard_slices(per_gpu * world, world, rank)
+    assert hi - lo == per_gpu
+    if rank != 0:
+        return None
+    sl = 1e3 / statistics.mean(inf_ms)
+    slb = per_gpu * world * reps / (tb * 1e-3)
+    return {"metric": "512x512 denoised slices/s (generator inference)",
+            "batch1": {"config": "BASELINE configs[1]: 1x1x512x512, one CUDA-graph replay per slice", "value": round(sl, 3),
+                       "ms_per_slice": round(statistics.mean(inf_ms), 4), "e2e_value": round(1e3 / statistics.mean(inf_e2e), 3),
+                       "eager_ms_per_slice": round(eager_ms, 4),
+                       "roofline": {"bound": "hbm", "achieved": round(B_ALG_INFER * sl / 1e9, 1), "peak": pk["hbm_gbs"], "unit": "GB/s",
+                                    "frac": round(B_ALG_INFER * sl / 1e9 / pk["hbm_gbs"], 4), "traffic": INFER_TRAFFIC_BYTES,
+                                    "algorithmic_bytes_per_slice": B_ALG_INFER},
+                       "kernel_ms_per_entry": per_entry},
+            "batched": {"config": f"BASELINE configs[4]: {per_gpu} slices per GPU x {world} GPU(s), slices sharded by rank, no "
+                                  f"collective; micro-batch {best[0]} per graph replay", "value": round(slb, 3),
+                        "slices": per_gpu * world, "ms_per_slice_per_gpu": round(tb / reps / per_gpu, 4),
+                        "e2e_value": round(per_gpu * world * reps / (tc * 1e-3), 3),
+                        "h2d_bytes_per_batch": per_gpu * 512 * 512 * 4, "d2h_bytes_per_batch": per_gpu * 512 * 512 * 4,
+                        "roofline": {"bound": "hbm", "achieved": round(B_ALG_INFER * slb / world / 1e9, 1), "peak": pk["hbm_gbs"],
+                                     "unit": "GB/s", "frac": round(B_ALG_INFER * slb / world / 1e9 / pk["hbm_gbs"], 4)},
+                        "timing": "CUDA events around the whole batch, max over ranks, 256 MiB L2 flush between batches"},
+            "value": round(slb, 3), "scaling": "weak (independent slices; no collective)"}
+
+
+def run_gpu_eager_baseline(dev, xd, yd):
+    """The GPU bar (SURVEY §8d Config 3): the reference's algorithm as plain torch ops (the oracle restatement; cuDNN /
+    cuFFT / ATen kernels, torch-eager) on the SAME B200, same weights and inputs, timed with CUDA events.  Never the
+    product path -- a reported baseline like cpu_baseline."""
+    from oracle.train_step import OracleTrainer
+    sd = {k: v.to(dev) for k, v in oracle_state().items()}
+    saved = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark,
+             torch.backends.cudnn.deterministic)
+    out = {"what": "oracle restatement of engine.py:40-55 in torch-eager on cuda (cuDNN/cuFFT/ATen), B=20 64x64, "
+                   "3 warm-up + 8 timed steps, CUDA events", "torch": torch.__version__,
+           "cudnn": torch.backends.cudnn.version()}
+    modes = {"fp32_reference_flags": dict(tf32=False, bench=False, det=True),       # train.py:75-76 + TF32 off (fp32 parity)
+             "tf32_reference_flags": dict(tf32=True, bench=False, det=True),        # train.py:75-76, torch's default conv TF32
+             "tf32_cudnn_benchmark": dict(tf32=True, bench=True, det=False)}        # fastest stock configuration
+    try:
+        for name, m in modes.items():
+            torch.backends.cudnn.allow_tf32 = m["tf32"]
+            torch.backends.cuda.matmul.allow_tf32 = False
+            torch.backends.cudnn.benchmark = m["bench"]
+            torch.backends.cudnn.deterministic = m["det"]
+            random.seed(2024)
+            tr = OracleTrainer(sd)
+            for _ in range(3):
+                tr.step(xd, yd)
+            torch.cuda.synchronize()
+            ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(8)]
+            for s, e in ev:
+                s.record(); tr.step(xd, yd); e.record()
+            torch.cuda.synchronize()
+            ms = statistics.median(s.elapsed_time(e) for s, e in ev)
+            out[name] = {"ms_per_step": round(ms, 3), "patches_per_s": round(BATCH / ms * 1e3, 2)}
+            del tr
+        # generator inference, batch 1, 512x512 (configs[1]) in the same three modes' fastest and fp32
+        from oracle import mtdgan_oracle as O
+        from mtdgan_b200.data import synthetic_pair
+        xs = synthetic_pair(1, 512, seed=4321)[0].to(dev)
+        gsd = {k[len("Generator."):]: v for k, v in sd.items() if k.startswith("Generator.")}
+        for name, tf32 in (("infer512_fp32", False), ("infer512_tf32", True)):
+            torch.backends.cudnn.allow_tf32 = tf32
+            torch.backends.cudnn.benchmark = True
+            torch.backends.cudnn.deterministic = False
+            with torch.no_grad():
+                for _ in range(3):
+                    O.generator_forward(gsd, xs)
+                torch.cuda.synchronize()
+                ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(10)]
+                for s, e in ev:
+                    s.record(); O.generator_forward(gsd, xs); e.record()
+                torch.cuda.synchronize()
+            ms = statistics.median(s.elapsed_time(e) for s, e in ev)
+            out[name] = {"ms_per_slice": round(ms, 3), "slices_per_s": round(1e3 / ms, 2)}
+    finally:
+        (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark,
+         torch.backends.cudnn.deterministic) = saved
+    return out
+
+
+def measure_tf32_peak(dev):
+    """Dense TF32 matmul peak measured the way MEASURED_PEAKS.json measured bf16: torch.matmul 8192^3 with
+    allow_tf32, best of 10 (burst) and back to back for ~2 s (sustained)."""
+    saved = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        n = 8192
+        a = torch.randn(n, n, device=dev)
+        b = torch.randn(n, n, device=dev)
+        for _ in range(3):
+            a @ b
+        torch.cuda.synchronize()
+        best = 1e9
+        for _ in range(10):
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record(); a @ b; e.record()
+            torch.cuda.synchronize()
+            best = min(best, s.elapsed_time(e))
+        reps = max(10, int(2000.0 / best))
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(reps):
+            a @ b
+        e.record()
+        torch.cuda.synchronize()
+        sus = s.elapsed_time(e) / reps
+        fl = 2.0 * n ** 3
+        return {"tf32_tflops": round(fl / best / 1e9, 1), "tf32_tflops_sustained": round(fl / sus / 1e9, 1),
+                "how": "torch.matmul fp32 8192^3, torch.backends.cuda.matmul.allow_tf32=True: best of 10 / back to back ~2 s"}
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = saved
 
 
 # ----------------------------------------------------------------------------------------------------
@@ -409,15 +622,16 @@ def cpu_train_steps(batch, steps, warmup):
 
 
 def run_cpu_baseline():
-    """Bounded sample (~10-30 s of CPU work): 1 warm-up + 2 timed train steps of BASELINE configs[0] (B = 4)."""
-    code = ("import bench, json; t = bench.cpu_train_steps(4, 2, 1); "
+    """Bounded sample (~10-30 s of CPU work) of the SAME workload as the GPU arm and the reference arm: 1 warm-up + 3
+    timed train steps on 20 synthetic 64x64 patches (BASELINE configs[2])."""
+    code = (f"import bench, json; t = bench.cpu_train_steps({BATCH}, 3, 1); "
             "print(json.dumps({'s_per_step': t}))")
     env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
     r = subprocess.run([sys.executable, "-c", code], cwd=ROOT, env=env, capture_output=True, text=True, timeout=900)
     t = json.loads(r.stdout.strip().splitlines()[-1])["s_per_step"]
-    return {"value": round(4 / t, 4), "unit": "patches/s", "cores": os.cpu_count(), "kind": "port",
-            "sample": "oracle port (torch-CPU, all host threads) of the full train step on 4 synthetic 64x64 patches "
-                      "(BASELINE configs[0]): 1 warm-up + 2 timed steps", "s_per_step": round(t, 3)}
+    return {"value": round(BATCH / t, 4), "unit": "patches/s", "cores": os.cpu_count(), "kind": "port",
+            "sample": f"oracle port (torch-CPU, all host threads) of the full train step on {BATCH} synthetic 64x64 patches "
+                      "(BASELINE configs[2], the GPU arm's batch): 1 warm-up + 3 timed steps", "s_per_step": round(t, 3)}
 
 
 def run_reference(args):
@@ -429,30 +643,35 @@ def run_reference(args):
     from oracle.mtdgan_oracle import synthetic_pair
     torch.set_num_threads(os.cpu_count())
     tr = OracleTrainer(oracle_state())
-    # size the per-step sample so that (steps + warmup) steps stay within ~4 minutes
-    x2, y2 = synthetic_pair(2, PATCH, seed=1234)
-    t0 = time.perf_counter(); tr.step(x2, y2); t_cal = time.perf_counter() - t0
-    budget = 240.0 / (args.steps + args.warmup)
+    # The batch is ALWAYS the GPU arm's (20 patches): the ratio the driver computes must compare equal configurations.
+    # What is bounded on a slow host is the NUMBER of timed steps (patches/s is a rate): the first step calibrates, and
+    # the run is cut to what fits ~4 minutes -- never below 2 timed steps -- and says so in `cpu_baseline.sample`.
     batch = BATCH
-    for b in (20, 8, 4, 2, 1):
-        batch = b
-        if t_cal * (0.55 + 0.45 * b / 2) <= budget:       # ~55 % of the CPU step is batch-independent (spectral norm, PCGrad)
-            break
     x, y = synthetic_pair(batch, PATCH, seed=1234)
-    for _ in range(args.warmup):
+    t0 = time.perf_counter(); tr.step(x, y); t_cal = time.perf_counter() - t0
+    warm = max(0, args.warmup - 1)
+    timed_steps = args.steps
+    if t_cal * (args.steps + warm) > 240.0:
+        warm = 0
+        timed_steps = max(2, min(args.steps, int(240.0 / t_cal)))
+        print(f"[bench --impl reference] host too slow for {args.steps} steps of B={batch} ({t_cal:.1f} s/step): "
+              f"timing {timed_steps} steps", file=sys.stderr)
+    for _ in range(warm):
         tr.step(x, y)
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(timed_steps):
         tr.step(x, y)
     dt = time.perf_counter() - t0
-    v = round(batch * args.steps / dt, 4)
+    v = round(batch * timed_steps / dt, 4)
     return {"impl": "reference", "metric": "train patches/s (64x64, bs20/GPU)", "value": v, "unit": "patches/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt / args.steps * 1e3, 2), "higher_is_better": True,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt / timed_steps * 1e3, 2), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "MTD_GAN_Method full train step, CPU oracle port of the reference (torch-CPU, all host threads)",
-                       "sample_batch": batch, "patch": PATCH},
+            "config": {"workload": "MTD_GAN_Method full train step (G + MTL-D + RC/NDS + PCGrad + AdamW), 20 synthetic 1x64x64 "
+                                   "patches (BASELINE configs[2]): CPU oracle port of the reference (torch-CPU, all host threads)",
+                       "global_batch": batch, "patch": PATCH, "parallelism": "cpu"},
             "cpu_baseline": {"value": v, "unit": "patches/s", "cores": os.cpu_count(), "kind": "port",
-                             "sample": f"{args.steps} timed steps of {batch} synthetic 64x64 patches each"},
+                             "sample": f"{timed_steps} timed steps of {batch} synthetic 64x64 patches each"
+                                       + ("" if timed_steps == args.steps else f" (cut from {args.steps}: slow host)")},
             "e2e": {"value": v, "unit": "patches/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
 
 
@@ -464,6 +683,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of the captured CUDA graph")
+    ap.add_argument("--no-gpu-eager", action="store_true", help="skip the torch-eager-on-GPU baseline leg")
+    ap.add_argument("--infer-batch", type=int, default=64, help="512x512 slices per GPU of the batched inference leg")
     args = ap.parse_args()
     claim_stdout()
     if args.impl == "reference":

@@ -167,7 +167,10 @@ int mtd_fft_cols_mix_bwd(const float* spec_x, const float* spec_g, float* spec_o
 
 /* ---- spectral norm (spectral_norm.cu) ------------------------------------------------------------
  * Replaces the forward-pre-hook of nn.utils.spectral_norm (networks.py:181-300) for all layers of a
- * discriminator forward at once.  Tables are device arrays built by the host mirror.              */
+ * discriminator forward at once.  Tables are device arrays built by the host mirror: layer table
+ * int64[L][8] = { W, u, v, rows, cols, u_off, v_off, p_off }; t_ws holds the per-row-block partial sums of W^T u
+ * (sum over layers of ceil(rows / mtd_sn_rows_per_wtu_item()) * cols floats, p_off = the layer's slice), reduced
+ * in a fixed order: u, v, sigma are bit-reproducible and identical on every data-parallel rank.     */
 int mtd_sn_rows_per_wtu_item(void);
 int mtd_sn_power_iter(const void* layer_tab, int n_layers, const void* work_wtu, int n_wtu, const void* work_wv,
                       int n_wv, float* t_ws, long long t_elems, float* s_ws, float* u_snap, float* v_snap,
@@ -212,9 +215,12 @@ int mtd_pcgrad_project(const void* seg_tab, const void* chunk_tab, int n_chunks,
 /* ---- AdamW (adamw.cu) — "next" row: torch.optim.AdamW step of optimizers.py:9 / engine.py:44,52 ------
  * seg table int64[nseg][8]: { param, grad, exp_avg, exp_avg_sq, numel, step counter (device float*), 0, 0 };
  * the step counters are incremented on the device, bias corrections derived in-kernel (graph-capturable).
- * chunk table as PCGrad.                                                                             */
-int mtd_adamw_step(const void* seg_tab, int n_segs, const void* chunk_tab, int n_chunks, float lr, float beta1,
-                   float beta2, float eps, float weight_decay, void* stream);
+ * chunk table as PCGrad.
+ * lr_dev (optional device float*): when non-NULL the learning rate is read from it instead of `lr`, so a captured
+ * CUDA graph follows an lr scheduler.  grad_scale multiplies every gradient on the fly (1/world_size of a summed
+ * all-reduce).  Bias corrections are evaluated in double like torch.optim.AdamW.                       */
+int mtd_adamw_step(const void* seg_tab, int n_segs, const void* chunk_tab, int n_chunks, float lr, const float* lr_dev,
+                   float beta1, float beta2, float eps, float weight_decay, float grad_scale, void* stream);
 
 #ifdef __cplusplus
 }

@@ -5,8 +5,11 @@
 // epilogue (conv_simt.cu / conv_tc.cu `scale`).  Semantics: torch.nn.utils.spectral_norm with
 // n_power_iterations=1, dim=0 (call sites arch/Ours/networks.py:181-300), SURVEY A4.
 //
-// layer table (device, int64[L][8]): { W ptr, u ptr, v ptr, rows, cols, u_off, v_off, 0 } where
-// u_off / v_off index the packed per-call snapshot buffers (and the t / s workspaces).
+// layer table (device, int64[L][8]): { W ptr, u ptr, v ptr, rows, cols, u_off, v_off, p_off } where
+// u_off / v_off index the packed per-call snapshot buffers (and the s workspace) and p_off the layer's slice of the
+// partial-sum workspace of W^T u: [ceil(rows/32)][cols] floats.  W^T u is reduced in a FIXED order (per-CTA partials,
+// then an ordered sum), so u, v and sigma are bit-reproducible from run to run and identical on every data-parallel
+// rank -- no atomics, no memset.
 #include "common.cuh"
 #include "mtdgan_b200.h"
 
@@ -16,7 +19,7 @@ struct SnLayer {
   const float* w;
   float* u;
   float* v;
-  long long rows, cols, uoff, voff, pad;
+  long long rows, cols, uoff, voff, poff;
 };
 static_assert(sizeof(SnLayer) == 64, "layer table entry must be 8 x int64");
 
@@ -34,7 +37,7 @@ __global__ void __launch_bounds__(256) sn_wtu_kernel(const SnLayer* __restrict__
   float acc = 0.f;
 #pragma unroll 8
   for (int r = wk.z; r < r1; ++r) acc = fmaf(__ldg(L.w + (size_t)r * L.cols + col), __ldg(L.u + r), acc);
-  atomicAdd(t_ws + L.voff + col, acc);
+  t_ws[L.poff + (long long)(wk.z / kRowsPerWtu) * L.cols + col] = acc;
 }
 
 // one CTA per layer: v = t / max(|t|, eps)
@@ -43,15 +46,22 @@ __global__ void __launch_bounds__(256) sn_norm_v_kernel(const SnLayer* __restric
   mtd_pdl_prologue();
   __shared__ float sh[32];
   const SnLayer L = tab[blockIdx.x];
-  const float* t = t_ws + L.voff;
+  const float* part = t_ws + L.poff;
+  const int nrb = (int)((L.rows + kRowsPerWtu - 1) / kRowsPerWtu);
+  float* t = v_snap + L.voff;                      // t = W^T u staged in the snapshot slot, normalised in place below
   float ss = 0.f;
-  for (int k = threadIdx.x; k < L.cols; k += blockDim.x) { float x = t[k]; ss = fmaf(x, x, ss); }
+  for (int k = threadIdx.x; k < L.cols; k += blockDim.x) {
+    float x = 0.f;
+    for (int rb = 0; rb < nrb; ++rb) x += part[(long long)rb * L.cols + k];      // fixed order
+    t[k] = x;
+    ss = fmaf(x, x, ss);
+  }
   ss = block_sum(ss, sh, true);
   const float inv = 1.f / fmaxf(sqrtf(ss), eps);
-  for (int k = threadIdx.x; k < L.cols; k += blockDim.x) {
+  for (int k = threadIdx.x; k < L.cols; k += blockDim.x) {     // each thread re-reads only what it wrote
     float x = t[k] * inv;
     L.v[k] = x;
-    v_snap[L.voff + k] = x;
+    t[k] = x;
   }
 }
 
@@ -127,7 +137,6 @@ int mtd_sn_power_iter(const void* layer_tab, int n_layers, const void* work_wtu,
   const SnLayer* tab = reinterpret_cast<const SnLayer*>(layer_tab);
   if (update) {
     MTD_REQUIRE(work_wtu && t_ws && n_wtu > 0 && t_elems > 0);
-    MTD_CUDA(cudaMemsetAsync(t_ws, 0, (size_t)t_elems * sizeof(float), st));
     mtd_launch(sn_wtu_kernel, n_wtu, 256, 0, st, tab, reinterpret_cast<const int4*>(work_wtu), t_ws);
     MTD_CHECK_LAUNCH();
     mtd_launch(sn_norm_v_kernel, n_layers, 256, 0, st, tab, t_ws, v_snap, eps);

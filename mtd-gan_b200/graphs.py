@@ -12,6 +12,8 @@ reads.
 """
 from __future__ import annotations
 
+import random
+
 import torch
 
 from . import _ext, ops
@@ -54,8 +56,39 @@ class GraphedTrainStep:
         self.opt_G.step()
         return d_losses.detach(), d_det, g_loss.detach(), g_det
 
-    def capture(self, x, y, warmup: int = 3):
+    # ---- training state that the warm-up steps of a capture must not disturb -----------------------------------
+    def _snapshot(self):
+        opt = []
+        for o in (self.opt_D, self.opt_G):
+            opt.append({p: {k: (v.detach().clone() if torch.is_tensor(v) else v) for k, v in st.items()}
+                        for p, st in o.state.items()})
+        return {"model": {k: v.detach().clone() for k, v in self.model.state_dict().items()}, "opt": opt,
+                "py": random.getstate(), "cpu": torch.get_rng_state(), "cuda": torch.cuda.get_rng_state()}
+
+    @torch.no_grad()
+    def _restore(self, snap):
+        sd = self.model.state_dict()
+        for k, v in snap["model"].items():
+            sd[k].copy_(v)                         # in place: parameter storage (and the graph's pointers) stay put
+        for p in self.model.parameters():
+            torch.autograd.graph.increment_version(p)
+        for o, saved in zip((self.opt_D, self.opt_G), snap["opt"]):
+            for p, st in o.state.items():
+                old = saved.get(p)
+                for k, v in st.items():
+                    if torch.is_tensor(v):         # state created by the warm-up steps goes back to its initial zeros
+                        v.zero_() if old is None else v.copy_(old[k])
+        random.setstate(snap["py"])
+        torch.set_rng_state(snap["cpu"])
+        torch.cuda.set_rng_state(snap["cuda"])
+
+    def capture(self, x, y, warmup: int = 3, preserve_state: bool = True):
+        """Warm up on a side stream (lazy one-time work: table builds, workspace allocation), then record one step.
+        preserve_state: weights, spectral-norm buffers, optimizer moments / step counters, Python `random` and the torch
+        RNGs are restored afterwards, so the first replay is training step 1 exactly as an eager run would execute it
+        (the warm-up steps are real optimizer steps on the capture batch and would otherwise shift the trajectory)."""
         self.x, self.y = x.clone(), y.clone()
+        snap = self._snapshot() if preserve_state else None
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
@@ -71,6 +104,9 @@ class GraphedTrainStep:
                 self.out = self.eager_step(self.x, self.y)
         finally:
             self.trace = _ext.stop_trace()        # (entry point, args) of every library call in the captured step
+        if snap is not None:
+            self._restore(snap)
+            torch.cuda.synchronize()
         return self
 
     def family_graph(self, names):
@@ -94,5 +130,7 @@ class GraphedTrainStep:
         self.x.copy_(x, non_blocking=True)
         self.y.copy_(y, non_blocking=True)
         self.wm.method.draw_orders_host()          # same `random` consumption as the reference's shuffles
+        self.opt_D.sync_lr_host()                  # lr schedulers: the captured copy nodes re-read the pinned scalars
+        self.opt_G.sync_lr_host()
         self.graph.replay()
         return self.out

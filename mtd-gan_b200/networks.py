@@ -144,12 +144,13 @@ class _SNState:
     def __init__(self, mods: List[nn.Module], device):
         rows_per = _ext.load().mtd_sn_rows_per_wtu_item()
         tab, wtu, wv = [], [], []
-        uoff = voff = 0
+        uoff = voff = poff = 0
         self.slices = []
         for i, m in enumerate(mods):
             w = m.weight_orig
             rows, cols = w.shape[0], w.numel() // w.shape[0]
-            tab.append([w.data_ptr(), m.weight_u.data_ptr(), m.weight_v.data_ptr(), rows, cols, uoff, voff, 0])
+            tab.append([w.data_ptr(), m.weight_u.data_ptr(), m.weight_v.data_ptr(), rows, cols, uoff, voff, poff])
+            poff += ((rows + rows_per - 1) // rows_per) * cols           # partial sums of W^T u, one row block each
             for c0 in range(0, cols, 256):
                 for r0 in range(0, rows, rows_per):
                     wtu.append([i, c0, r0, 0])
@@ -164,7 +165,8 @@ class _SNState:
         self.tab = torch.tensor(tab, dtype=torch.int64).to(device)
         self.wtu = torch.tensor(wtu, dtype=torch.int32).to(device)
         self.wv = torch.tensor(wv, dtype=torch.int32).to(device)
-        self.t_ws = torch.empty(voff, dtype=torch.float32, device=device)
+        self.t_ws = torch.empty(poff, dtype=torch.float32, device=device)
+        self.t_elems = poff
         self.s_ws = torch.empty(uoff, dtype=torch.float32, device=device)
 
     @staticmethod
@@ -250,7 +252,7 @@ class Multi_Task_Discriminator_Skip(nn.Module):
         v_snap = torch.empty(groups, s.v_total, dtype=torch.float32, device=device)
         inv_sigma = torch.empty(groups, s.n_layers, dtype=torch.float32, device=device)
         for g in range(groups):
-            call("mtd_sn_power_iter", ptr(s.tab), s.n_layers, ptr(s.wtu), s.n_wtu, ptr(s.wv), s.n_wv, fptr(s.t_ws), s.v_total,
+            call("mtd_sn_power_iter", ptr(s.tab), s.n_layers, ptr(s.wtu), s.n_wtu, ptr(s.wv), s.n_wv, fptr(s.t_ws), s.t_elems,
                  fptr(s.s_ws), fptr(u_snap[g]), fptr(v_snap[g]), fptr(inv_sigma[g]), 1 if self.training else 0, 1e-12, stream())
         inv_t = inv_sigma.t().contiguous() if groups > 1 else inv_sigma.reshape(s.n_layers, 1)     # (layers, groups)
         out = {}

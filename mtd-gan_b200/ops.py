@@ -32,7 +32,13 @@ _pack_cache: dict = {}        # id(weight object) -> {(kind, transposed, stride)
 
 def clear_pack_cache():
     """Invalidate every packed copy (used before CUDA-graph capture so the packing kernels are captured too).  The
-    registry of (weight, kind, cfg) stays, so `repack_stale()` can rebuild everything in a few batched launches."""
+    registry of (weight, kind, cfg) stays, so `repack_stale()` can rebuild everything in a few batched launches.
+
+    Packed copies are keyed on the parameter's version counter and storage pointer.  Writes through `p.data`
+    (`p.data.normal_()`, weight clipping, EMA swaps) do NOT move the version counter: call this function (exported as
+    `mtdgan_b200.invalidate_weight_caches()`) after such a write, or write under `torch.no_grad()` on `p` itself.
+    Construction-time `.data` init (the reference's `__init_weights`) and `load_state_dict` need nothing: the first
+    runs before any pack exists, the second bumps the version."""
     for slot in _pack_cache.values():
         for key, ent in list(slot.items()):
             slot[key] = (None,) + tuple(ent[1:])
@@ -497,7 +503,10 @@ class ConvFn(Function):
         # spectrally-normalised layer inside a deferred-finishing pass: the correction coefficient <G_g, W~_g> of every
         # batched call g comes out of the activation-backward pass itself (mtd_act_bwd_sn) -- no dot pass later
         zw = None
-        if (want_w and inv_sigma is not None and _finish_queue is not None and cfg.post_act == ACT_NONE and not ctx.has_add
+        # Deferred finishing hands autograd a dw tensor that is only filled when the context exits.  That is sound while
+        # nothing inspects gradients mid-pass; anomaly mode (NaN checks on every backward output) finishes immediately.
+        deferred = _finish_queue is not None and not torch.is_anomaly_enabled()
+        if (want_w and inv_sigma is not None and deferred and cfg.post_act == ACT_NONE and not ctx.has_add
                 and cfg.pre_act in (ACT_NONE, ACT_LEAKY) and cfg.cout % 4 == 0 and G <= 4):
             zw = _zw_alloc(G, dy)
         if zw is not None:
@@ -535,7 +544,7 @@ class ConvFn(Function):
                 for g in range(G):          # one packed weight gradient per batched reference call (own u, v, sigma)
                     gp = _empty((weight.numel(),), dy)
                     if G == 1:
-                        if _WGRAD_SIDE and _finish_queue is not None:
+                        if _WGRAD_SIDE and deferred:
                             _on_side_stream(lambda gp=gp: _conv_wgrad_launch(x1, x2, dz, gp, B, H, W, C1, C2, cfg), x1, x2, dz, gp)
                         else:
                             _conv_wgrad_launch(x1, x2, dz, gp, B, H, W, C1, C2, cfg)
@@ -545,7 +554,7 @@ class ConvFn(Function):
                         sl = slice(g * Bg, (g + 1) * Bg)
                         _conv_wgrad_launch(x1[sl], None if x2 is None else x2[sl], dz[sl], gp, Bg, H, W, C1, C2, cfg)
                         insts.append((gp, weight.detach(), u[g], v[g], inv_sigma[g:g + 1], cfg, 0, 0))
-            if _finish_queue is not None:
+            if deferred:
                 grp = _finish_queue.get(weight.data_ptr())
                 if grp is None:
                     dw = torch.empty_like(weight)

@@ -16,6 +16,26 @@ class FusedAdamW(torch.optim.Optimizer):
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2):
         defaults = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay)
         super().__init__(params, defaults)
+        self.grad_scale = 1.0            # multiplies every gradient inside the kernel (1/world of a summed all-reduce)
+        self._lr_bufs = {}               # group index -> (pinned host float32[1], device float32[1])
+
+    # The learning rate travels through device memory: step() writes group['lr'] into a pinned host scalar and
+    # enqueues its copy to a device scalar the kernel reads.  Captured into a CUDA graph that copy is a memcpy node
+    # re-reading the pinned scalar on every replay, so `sync_lr_host()` before a replay is all an lr scheduler
+    # (train.py steps scheduler_D / scheduler_G every epoch) needs -- betas / eps / weight decay stay launch constants.
+    def _lr_buffers(self, gi, device):
+        ent = self._lr_bufs.get(gi)
+        if ent is None or ent[1].device != device:
+            ent = (torch.zeros(1, dtype=torch.float32).pin_memory(), torch.zeros(1, dtype=torch.float32, device=device))
+            self._lr_bufs[gi] = ent
+        return ent
+
+    def sync_lr_host(self):
+        """Refresh the pinned learning-rate scalars from param_groups (call before replaying a captured step)."""
+        for gi, group in enumerate(self.param_groups):
+            ent = self._lr_bufs.get(gi)
+            if ent is not None:
+                ent[0][0] = float(group["lr"])
 
     @torch.no_grad()
     def step(self, closure=None):
@@ -23,7 +43,7 @@ class FusedAdamW(torch.optim.Optimizer):
         if closure is not None:
             with torch.enable_grad():
                 loss = closure()
-        for group in self.param_groups:
+        for gi, group in enumerate(self.param_groups):
             b1, b2 = group["betas"]
             rows, numels, keep = [], [], []
             device = None
@@ -51,9 +71,14 @@ class FusedAdamW(torch.optim.Optimizer):
                 continue
             seg = _ext.device_table(rows, torch.int64, device)
             chunks, n_chunks = _chunk_table(numels, device)
-            lr = group["lr"]
-            call("mtd_adamw_step", ptr(seg), len(rows), ptr(chunks), n_chunks, float(lr), float(b1), float(b2),
-                 float(group["eps"]), float(group["weight_decay"]), stream())
+            lr = float(group["lr"])
+            lr_dev = None
+            if torch.cuda.is_current_stream_capturing():      # eager launches take the host scalar by value
+                lr_host, lr_dev = self._lr_buffers(gi, device)
+                lr_host[0] = lr
+                lr_dev.copy_(lr_host, non_blocking=True)
+            call("mtd_adamw_step", ptr(seg), len(rows), ptr(chunks), n_chunks, lr, ptr(lr_dev), float(b1), float(b2),
+                 float(group["eps"]), float(group["weight_decay"]), float(self.grad_scale), stream())
             for p in group["params"]:
                 if p.grad is not None:
                     torch.autograd.graph.increment_version(p)      # the kernel wrote p in place (pack caches key on it)

@@ -219,14 +219,15 @@ def charbonnier(x: Tensor, y: Tensor, eps: float = 1e-3) -> Tensor:
 _GAUSS_1D = [0.05, 0.25, 0.4, 0.25, 0.05]     # losses.py:116
 
 
-def _gauss_kernel() -> Tensor:
+def _gauss_kernel(like: Optional[Tensor] = None) -> Tensor:
     k = torch.tensor([_GAUSS_1D], dtype=torch.float32)
-    return torch.matmul(k.t(), k)[None, None]   # losses.py:117 (1 gray channel)
+    k = torch.matmul(k.t(), k)[None, None]      # losses.py:117 (1 gray channel)
+    return k if like is None else k.to(device=like.device, dtype=like.dtype)   # losses.py:118-119 (kernel follows the device)
 
 
 def _conv_gauss(img: Tensor) -> Tensor:
     """losses.py:122-125"""
-    return F.conv2d(F.pad(img, (2, 2, 2, 2), mode="replicate"), _gauss_kernel())
+    return F.conv2d(F.pad(img, (2, 2, 2, 2), mode="replicate"), _gauss_kernel(img))
 
 
 def laplacian(img: Tensor) -> Tensor:

@@ -33,7 +33,7 @@ class OracleTrainer:
         dm = list(dropout_masks) if dropout_masks is not None else None
         if dm is None:                                       # dropout drawn like nn.Dropout(0.3) would
             B = x.shape[0]
-            dm = [torch.nn.functional.dropout(torch.ones(B, 512), 0.3, True) for _ in range(5)]
+            dm = [torch.nn.functional.dropout(torch.ones(B, 512, device=x.device), 0.3, True) for _ in range(5)]
         # ---- discriminator (engine.py:40-46)
         self.opt_D.zero_grad(set_to_none=True)
         d_losses, d_det = O.d_loss(self.sd, x, y, True, dm[:4])

@@ -59,7 +59,7 @@ with torch.no_grad():
     x64 = O.synthetic_pair(2, 64, seed=11)[0]
     save("gen_fwd_64.pt", {"out": m.Generator(x64)})
     x512 = O.synthetic_pair(1, 512, seed=12)[0]
-    save("gen_fwd_512.pt", {"out": m.Generator(x512).half()})     # fp16 storage: 512 KiB; compare at 1e-3
+    save("gen_fwd_512.pt", {"out": m.Generator(x512)})            # fp32 storage (1 MiB): compared at 1e-4
 
 # 4. stand-alone FFT_ConvBlock forward + backward ---------------------------------------------------
 torch.manual_seed(5)

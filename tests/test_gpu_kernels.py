@@ -252,7 +252,7 @@ def test_spectral_norm_conv_matches_torch():
     u_snap = torch.empty(st.u_total, device=DEV)
     v_snap = torch.empty(st.v_total, device=DEV)
     inv = torch.empty(1, device=DEV)
-    call("mtd_sn_power_iter", ptr(st.tab), 1, ptr(st.wtu), st.n_wtu, ptr(st.wv), st.n_wv, fptr(st.t_ws), st.v_total,
+    call("mtd_sn_power_iter", ptr(st.tab), 1, ptr(st.wtu), st.n_wtu, ptr(st.wv), st.n_wv, fptr(st.t_ws), st.t_elems,
          fptr(st.s_ws), fptr(u_snap), fptr(v_snap), fptr(inv), 1, 1e-12, stream())
     xc = nhwc(x.float()).to(DEV).requires_grad_(True)
     cfg = ops.ConvCfg(cin=16, cout=24, pre_act=ops.ACT_LEAKY)
@@ -481,7 +481,7 @@ def test_spectral_norm_grouped_deferred_matches_two_calls():
     v_snap = torch.empty(2, st.v_total, device=DEV)
     inv = torch.empty(2, 1, device=DEV)
     for g in range(2):
-        call("mtd_sn_power_iter", ptr(st.tab), 1, ptr(st.wtu), st.n_wtu, ptr(st.wv), st.n_wv, fptr(st.t_ws), st.v_total,
+        call("mtd_sn_power_iter", ptr(st.tab), 1, ptr(st.wtu), st.n_wtu, ptr(st.wv), st.n_wv, fptr(st.t_ws), st.t_elems,
              fptr(st.s_ws), fptr(u_snap[g]), fptr(v_snap[g]), fptr(inv[g]), 1, 1e-12, stream())
     xc = nhwc(torch.cat([xa, xb]).float()).to(DEV)
     cfg = ops.ConvCfg(cin=32, cout=64, pre_act=ops.ACT_LEAKY)
