@@ -222,6 +222,20 @@ int mtd_pcgrad_project(const void* seg_tab, const void* chunk_tab, int n_chunks,
 int mtd_adamw_step(const void* seg_tab, int n_segs, const void* chunk_tab, int n_chunks, float lr, const float* lr_dev,
                    float beta1, float beta2, float eps, float weight_decay, float grad_scale, void* stream);
 
+/* ---- data edge (data_edge.cu) — "next" row: the `window_patch` / `window` transform chains of
+ * create_datasets/Mayo.py:117-136, 158-167 on int16 HU slices resident in HBM.
+ * mtd_hu_foreground_bbox: bbox int32[S][4] = {y0, y1, x0, x1} (half-open) of {hu > a_min} per slice (CropForegroundd with
+ *   select_fn x > 0 after windowing), {0,0,0,0} for an empty slice.
+ * mtd_window_crop_patches: patch table int32[n][8] = {slice, oy, ox, by0, by1, bx0, bx1, aug} — (oy, ox) = slice
+ *   coordinates of crop pixel (0,0) (negative inside SpatialPadd padding), [by0,by1) x [bx0,bx1) the foreground box (pixels
+ *   outside it are padding zeros), aug bits 0-1 = RandRotate90d k, bit 2 = RandFlipd over both axes; writes the windowed
+ *   low-dose / full-dose patches x, y (n, roi, roi) float32.
+ * mtd_window_slices: ScaleIntensityRanged(a_min, a_max, 0, 1, clip=True) of whole slices (valid / test transform).  */
+int mtd_hu_foreground_bbox(const short* hu, int S, int H, int W, float a_min, int* bbox, void* stream);
+int mtd_window_crop_patches(const short* lo, const short* hi, int S, int H, int W, const int* patch_tab, int n_patches, int roi,
+                            float a_min, float a_max, float* x, float* y, void* stream);
+int mtd_window_slices(const short* hu, long long n, float a_min, float a_max, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -114,6 +114,46 @@ class ResFFT_Generator(nn.Module):
         return to_nchw(t)
 
 
+class REDCNN_Generator(nn.Module):
+    """networks.py:478-505: 11 conv + ReLU encoders and 11 ConvTranspose decoders with additive skips, no
+    Res-FFT-Conv blocks (the generator of the ablation rows `Ablation_CLS` ... `Ablation_CLS_SEG_REC_NDS_RC`).
+    Init (:490-496) covers every module whose class name contains 'Conv' -- ConvTranspose2d included, unlike
+    ResFFT_Generator's."""
+
+    def __init__(self, in_channels=1, out_channels=96, num_layers=10, kernel_size=5, padding=0):
+        super().__init__()
+        enc = [nn.Conv2d(in_channels, out_channels, kernel_size=kernel_size, stride=1, padding=padding)]
+        dec = [nn.ConvTranspose2d(out_channels, in_channels, kernel_size=kernel_size, stride=1, padding=padding)]
+        for _ in range(num_layers):
+            enc.append(nn.Conv2d(out_channels, out_channels, kernel_size=kernel_size, stride=1, padding=padding))
+            dec.append(nn.ConvTranspose2d(out_channels, out_channels, kernel_size=kernel_size, stride=1, padding=padding))
+        self.encoder = nn.ModuleList(enc)
+        self.decoder = nn.ModuleList(dec)
+        self._geom = (in_channels, out_channels, num_layers, kernel_size, padding)
+        for m in self.modules():
+            if type(m).__name__.find('Conv') != -1:
+                m.weight.data.normal_(0, 0.01)
+                if hasattr(m.bias, 'data'):
+                    m.bias.data.fill_(0)
+
+    def forward(self, x: torch.Tensor):
+        cin, c, nl, k, p = self._geom
+        if 2 * p != k - 1:
+            raise _ext.MtdError("B200 path needs a size-preserving conv (2*padding == kernel_size-1), e.g. k=3, p=1")
+        x = check_input(x, "REDCNN_Generator")
+        t = to_nhwc(x)
+        residuals = []
+        for i, m in enumerate(self.encoder):                                  # :499-502
+            residuals.append(t)
+            t = conv(t, m.weight, m.bias, ConvCfg(cin=m.in_channels, cout=m.out_channels, kh=k, kw=k, stride=1, pad=p,
+                                                  pre_act=ACT_RELU))
+        for i in range(len(self.decoder) - 1, -1, -1):                        # :503-504 (both lists reversed)
+            m = self.decoder[i]
+            t = conv(t, m.weight, m.bias, ConvCfg(cin=m.in_channels, cout=m.out_channels, kh=k, kw=k, stride=1, pad=p,
+                                                  transposed=1, post_act=ACT_RELU), add1=residuals[i])
+        return to_nchw(t)
+
+
 # ================================================================================================
 # Discriminator
 # ================================================================================================
@@ -175,7 +215,19 @@ class _SNState:
                 + tuple(m.weight_v.data_ptr() for m in mods))
 
 
-class Multi_Task_Discriminator_Skip(nn.Module):
+class _UNetDiscriminator(nn.Module):
+    """Shared U-Net discriminator body of `Multi_Task_Discriminator_Skip` (networks.py:177-474) and of the five partial
+    ablation discriminators (`CLS_` :507-609, `SEG_` :611-764, `CLS_SEG_` :766-932, `CLS_REC_` :934-1101, `SEG_REC_`
+    :1103-1320): spectrally-normalised encoder + bottleneck, then any of the CLS head (flatten, c_fc, dropout), the SEG
+    decoder (bilinear up + skip cat + 2 convs, x6) and the REC decoder (UpsampleBlock + skip cat + 2 convs, x6), then the
+    output heads.  Subclasses only state WHICH parts exist and what `forward` returns; module registration order
+    (it fixes the state_dict key order and the RNG order of the spectral-norm u/v draws) follows the reference.
+    """
+    _HAS_CLS = _HAS_SEG = _HAS_REC = True
+    _SEG_PREFIX = "s_"                       # SEG_Discriminator registers its decoder as up{i} / dconv{i}{j}
+    _HEADS = ("enc_out", "dec_out", "rec_out")
+    _RETURNS = ("enc", "dec", "rec")
+
     def __init__(self, in_channels, out_channels):
         super().__init__()
         c = out_channels
@@ -199,46 +251,33 @@ class Multi_Task_Discriminator_Skip(nn.Module):
         reg("bconv1", sn(nn.Conv2d(8 * c, 8 * c, kernel_size=1, stride=1, padding=0))); reg("brelu1", act(), False)
         reg("bconv2", sn(nn.Conv2d(8 * c, 8 * c, kernel_size=1, stride=1, padding=0))); reg("brelu2", act(), False)
         # CLS Dec (:224-227)
-        self.c_flatten = nn.Flatten()
-        reg("c_fc", sn(nn.Linear(512, 512, True)))
-        self.c_relu = act()
-        self.c_drop = nn.Dropout(p=0.3)
+        if self._HAS_CLS:
+            self.c_flatten = nn.Flatten()
+            reg("c_fc", sn(nn.Linear(512, 512, True)))
+            self.c_relu = act()
+            self.c_drop = nn.Dropout(p=0.3)
         # SEG / REC Dec (:230-301)
         dec = [(16 * c, 8 * c), (16 * c, 8 * c), (16 * c, 4 * c), (8 * c, 2 * c), (4 * c, c), (2 * c, 1)]
         ups = [8 * c, 8 * c, 8 * c, 4 * c, 2 * c, c]
-        for i, (a, b) in enumerate(dec, 1):
-            reg(f"s_up{i}", nn.Upsample(scale_factor=2, mode='bilinear', align_corners=False), False)
-            reg(f"s_dconv{i}1", conv3(a, b)); reg(f"s_drelu{i}1", act(), False)
-            reg(f"s_dconv{i}2", conv3(b, b)); reg(f"s_drelu{i}2", act(), False)
-        for i, ((a, b), uc) in enumerate(zip(dec, ups), 1):
-            reg(f"r_up{i}", UpsampleBlock(scale=2, input_channels=uc, output_channels=uc), False)
-            reg(f"r_dconv{i}1", conv3(a, b)); reg(f"r_drelu{i}1", act(), False)
-            reg(f"r_dconv{i}2", conv3(b, b)); reg(f"r_drelu{i}2", act(), False)
-        # Heads (:304-306)
-        self.enc_out = nn.Linear(512, 1)
-        self.dec_out = nn.Conv2d(in_channels, 1, 1)
-        self.rec_out = nn.Conv2d(in_channels, 1, 1)
+        sp = self._SEG_PREFIX
+        if self._HAS_SEG:
+            for i, (a, b) in enumerate(dec, 1):
+                reg(f"{sp}up{i}", nn.Upsample(scale_factor=2, mode='bilinear', align_corners=False), False)
+                reg(f"{sp}dconv{i}1", conv3(a, b)); reg(f"{sp}drelu{i}1", act(), False)
+                reg(f"{sp}dconv{i}2", conv3(b, b)); reg(f"{sp}drelu{i}2", act(), False)
+        if self._HAS_REC:
+            for i, ((a, b), uc) in enumerate(zip(dec, ups), 1):
+                reg(f"r_up{i}", UpsampleBlock(scale=2, input_channels=uc, output_channels=uc), False)
+                reg(f"r_dconv{i}1", conv3(a, b)); reg(f"r_drelu{i}1", act(), False)
+                reg(f"r_dconv{i}2", conv3(b, b)); reg(f"r_drelu{i}2", act(), False)
+        # Heads (:304-306) -- SEG_Discriminator registers an `enc_out` it never uses (:695); kept for key parity
+        for h in self._HEADS:
+            setattr(self, h, nn.Linear(512, 1) if h == "enc_out" else nn.Conv2d(in_channels, 1, 1))
         self._sn_state: Optional[_SNState] = None
         _normal_init(self)
 
-    # ---- parameter partitions (networks.py:318-380) -------------------------------------------------
     def _params_of(self, names):
         return chain(*[getattr(self, n).parameters() for n in names])
-
-    def shared_parameters(self) -> Iterator[nn.parameter.Parameter]:
-        names = []
-        for i in range(1, 7):
-            names += [f"conv{i}1", f"conv{i}2", f"down{i}"]
-        return self._params_of(names + ["bconv1", "bconv2"])
-
-    def task_specific_parameters(self) -> Iterator[nn.parameter.Parameter]:
-        names = [f"s_dconv{i}{j}" for i in range(1, 7) for j in (1, 2)]
-        for i in range(1, 7):
-            names += [f"r_up{i}", f"r_dconv{i}1", f"r_dconv{i}2"]
-        return self._params_of(names + ["enc_out", "dec_out", "rec_out"])
-
-    def last_shared_parameters(self) -> Iterator[nn.parameter.Parameter]:
-        return self.bconv2.parameters()
 
     # ---- spectral norm -------------------------------------------------------------------------------
     def _spectral_norm_step(self, device, groups: int = 1):
@@ -262,8 +301,8 @@ class Multi_Task_Discriminator_Skip(nn.Module):
         return out
 
     # ---- forward (networks.py:383-474) -----------------------------------------------------------------
-    def forward(self, input, weight_grads: bool = True, need_rec: bool = True, groups: int = 1):
-        """Returns (x_enc (B,1), x_dec (B,1,64,64), x_rec (B,1,64,64)).
+    def _forward_parts(self, input, weight_grads: bool = True, need=("enc", "dec", "rec"), groups: int = 1):
+        """-> dict with the requested outputs among x_enc (B,1), x_dec (B,1,64,64), x_rec (B,1,64,64).
 
         groups > 1: `input` is the concatenation along the batch of `groups` inputs the reference would pass in
         `groups` consecutive calls (d_loss: D(real) then D(fake), networks.py:1959-1960).  Spectral norm runs one
@@ -272,12 +311,12 @@ class Multi_Task_Discriminator_Skip(nn.Module):
         order -- results equal the separate calls, with half the kernel launches and twice the rows per launch.
 
         weight_grads=False treats the weights as constants (used by g_loss, where the reference's D weight
-        gradients are dead work wiped by the next zero_grad, engine.py:40-41,51); need_rec=False skips the
-        restoration decoder when the caller discards x_rec (networks.py:1969-1970, 1996) and returns None.
+        gradients are dead work wiped by the next zero_grad, engine.py:40-41,51); decoders whose output is not in
+        `need` are skipped (networks.py:1969-1970, 1996 discard x_rec).
         """
-        x = check_input(input, "Multi_Task_Discriminator_Skip")
+        x = check_input(input, type(self).__name__)
         if x.dim() != 4 or x.shape[2] != 64 or x.shape[3] != 64:
-            raise RuntimeError(f"Multi_Task_Discriminator_Skip expects (B, C, 64, 64) inputs, got {tuple(x.shape)}")
+            raise RuntimeError(f"{type(self).__name__} expects (B, C, 64, 64) inputs, got {tuple(x.shape)}")
         if groups < 1 or x.shape[0] % groups:
             raise RuntimeError(f"batch {x.shape[0]} is not divisible into {groups} groups")
         sn = self._spectral_norm_step(x.device, groups)
@@ -306,39 +345,113 @@ class Multi_Task_Discriminator_Skip(nn.Module):
             t = layer(f"down{i}", t, act=ACT_NONE)          # no activation after down* (:387-407)
         t = layer("bconv1", t)
         x_bot = layer("bconv2", t)                          # (B,1,1,512)
+        out = {}
+        B = x.shape[0]
 
         # CLS decoder (:414-417, :470)
-        h = layer("c_fc", x_bot)
-        B = x.shape[0]
-        if self.training and self.c_drop.p > 0:
-            masks = []
-            for _ in range(groups):             # one draw per reference call, in call order (RNG parity)
-                mask = _dropout_mask_provider(B // groups, 512, x.device) if _dropout_mask_provider is not None else None
-                if mask is None:
-                    mask = F.dropout(torch.ones(B // groups, 512, device=x.device), self.c_drop.p, True)
-                masks.append(mask.to(torch.float32))
-            mask = masks[0] if groups == 1 else torch.cat(masks, 0)
-            h = MulConstFn.apply(h, mask.contiguous())
-        x_enc = layer("enc_out", h, act=ACT_NONE).reshape(B, 1)
+        if self._HAS_CLS and "enc" in need:
+            h = layer("c_fc", x_bot)
+            if self.training and self.c_drop.p > 0:
+                masks = []
+                for _ in range(groups):             # one draw per reference call, in call order (RNG parity)
+                    mask = _dropout_mask_provider(B // groups, 512, x.device) if _dropout_mask_provider is not None else None
+                    if mask is None:
+                        mask = F.dropout(torch.ones(B // groups, 512, device=x.device), self.c_drop.p, True)
+                    masks.append(mask.to(torch.float32))
+                mask = masks[0] if groups == 1 else torch.cat(masks, 0)
+                h = MulConstFn.apply(h, mask.contiguous())
+            out["enc"] = layer("enc_out", h, act=ACT_NONE).reshape(B, 1)
 
         # SEG decoder (:420-442, :471)
-        t = x_bot
-        for i in range(1, 7):
-            t = Upsample2xFn.apply(t)
-            t = layer(f"s_dconv{i}1", t, x2=skips[6 - i])
-            t = layer(f"s_dconv{i}2", t)
-        x_dec = to_nchw(layer("dec_out", t, act=ACT_NONE))
+        if self._HAS_SEG and "dec" in need:
+            sp = self._SEG_PREFIX
+            t = x_bot
+            for i in range(1, 7):
+                t = Upsample2xFn.apply(t)
+                t = layer(f"{sp}dconv{i}1", t, x2=skips[6 - i])
+                t = layer(f"{sp}dconv{i}2", t)
+            out["dec"] = to_nchw(layer("dec_out", t, act=ACT_NONE))
 
         # REC decoder (:445-467, :472)
-        x_rec = None
-        if need_rec:
+        if self._HAS_REC and "rec" in need:
             t = x_bot
             for i in range(1, 7):
                 t = getattr(self, f"r_up{i}").forward_nhwc(t, freeze=not weight_grads)
                 t = layer(f"r_dconv{i}1", t, x2=skips[6 - i])
                 t = layer(f"r_dconv{i}2", t)
-            x_rec = to_nchw(layer("rec_out", t, act=ACT_NONE))
-        return x_enc, x_dec, x_rec
+            out["rec"] = to_nchw(layer("rec_out", t, act=ACT_NONE))
+        return out
+
+    def forward(self, input, weight_grads: bool = True, groups: int = 1):
+        parts = self._forward_parts(input, weight_grads, self._RETURNS, groups)
+        res = tuple(parts[k] for k in self._RETURNS)
+        return res[0] if len(res) == 1 else res
+
+
+class Multi_Task_Discriminator_Skip(_UNetDiscriminator):
+    """networks.py:177-474: all three heads; `forward(input) -> (x_enc, x_dec, x_rec)`."""
+
+    # ---- parameter partitions (networks.py:318-380) -------------------------------------------------
+    def shared_parameters(self) -> Iterator[nn.parameter.Parameter]:
+        names = []
+        for i in range(1, 7):
+            names += [f"conv{i}1", f"conv{i}2", f"down{i}"]
+        return self._params_of(names + ["bconv1", "bconv2"])
+
+    def task_specific_parameters(self) -> Iterator[nn.parameter.Parameter]:
+        names = [f"s_dconv{i}{j}" for i in range(1, 7) for j in (1, 2)]
+        for i in range(1, 7):
+            names += [f"r_up{i}", f"r_dconv{i}1", f"r_dconv{i}2"]
+        return self._params_of(names + ["enc_out", "dec_out", "rec_out"])
+
+    def last_shared_parameters(self) -> Iterator[nn.parameter.Parameter]:
+        return self.bconv2.parameters()
+
+    def forward(self, input, weight_grads: bool = True, need_rec: bool = True, groups: int = 1):
+        """Returns (x_enc (B,1), x_dec (B,1,64,64), x_rec (B,1,64,64)); need_rec=False skips the restoration decoder
+        when the caller discards x_rec and returns None in its place.  See `_forward_parts` for `groups` /
+        `weight_grads`."""
+        need = ("enc", "dec", "rec") if need_rec else ("enc", "dec")
+        p = self._forward_parts(input, weight_grads, need, groups)
+        return p["enc"], p["dec"], p.get("rec")
+
+
+# ---- partial discriminators of the ablation study (networks.py:507-1320) ---------------------------------------
+class CLS_Discriminator(_UNetDiscriminator):
+    """networks.py:507-609 -> x_enc"""
+    _HAS_SEG = _HAS_REC = False
+    _HEADS = ("enc_out",)
+    _RETURNS = ("enc",)
+
+
+class SEG_Discriminator(_UNetDiscriminator):
+    """networks.py:611-764 -> x_dec.  Decoder modules are named up{i} / dconv{i}{j} (no `s_` prefix) and an unused
+    `enc_out` head is registered (:695), both kept for state_dict parity."""
+    _HAS_CLS = _HAS_REC = False
+    _SEG_PREFIX = ""
+    _HEADS = ("enc_out", "dec_out")
+    _RETURNS = ("dec",)
+
+
+class CLS_SEG_Discriminator(_UNetDiscriminator):
+    """networks.py:766-932 -> (x_enc, x_dec)"""
+    _HAS_REC = False
+    _HEADS = ("enc_out", "dec_out")
+    _RETURNS = ("enc", "dec")
+
+
+class CLS_REC_Discriminator(_UNetDiscriminator):
+    """networks.py:934-1101 -> (x_enc, x_rec)"""
+    _HAS_SEG = False
+    _HEADS = ("enc_out", "rec_out")
+    _RETURNS = ("enc", "rec")
+
+
+class SEG_REC_Discriminator(_UNetDiscriminator):
+    """networks.py:1103-1320 -> (x_dec, x_rec)"""
+    _HAS_CLS = False
+    _HEADS = ("dec_out", "rec_out")
+    _RETURNS = ("dec", "rec")
 
 
 # ================================================================================================
@@ -419,3 +532,135 @@ class MTD_GAN_Method(nn.Module):
         gt = L.g_terms(gen_enc, gen_dec, fake, x, y, eps=self.pixel_loss.eps)                # :1998-2002
         details = {'G/gen_enc': gt[1], 'G/gen_dec': gt[2], 'G/pix_loss': gt[3], 'G/edge_loss': gt[4]}
         return gt[0], details
+
+
+# ================================================================================================
+# Ablation rows (networks.py:1324-1936; selected by models.py:56-75, trained by engine.py:58-73)
+# ================================================================================================
+class _AblationMethod(nn.Module):
+    """The ten `Ablation_*` wrappers differ only in (generator, discriminator, which discriminator outputs carry an
+    adversarial term, whether the SEG term is NDS-masked, whether the REC / RC terms exist), so they are stated as
+    data.  `d_loss` / `g_loss` return `(total_loss, details)` with a SCALAR total (engine.py:61-62 calls
+    `d_loss.backward()`), unlike MTD_GAN_Method's 3-vector.  The reference's debugging `print(...max())` calls
+    (:1346-1347 ...), one host synchronisation each, are not reproduced.
+
+    _D_GAN: ((detail suffix, output name), ...) -- adversarial terms of d_loss, each on real (target 1) and fake (0).
+    _G_GAN: ((detail key, output name), ...) -- adversarial terms of g_loss (target 1); the reference unpacks
+            CLS_REC / SEG_REC outputs positionally as `gen_enc, gen_dec` (:1521, :1577), i.e. the second term of
+            `Ablation_CLS_REC` sits on the restoration output -- kept.
+    """
+    _GEN = "red"
+    _DISC = None
+    _D_GAN = ()
+    _G_GAN = ()
+    _NDS = False
+    _REC = False
+    _RC = False
+
+    def __init__(self):
+        super().__init__()
+        if self._GEN == "red":
+            self.Generator = REDCNN_Generator(in_channels=1, out_channels=32, num_layers=10, kernel_size=3, padding=1)
+        else:
+            self.Generator = ResFFT_Generator(in_channels=1, out_channels=32, num_layers=10, kernel_size=3, padding=1)
+        self.Discriminator = self._DISC(in_channels=1, out_channels=64)
+        if self._NDS:
+            self.gan_metric_cls = L.ls_gan
+            self.gan_metric_seg = L.NDS_Loss
+        else:
+            self.gan_metric = L.ls_gan
+        self.pixel_loss = L.CharbonnierLoss()
+        self.edge_loss = L.EdgeLoss()
+
+    def _masked(self, out_name):
+        return self._NDS and out_name == "dec"
+
+    def d_loss(self, x, y):
+        x, y = check_input(x, "d_loss"), check_input(y, "d_loss")
+        with torch.no_grad():
+            fake = self.Generator(x)
+        D = self.Discriminator
+        B = y.shape[0]
+        need = tuple(sorted({o for _, o in self._D_GAN} | ({"rec"} if self._REC else set())))
+        p = D._forward_parts(torch.cat([y, fake], 0), True, need, groups=2)         # D(y) then D(fake) as one grouped pass
+        real = {k: v[:B] for k, v in p.items()}
+        fk = {k: v[B:] for k, v in p.items()}
+        spec, ins, keys = [], [], []
+        for suffix, o in self._D_GAN:
+            spec += [(1.0, self._masked(o)), (0.0, self._masked(o))]
+            ins += [real[o], fk[o]]
+            keys += [f"D/real_{suffix}", f"D/fake_{suffix}"]
+        dt = L._SqErrTerms.apply(x if self._NDS else None, y if self._NDS else None, tuple(spec), *ins)
+        total = dt[0]
+        # the reference lists real_enc, fake_enc, real_dec, fake_dec: same order as built here
+        details = {k: dt[1 + i] for i, k in enumerate(keys)}
+        if self._REC:
+            rt = L.rec_terms(real["rec"], y, fk["rec"], fake)
+            total = total + rt[0]
+            details['D/rec_loss_real'], details['D/rec_loss_fake'] = rt[1], rt[2]
+        if self._RC:
+            p2 = D._forward_parts(Clip01Fn.apply(p["rec"]), True, ("enc", "dec"), groups=2)
+            ct = L.consist_terms(real["enc"], p2["enc"][:B], real["dec"], p2["dec"][:B], fk["enc"], p2["enc"][B:], fk["dec"],
+                                 p2["dec"][B:])
+            total = total + ct[0]
+            for i, k in enumerate(("real_enc", "real_dec", "fake_enc", "fake_dec")):
+                details[f'D/consist_loss_{k}'] = ct[1 + i]
+        return total, details
+
+    def g_loss(self, x, y):
+        x, y = check_input(x, "g_loss"), check_input(y, "g_loss")
+        fake = self.Generator(x)
+        need = tuple(sorted({o for _, o in self._G_GAN}))
+        p = self.Discriminator._forward_parts(fake, False, need)      # D weights are constants here (engine.py:66-70)
+        spec = tuple((1.0, self._masked(o)) for _, o in self._G_GAN)
+        at = L._SqErrTerms.apply(x if self._NDS else None, y if self._NDS else None, spec, *[p[o] for _, o in self._G_GAN])
+        pix = L._DiffTerms.apply(L.CHARB, self.pixel_loss.eps, (50.0,), fake, y)
+        edge = L._EdgeTerm.apply(fake, y, self.edge_loss.loss.eps, 50.0)
+        details = {k: at[1 + i] for i, (k, _) in enumerate(self._G_GAN)}
+        details['G/pix_loss'], details['G/edge_loss'] = pix[0], edge[0]
+        return at[0] + pix[0] + edge[0], details
+
+
+class Ablation_CLS(_AblationMethod):                              # networks.py:1324-1372
+    _DISC, _D_GAN, _G_GAN = CLS_Discriminator, (("enc", "enc"),), (("G/gen_enc", "enc"),)
+
+
+class Ablation_SEG(_AblationMethod):                              # :1374-1423 (the decision map is reported as *_enc)
+    _DISC, _D_GAN, _G_GAN = SEG_Discriminator, (("enc", "dec"),), (("G/gen_enc", "dec"),)
+
+
+class Ablation_CLS_SEG(_AblationMethod):                          # :1427-1480
+    _DISC = CLS_SEG_Discriminator
+    _D_GAN, _G_GAN = (("enc", "enc"), ("dec", "dec")), (("G/gen_enc", "enc"), ("G/gen_dec", "dec"))
+
+
+class Ablation_CLS_REC(_AblationMethod):                          # :1482-1539
+    _DISC, _REC = CLS_REC_Discriminator, True
+    _D_GAN, _G_GAN = (("enc", "enc"),), (("G/gen_enc", "enc"), ("G/gen_dec", "rec"))
+
+
+class Ablation_SEG_REC(_AblationMethod):                          # :1541-1595
+    _DISC, _REC = SEG_REC_Discriminator, True
+    _D_GAN, _G_GAN = (("dec", "dec"),), (("G/gen_enc", "dec"), ("G/gen_dec", "rec"))
+
+
+class Ablation_CLS_SEG_REC(_AblationMethod):                      # :1599-1656
+    _DISC, _REC = Multi_Task_Discriminator_Skip, True
+    _D_GAN, _G_GAN = (("enc", "enc"), ("dec", "dec")), (("G/gen_enc", "enc"), ("G/gen_dec", "dec"))
+
+
+class Ablation_CLS_SEG_REC_NDS(Ablation_CLS_SEG_REC):             # :1659-1717
+    _NDS = True
+
+
+class Ablation_CLS_SEG_REC_RC(Ablation_CLS_SEG_REC):              # :1720-1790
+    _RC = True
+
+
+class Ablation_CLS_SEG_REC_NDS_RC(Ablation_CLS_SEG_REC):          # :1793-1864
+    _NDS = _RC = True
+
+
+class Ablation_CLS_SEG_REC_NDS_RC_ResFFT(Ablation_CLS_SEG_REC):   # :1867-1936
+    _NDS = _RC = True
+    _GEN = "resfft"

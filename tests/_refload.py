@@ -17,6 +17,10 @@ def load_reference():
     names (losses, arch, module) collide with this repo's drop-in mirrors, so the reference is
     imported under a temporarily swapped sys.path / sys.modules and handed back as objects."""
     assert reference_available()
+    try:                       # the reference's losses.py imports torchvision; its op registration inspects sys.modules
+        import torchvision  # noqa: F401   and must not run while the reference's namespace packages are half-imported
+    except Exception:
+        pass
     saved_path = list(sys.path)
     saved_mods = {k: sys.modules.pop(k) for k in list(sys.modules)
                   if k in ("losses", "arch", "module") or k.startswith(("arch.", "module."))}
