@@ -779,6 +779,224 @@ __global__ void tc_finish_kernel(const __grid_constant__ TcArgs a, size_t total)
   }
 }
 
+// =====================================================================================================
+// 32 -> 32 channel 3x3 layers (every spatial conv of the Res-FFT-Conv generator: 22 encoder / decoder layers and 21
+// `img_conv`s, forward and data gradient; ALL of inference): halo-tile kernel.
+//
+// The general kernel above streams, per 128-pixel tile, nine tap-shifted 16 KB A boxes plus nine hi|lo weight tiles
+// from L2 (216 KB) and rounds each box in shared memory.  Here
+//   * the 72 KB hi|lo weight of the layer is loaded ONCE per CTA and stays resident in shared memory;
+//   * one TMA box lands the (16+2) x (8+2) pixel HALO of a 16 x 8 pixel tile (23 KB, raw fp32, SWIZZLE_128B);
+//   * four conversion warps split it ONCE into tf32 hi / lo planes laid out [8 chunks of 4 channels][180 halo pixels]
+//     [16 B] -- the no-swizzle K-major ("interleaved") UMMA layout: a core matrix is 8 consecutive halo pixels x 16 B,
+//     LBO = plane stride (2880 B), SBO = one halo row (10 pixels = 160 B);
+//   * the nine taps are nine DESCRIPTOR START ADDRESSES into the same planes (shift by (dy*10 + dx) * 16 B): no data
+//     moves for a tap;
+//   * B_hi | B_lo of a tap are adjacent 4 KB tiles, i.e. one N = 64 operand: one MMA gives a_hi*w_hi (columns 0-31) and
+//     a_hi*w_lo (columns 32-63), a second N = 32 MMA adds a_lo*w_hi to columns 32-63; the epilogue sums the halves
+//     (small terms are accumulated separately from the main product).
+// L2 -> SM traffic per tile: 23 KB instead of 216 KB; conversion work 1440 instead of 9216 float4 per tile.
+// =====================================================================================================
+constexpr int kHaloW = 10, kHaloH = 18, kHaloPix = kHaloW * kHaloH;            // halo of a 16 x 8 tile
+constexpr int kRawBytes = kHaloPix * 128;                                      // 23040
+constexpr int kRawStage = (kRawBytes + 1023) & ~1023;                          // 23552 (SWIZZLE_128B: 1024-aligned stages)
+constexpr int kPlaneBytes = kHaloPix * 16;                                     // 2880: one 4-channel chunk of all halo pixels
+constexpr int kCvStage = 2 * 8 * kPlaneBytes;                                  // hi planes | lo planes = 46080
+constexpr int kC32WBytes = 9 * 2 * 4096;                                       // 9 taps x (hi | lo) 32 x 32 tiles
+
+// no-swizzle K-major descriptor: [0,14) start >> 4 | [16,30) LBO >> 4 (between the two 16-byte K chunks of one MMA)
+// | [32,46) SBO >> 4 (between 8-row groups) | version 1 | layout 0
+__device__ __forceinline__ uint64_t make_interleave_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) |
+         (1ull << 46);
+}
+
+template <int NPASS>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_c32_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+                const __grid_constant__ CUtensorMap mapBlo, const __grid_constant__ TcArgs a) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  constexpr int kNA = NPASS == 3 ? 2 : 1;
+  constexpr uint32_t kAccCols = NPASS == 3 ? 64 : 32;
+  constexpr uint32_t kTmemCols = 2 * kAccCols;
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t w_base = base;                                      // [tap][hi 4 KB | lo 4 KB]
+  const uint32_t raw_base = w_base + kC32WBytes;                     // 2 raw halo stages
+  const uint32_t cv_base = raw_base + 2 * kRawStage;                 // 2 converted stages (hi planes | lo planes)
+  const uint32_t bar_base = cv_base + 2 * kCvStage;
+  const uint32_t wfull = bar_base;
+  auto rfull = [&](int s) { return bar_base + 8u * (1 + s); };
+  auto rempty = [&](int s) { return bar_base + 8u * (3 + s); };
+  auto cfull = [&](int s) { return bar_base + 8u * (5 + s); };
+  auto cempty = [&](int s) { return bar_base + 8u * (7 + s); };
+  auto tfull_bar = [&](int i) { return bar_base + 8u * (9 + i); };
+  auto tempty_bar = [&](int i) { return bar_base + 8u * (11 + i); };
+  const uint32_t tmem_slot = bar_base + 8u * 13;
+  unsigned char* gen_base = smem_raw + (base - smem_u32(smem_raw));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&mapA);
+    prefetch_tmap(&mapB);
+    if (NPASS == 3) prefetch_tmap(&mapBlo);
+    mbar_init(wfull, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(rfull(s), 1);
+      mbar_init(rempty(s), 4);
+      mbar_init(cfull(s), 4);
+      mbar_init(cempty(s), 1);
+      mbar_init(tfull_bar(s), 1);
+      mbar_init(tempty_bar(s), 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(kTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gen_base + (tmem_slot - base));
+  mtd_pdl_prologue();
+
+  const int tiles_per_img = a.n_ht * a.n_wt;
+  auto decode = [&](int tile, int& b, int& h0, int& w0) {
+    b = tile / tiles_per_img;
+    const int r = tile - b * tiles_per_img;
+    const int th = r / a.n_wt;
+    h0 = th * 16; w0 = (r - th * a.n_wt) * 8;
+  };
+
+  if (warp == 0) {
+    // ===== TMA producer: the weights once, then one halo box per tile =====
+    if (lane == 0) {
+      mbar_expect_tx(wfull, kNA * 9 * 4096);
+      for (int t = 0; t < 9; ++t) {
+        tma_load_4d(&mapB, w_base + (uint32_t)t * 8192u, wfull, 0, 0, t, 0);
+        if (NPASS == 3) tma_load_4d(&mapBlo, w_base + (uint32_t)t * 8192u + 4096u, wfull, 0, 0, t, 0);
+      }
+      PipeState st;
+      for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+        int b, h0, w0;
+        decode(tile, b, h0, w0);
+        mbar_wait(rempty(st.stage), st.phase ^ 1u);
+        mbar_expect_tx(rfull(st.stage), kRawBytes);
+        tma_load_4d(&mapA, raw_base + (uint32_t)st.stage * kRawStage, rfull(st.stage), 0, w0 - 1, h0 - 1, b);
+        st.advance(2);
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      PipeState st;
+      constexpr uint32_t idesc_main = make_idesc(NPASS == 3 ? 64 : 32), idesc_lo = make_idesc(32);
+      mbar_wait(wfull, 0);
+      int lt = 0;
+      for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++lt) {
+        const int acc = lt & 1;
+        const uint32_t acc_phase = (uint32_t)(lt >> 1) & 1u;
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        mbar_wait(cfull(st.stage), st.phase);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)acc * kAccCols;
+        const uint32_t hi_base = cv_base + (uint32_t)st.stage * kCvStage, lo_base = hi_base + 8 * kPlaneBytes;
+#pragma unroll 1
+        for (int t = 0; t < 9; ++t) {
+          const uint32_t shift = (uint32_t)((a.dy[t] + 1) * kHaloW + (a.dx[t] + 1)) * 16u;
+          const uint64_t db = make_sw128_desc(w_base + (uint32_t)t * 8192u);
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            const uint64_t da = make_interleave_desc(hi_base + (uint32_t)(2 * kk) * kPlaneBytes + shift, kPlaneBytes, kHaloW * 16);
+            umma_tf32(tmem_d, da, db + 2u * kk, idesc_main, (t > 0 || kk > 0) ? 1u : 0u);
+            if (NPASS == 3) {
+              const uint64_t dal = make_interleave_desc(lo_base + (uint32_t)(2 * kk) * kPlaneBytes + shift, kPlaneBytes, kHaloW * 16);
+              umma_tf32(tmem_d + 32u, dal, db + 2u * kk, idesc_lo, 1u);
+            }
+          }
+        }
+        umma_commit(cempty(st.stage));
+        umma_commit(tfull_bar(acc));
+        st.advance(2);
+      }
+    }
+  } else if (warp < 6) {
+    // ===== operand split: raw halo (pixel-major, swizzled) -> tf32 hi / lo planes (chunk-major) =====
+    const int ct = threadIdx.x - 64;               // 0..127
+    PipeState sr, sc;
+    for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+      mbar_wait(rfull(sr.stage), sr.phase);
+      mbar_wait(cempty(sc.stage), sc.phase ^ 1u);
+      const unsigned char* raw = gen_base + (raw_base - base) + (size_t)sr.stage * kRawStage;
+      unsigned char* hip = gen_base + (cv_base - base) + (size_t)sc.stage * kCvStage;
+      unsigned char* lop = hip + 8 * kPlaneBytes;
+#pragma unroll 4
+      for (int i = ct; i < 8 * kHaloPix; i += 128) {
+        const int kc = i / kHaloPix, p = i - kc * kHaloPix;           // consecutive lanes: consecutive halo pixels, same chunk
+        const uint4 v = *reinterpret_cast<const uint4*>(raw + (size_t)p * 128 + ((kc ^ (p & 7)) << 4));
+        uint4 h;
+        h.x = (v.x + 0x1000u) & 0xffffe000u; h.y = (v.y + 0x1000u) & 0xffffe000u;
+        h.z = (v.z + 0x1000u) & 0xffffe000u; h.w = (v.w + 0x1000u) & 0xffffe000u;
+        *reinterpret_cast<uint4*>(hip + (size_t)kc * kPlaneBytes + (size_t)p * 16) = h;
+        if (NPASS == 3) {
+          uint4 l;
+          l.x = (__float_as_uint(__uint_as_float(v.x) - __uint_as_float(h.x)) + 0x1000u) & 0xffffe000u;
+          l.y = (__float_as_uint(__uint_as_float(v.y) - __uint_as_float(h.y)) + 0x1000u) & 0xffffe000u;
+          l.z = (__float_as_uint(__uint_as_float(v.z) - __uint_as_float(h.z)) + 0x1000u) & 0xffffe000u;
+          l.w = (__float_as_uint(__uint_as_float(v.w) - __uint_as_float(h.w)) + 0x1000u) & 0xffffe000u;
+          *reinterpret_cast<uint4*>(lop + (size_t)kc * kPlaneBytes + (size_t)p * 16) = l;
+        }
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> tensor-core (async proxy) reads
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(cfull(sc.stage));
+        mbar_arrive(rempty(sr.stage));
+      }
+      sr.advance(2);
+      sc.advance(2);
+    }
+  } else {
+    // ===== epilogue =====
+    const int q = warp & 3;
+    const int r = q * 32 + lane;                   // accumulator row: pixel (hl, wl) = (r / 8, r % 8) of the tile
+    const int hl = r >> 3, wl = r & 7;
+    int lt = 0;
+    for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++lt) {
+      int b, h0, w0;
+      decode(tile, b, h0, w0);
+      const int acc = lt & 1;
+      const uint32_t acc_phase = (uint32_t)(lt >> 1) & 1u;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      uint32_t v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * kAccCols, v);
+      if (NPASS == 3) {
+        uint32_t u[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * kAccCols + 32u, u);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(u[j]));
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));            // accumulator is in registers: the next tile may overwrite it
+      const float scale = tc_row_scale(a, b);
+      const size_t rowoff = (((size_t)b * a.H + (h0 + hl)) * a.W + (w0 + wl)) * 32;
+#pragma unroll
+      for (int j = 0; j < 32; j += 4)
+        tc_store4(a, a.out, rowoff + j, j, scale, __uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                  __uint_as_float(v[j + 3]));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+  }
+}
+
 // second phase of a stream-K launch (v1 kernel): out tile = epilogue( sum over the tile's pieces, in piece order ).
 // One thread per 4 output channels of one tile row; consecutive threads walk a row, so workspace reads and output
 // writes are coalesced.
@@ -1098,6 +1316,53 @@ int launch_tc_v1(const float* x1, const float* x2, const float* wp, int passes, 
   return MTD_OK;
 }
 
+int g_c32_enabled = 1;      // mtd_tc_set_c32(0) routes 32 -> 32 3x3 layers through the general kernel (A/B measurements)
+
+bool c32_eligible(const TcArgs& a) {
+  if (!g_c32_enabled || g_tc_version != 1) return false;
+  if (a.C1 != 32 || a.C2 != 0 || a.N != 32 || a.T != 9 || a.es > 1 || a.n_cls > 1 || a.n_split != 0) return false;
+  if (a.omy != 1 || a.omx != 1 || a.ooy != 0 || a.oox != 0 || a.outH != a.H || a.outW != a.W) return false;
+  if (a.H % 16 || a.W % 8) return false;
+  bool seen[9] = {};
+  for (int t = 0; t < 9; ++t) {       // the taps must be exactly the 3 x 3 neighbourhood (any order)
+    if (a.dy[t] < -1 || a.dy[t] > 1 || a.dx[t] < -1 || a.dx[t] > 1) return false;
+    seen[(a.dy[t] + 1) * 3 + a.dx[t] + 1] = true;
+  }
+  for (bool s_ : seen) if (!s_) return false;
+  return true;
+}
+
+template <int NPASS>
+int launch_c32_n(const CUtensorMap& mA, const CUtensorMap& mB, const CUtensorMap& mBlo, TcArgs& a, cudaStream_t st) {
+  const size_t smem = 1024 + kC32WBytes + 2 * kRawStage + 2 * kCvStage + 8 * 14 + 16;
+  static bool attr_set = false;
+  if (!attr_set) {
+    MTD_CUDA(cudaFuncSetAttribute(conv_c32_kernel<NPASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  mtd_launch(conv_c32_kernel<NPASS>, a.grid, kThreads, smem, st, mA, mB, mBlo, a);
+  MTD_CHECK_LAUNCH();
+  return MTD_OK;
+}
+
+int launch_c32(const float* x, const float* wp, int passes, TcArgs& a, cudaStream_t st) {
+  a.n_wt = a.W / 8; a.n_ht = a.H / 16;
+  a.n_tiles = a.B * a.n_wt * a.n_ht;
+  a.grid = a.n_tiles < mtd_sm_count() ? a.n_tiles : mtd_sm_count();
+  CUtensorMap mA, mB;
+  int rc = make_act_map(&mA, x, 32, a.W, a.H, a.B, kHaloW, kHaloH, 1, false, 1);
+  if (rc) return rc;
+  const long long K = 9 * 32;
+  rc = make_w_map(&mB, wp, K, 32, 32);
+  if (rc) return rc;
+  CUtensorMap mBlo = mB;
+  if (passes == 3) {
+    rc = make_w_map(&mBlo, wp + (size_t)a.wrows_total * K, K, 32, 32);
+    if (rc) return rc;
+  }
+  return passes == 3 ? launch_c32_n<3>(mA, mB, mBlo, a, st) : launch_c32_n<1>(mA, mB, mBlo, a, st);
+}
+
 // wp: packed weights, tile-major (mtd_conv_pack_*_blocked); for passes == 3 the buffer holds [hi | lo].
 // v2 kernel only: `finish` = run the split-K finishing pass here (false when the caller batches several launches into
 // one output, e.g. the four parity classes of a stride-2 dgrad); the chosen ksplit is returned through a.ksplit.
@@ -1108,6 +1373,7 @@ int launch_tc(const float* x1, const float* x2, const float* wp, int passes, TcA
   if (!mtd_aligned16(x1) || !mtd_aligned16(wp) || !mtd_aligned16(a.out) || (x2 && !mtd_aligned16(x2)) ||
       (a.bias && !mtd_aligned16(a.bias)))
     return MTD_EALIGN;
+  if (c32_eligible(a)) return launch_c32(x1, wp, passes, a, st);
   a.n_wt = a.W / a.TW; a.n_ht = a.H / a.TH; a.n_bt = (a.B + a.TB - 1) / a.TB;
   const int m_tiles = a.n_wt * a.n_ht * a.n_bt;
   a.kc1 = a.C1 / 32; a.kc2 = a.C2 / 32;
@@ -1485,6 +1751,13 @@ int mtd_tc_set_tuning(int bn, int sk_per) {
   if (bn != 0 && bn != 32 && bn != 64 && bn != 128) return MTD_EINVAL;
   g_tune_bn = bn; g_tune_per = sk_per;
   return MTD_OK;
+}
+
+// 1 (default): 32 -> 32 channel 3x3 layers run on the halo-tile kernel (conv_c32_kernel); 0: on the general kernel.
+int mtd_tc_set_c32(int enabled) {
+  const int prev = g_c32_enabled;
+  g_c32_enabled = enabled ? 1 : 0;
+  return prev;
 }
 
 int mtd_conv_fwd_tc_supported(int B, int H, int W, int C1, int C2, int N, int kh, int kw, int stride, int pad) {

@@ -109,6 +109,9 @@ TC_CASES = [
     (20, 2, 2, 512, 512, 512, 3, 1, 0, 2, 0, False),     # M = 80, two sources, split-K
     (20, 1, 1, 512, 0, 512, 1, 0, 0, 2, 0, False),       # bottleneck 1x1 at 1x1 spatial (TB = 128)
     (3, 4, 4, 512, 0, 2048, 1, 0, 0, 0, 0, False),       # UpsampleBlock 1x1 conv C -> 4C
+    (5, 16, 8, 32, 0, 32, 3, 1, 0, 1, 0, False),         # halo-tile kernel: one 16 x 8 tile per image (all four borders padded)
+    (1, 512, 512, 32, 0, 32, 3, 1, 1, 0, 1, True),       # halo-tile kernel at the inference geometry (2048 tiles, 14 per CTA)
+    (3, 64, 32, 32, 0, 32, 3, 1, 0, 1, 0, False),        # halo-tile kernel, 4 x 4 tiles per image, ragged over 148 CTAs
 ]
 
 
@@ -541,3 +544,33 @@ def test_repack_stale_rebuilds_all_packs_in_batches():
     for (y1, g1), (y2, g2) in zip(got, want):
         assert torch.equal(y1, y2) and torch.equal(g1, g2)
     assert ops.repack_stale() == 0
+
+
+@pytest.mark.parametrize("passes", [1, 3], ids=["tf32", "tf32x3"])
+def test_halo_tile_kernel_equals_general_kernel(passes):
+    """32 -> 32 channel 3x3 layers: the halo-tile kernel (resident weights, one halo box per tile, taps as descriptor
+    offsets) and the general tap-streaming kernel evaluate the same products, so forward and data gradient agree to
+    summation order."""
+    from mtdgan_b200 import _ext, ops
+    ops.set_conv_mode("auto", passes)
+    lib = _ext.load()
+    try:
+        x = nhwc(_rand(4, 32, 64, 64, seed=1).float()).to(DEV).requires_grad_(True)
+        w = _rand(32, 32, 3, 3, seed=2, scale=1.0 / math.sqrt(288)).float().to(DEV).requires_grad_(True)
+        b = _rand(32, seed=3, scale=0.1).float().to(DEV).requires_grad_(True)
+        g = nhwc(_rand(4, 32, 64, 64, seed=5).float()).to(DEV)
+        cfg = ops.ConvCfg(cin=32, cout=32, kh=3, kw=3, stride=1, pad=1, pre_act=ops.ACT_RELU)
+        res = []
+        for enabled in (1, 0):
+            prev = lib.mtd_tc_set_c32(enabled)
+            try:
+                y = ops.conv(x, w, b, cfg)
+                dx, = torch.autograd.grad(y, [x], g)
+                res.append((y.detach().clone(), dx.clone()))
+            finally:
+                lib.mtd_tc_set_c32(prev)
+        torch.cuda.synchronize()
+        assert rel_err(res[0][0], res[1][0]) <= (1e-6 if passes == 3 else 1e-5)
+        assert rel_err(res[0][1], res[1][1]) <= (1e-6 if passes == 3 else 1e-5)
+    finally:
+        ops.set_conv_mode("auto", 3)
