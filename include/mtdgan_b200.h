@@ -207,6 +207,8 @@ int mtd_loss_finalize(const double* acc, int k, float s0, float s1, float s2, fl
 /* ---- PCGrad (pcgrad.cu) -----------------------------------------------------------------------------
  * Replaces PCGrad._project_conflicting of module/weight_methods.py:449-464 and module/pcgrad.py:50-70. */
 int mtd_pcgrad_chunk_elems(void);
+/* out_seg = scale_seg * g_0 for every segment (same tables): gathers gradient tensors into one flat collective operand */
+int mtd_segments_scale_copy(const void* seg_tab, const void* chunk_tab, int n_chunks, void* stream);
 int mtd_pcgrad_gram(const void* seg_tab, const void* chunk_tab, int n_chunks, int T, double* gram_ws, void* stream);
 int mtd_pcgrad_solve_combine(const void* seg_tab, const void* chunk_tab, int n_chunks, int T, const int* orders, int mean,
                              double* gram_ws, float* coef_out, float* cmat_out, double* gram_out, void* stream);

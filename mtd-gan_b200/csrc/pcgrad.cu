@@ -120,11 +120,43 @@ __global__ void __launch_bounds__(256) pcgrad_combine_kernel(const Seg* __restri
   }
 }
 
+// out = scale_seg * g_0 for every segment: gathers a list of gradient tensors into one flat buffer (the operand of a
+// reduce-scatter / all-reduce) in ONE launch, with the 1/world_size of the batch mean folded in.
+__global__ void __launch_bounds__(256) segs_scale_copy_kernel(const Seg* __restrict__ segs, const int2* __restrict__ chunks) {
+  mtd_pdl_prologue();
+  const int2 ck = chunks[blockIdx.x];
+  const Seg s = segs[ck.x];
+  const long long end = min(s.numel, (long long)ck.y + kChunk);
+  const float scale = __int_as_float((int)s.scale_bits);
+  const float* g = s.g[0];
+  long long i0 = ck.y;
+  if ((((uintptr_t)g | (uintptr_t)s.out) & 15u) == 0) {
+    const long long n4 = (end - ck.y) >> 2;
+    const float4* g4 = reinterpret_cast<const float4*>(g + ck.y);
+    float4* o4 = reinterpret_cast<float4*>(s.out + ck.y);
+    for (long long q = threadIdx.x; q < n4; q += blockDim.x) {
+      float4 v = __ldg(g4 + q);
+      v.x *= scale; v.y *= scale; v.z *= scale; v.w *= scale;
+      o4[q] = v;
+    }
+    i0 = ck.y + (n4 << 2);
+  }
+  for (long long i = i0 + threadIdx.x; i < end; i += blockDim.x) s.out[i] = scale * __ldg(g + i);
+}
+
 }  // namespace
 
 extern "C" {
 
 int mtd_pcgrad_chunk_elems(void) { return kChunk; }
+
+int mtd_segments_scale_copy(const void* seg_tab, const void* chunk_tab, int n_chunks, void* stream) {
+  MTD_REQUIRE(seg_tab && chunk_tab && n_chunks > 0);
+  mtd_launch(segs_scale_copy_kernel, n_chunks, 256, 0, (cudaStream_t)stream, reinterpret_cast<const Seg*>(seg_tab),
+             reinterpret_cast<const int2*>(chunk_tab));
+  MTD_CHECK_LAUNCH();
+  return MTD_OK;
+}
 
 // gram_ws: 16 doubles (zeroed here); entry [a*4+b], a <= b.  Split form for multi-GPU use: the caller
 // all-reduces gram_ws between the two calls (each rank holds a shard of the gradients).

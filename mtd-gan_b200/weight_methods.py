@@ -170,6 +170,12 @@ class PCGrad(WeightMethod):
         if isinstance(shared_parameters, torch.Tensor):
             shared_parameters = [shared_parameters]
         shared_parameters = list(shared_parameters)
+        if task_specific_parameters is not None:
+            if isinstance(task_specific_parameters, torch.Tensor):
+                task_specific_parameters = [task_specific_parameters]
+            task_specific_parameters = list(task_specific_parameters)
+        if mdist.active():
+            return self._set_pc_grads_distributed(losses, shared_parameters, task_specific_parameters)
         # shared part (:431-439): one backward pass per task, weight-gradient GEMMs only for the shared set
         shared_grads = []
         with wgrad_only_for(shared_parameters):
@@ -181,14 +187,34 @@ class PCGrad(WeightMethod):
             p.grad = g
         # task specific part (:442-447)
         if task_specific_parameters is not None:
-            if isinstance(task_specific_parameters, torch.Tensor):
-                task_specific_parameters = [task_specific_parameters]
-            task_specific_parameters = list(task_specific_parameters)
             with wgrad_only_for(task_specific_parameters), deferred_wgrad_finish():
                 ts_grads = torch.autograd.grad(losses.sum(), task_specific_parameters)
-            if mdist.active():
-                ts_grads = mdist.allreduce_mean_list(ts_grads)
             for p, g in zip(task_specific_parameters, ts_grads):
+                p.grad = g
+
+    def _set_pc_grads_distributed(self, losses, shared_parameters, task_specific_parameters):
+        """Same gradients as the single-process path on the concatenated batch, with the collectives
+        overlapped: the four backward passes are independent `autograd.grad` calls, so the task-specific one runs FIRST
+        and its all-reduce, like the reduce-scatter of each task's shared gradients, proceeds on the communication
+        stream while the next backward pass computes (distributed.py)."""
+        ts_pending = None
+        if task_specific_parameters is not None:
+            with wgrad_only_for(task_specific_parameters), deferred_wgrad_finish():
+                ts_grads = torch.autograd.grad(losses.sum(), task_specific_parameters, retain_graph=True)
+            ts_pending = mdist.allreduce_mean_list_async(ts_grads)
+        pipe = mdist.ShardedPCGrad()
+        n = len(losses)
+        with wgrad_only_for(shared_parameters):
+            for k, l in enumerate(losses):
+                with deferred_wgrad_finish():
+                    g = torch.autograd.grad(l, shared_parameters, retain_graph=(k + 1 < n))
+                pipe.submit(g)
+        orders = self.refresh_orders(shared_parameters[0].device)
+        merged = pipe.finish(orders, self.reduction == "mean", _cuda_gram, _cuda_solve_combine)
+        for p, g in zip(shared_parameters, merged):
+            p.grad = g
+        if ts_pending is not None:
+            for p, g in zip(task_specific_parameters, ts_pending.wait()):
                 p.grad = g
 
     def refresh_orders(self, device):

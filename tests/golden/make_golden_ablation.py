@@ -39,6 +39,33 @@ def drop_mask(b, seed):
     return (torch.rand(b, 512, generator=g) >= 0.3).float() / 0.7
 
 
+def gap(g32, g64):
+    """fp32-vs-fp64 gap of the REFERENCE itself (same method as make_golden.py): the conditioning noise floor of a
+    gradient tensor (ReLU / LeakyReLU mask flips at near-zero pre-activations)."""
+    a, b = g32.detach().double().flatten(), g64.detach().double().flatten()
+    rms = float(b.norm()) / (b.numel() ** 0.5) + 1e-300
+    return {"norm": abs(float(a.norm()) - float(b.norm())) / (float(b.norm()) + 1e-300), "samp": float((a - b).abs().max()) / rms}
+
+
+def run64(name):
+    """The same two backward passes in float64."""
+    torch.manual_seed(2024)
+    random.seed(2024)
+    m = getattr(N, name)().double().train()
+    m.edge_loss.kernel = m.edge_loss.kernel.double()
+    if hasattr(m.Discriminator, "c_drop"):
+        m.Discriminator.c_drop = MaskDrop([drop_mask(2, 900 + i).double() for i in range(5)])
+    with contextlib.redirect_stdout(io.StringIO()):
+        d_total, _ = m.d_loss(x.double(), y.double())
+    d_total.backward()
+    dg = {k: (None if p.grad is None else p.grad.clone()) for k, p in m.Discriminator.named_parameters()}
+    m.zero_grad(set_to_none=True)
+    with contextlib.redirect_stdout(io.StringIO()):
+        g_total, _ = m.g_loss(x.double(), y.double())
+    g_total.backward()
+    return dg, {k: p.grad.clone() for k, p in m.Generator.named_parameters()}
+
+
 out = {}
 x, y = O.synthetic_pair(2, 64, seed=77)
 for name in NAMES:
@@ -51,6 +78,8 @@ for name in NAMES:
     with contextlib.redirect_stdout(io.StringIO()):          # the reference prints tensor maxima
         d_total, d_det = m.d_loss(x, y)
     d_total.backward()
+    dg64, gg64 = run64(name)
+    fix["d_grads_noise"] = {k: gap(p.grad, dg64[k]) for k, p in m.Discriminator.named_parameters() if p.grad is not None}
     fix["d_total"] = float(d_total)
     fix["d_details"] = {k: float(v) for k, v in d_det.items()}
     fix["d_grads"] = {k: (None if p.grad is None else summarize(p.grad, 16)) for k, p in m.Discriminator.named_parameters()}
@@ -61,9 +90,11 @@ for name in NAMES:
     fix["g_total"] = float(g_total)
     fix["g_details"] = {k: float(v) for k, v in g_det.items()}
     fix["g_grads"] = {k: summarize(p.grad, 16) for k, p in m.Generator.named_parameters()}
+    fix["g_grads_noise"] = {k: gap(p.grad, gg64[k]) for k, p in m.Generator.named_parameters()}
     fix["buffers"] = {k: summarize(v, 8) for k, v in m.Discriminator.named_buffers()}
     out[name] = fix
-    print(name, fix["d_total"], fix["g_total"], len(fix["d_grads"]), flush=True)
+    print(name, fix["d_total"], fix["g_total"], len(fix["d_grads"]), "worst D noise %.2e, worst G noise %.2e"
+          % (max(v["samp"] for v in fix["d_grads_noise"].values()), max(v["samp"] for v in fix["g_grads_noise"].values())), flush=True)
 
 # stand-alone REDCNN_Generator forward (eval)
 torch.manual_seed(2024)

