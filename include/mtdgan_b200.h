@@ -155,6 +155,8 @@ int mtd_split_tf32(float* hi, float* lo, long long n, void* stream);
  * Replaces torch.fft.rfft2 / cat / fft_conv 1x1 + ReLU / chunk / complex / torch.fft.irfft2 at
  * arch/Ours/networks.py:24-29 and their autograd backward.  Half spectrum layout:
  * spec[B][W/2+1][H][C] complex64 (interleaved).  H, W powers of two; C == 32 for the mix.          */
+/* 1 when the frequency branch supports the geometry: C == 32 and H, W in {64, 128, 256, 512} (four-step FFTs 8x8 ... 16x32) */
+int mtd_fft_supported(int H, int W, int C);
 long long mtd_fft_spec_elems(int B, int H, int W, int C);          /* floats in a spectrum buffer      */
 long long mtd_fft_bwd_part_elems(int B, int W);                    /* floats in the bwd partial buffer */
 int mtd_fft_rows_fwd(const float* x, float* spec, int B, int H, int W, int C, void* stream);

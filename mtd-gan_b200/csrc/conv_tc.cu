@@ -891,6 +891,14 @@ conv_c32_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     if (lane == 0) {
       PipeState st;
       constexpr uint32_t idesc_main = make_idesc(NPASS == 3 ? 64 : 32), idesc_lo = make_idesc(32);
+      // All descriptors are precomputed: the issuing thread is ONE lane, every integer instruction in its loop costs a
+      // full dependent-issue latency.  Per tap: the B descriptor and the halo shift (in 16-byte descriptor units).
+      uint32_t shift16[9];
+#pragma unroll
+      for (int t = 0; t < 9; ++t) shift16[t] = (uint32_t)((a.dy[t] + 1) * kHaloW + (a.dx[t] + 1));
+      const uint64_t db0 = make_sw128_desc(w_base);
+      const uint64_t da_stage[2] = {make_interleave_desc(cv_base, kPlaneBytes, kHaloW * 16),
+                                    make_interleave_desc(cv_base + kCvStage, kPlaneBytes, kHaloW * 16)};
       mbar_wait(wfull, 0);
       int lt = 0;
       for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++lt) {
@@ -900,19 +908,18 @@ conv_c32_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         mbar_wait(cfull(st.stage), st.phase);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)acc * kAccCols;
-        const uint32_t hi_base = cv_base + (uint32_t)st.stage * kCvStage, lo_base = hi_base + 8 * kPlaneBytes;
-#pragma unroll 1
+        const uint64_t da_hi = st.stage ? da_stage[1] : da_stage[0];
+#pragma unroll
         for (int t = 0; t < 9; ++t) {
-          const uint32_t shift = (uint32_t)((a.dy[t] + 1) * kHaloW + (a.dx[t] + 1)) * 16u;
-          const uint64_t db = make_sw128_desc(w_base + (uint32_t)t * 8192u);
+          // start-address field arithmetic (16-byte units): + tap shift, + 2 planes per K = 8 slice; the lo planes
+          // follow the 8 hi planes; the B tile of tap t is 8 KB further, its K slices 32 B apart
+          const uint64_t dat = da_hi + shift16[t];
+          const uint64_t dbt = db0 + (uint64_t)(t * (8192 >> 4));
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk) {
-            const uint64_t da = make_interleave_desc(hi_base + (uint32_t)(2 * kk) * kPlaneBytes + shift, kPlaneBytes, kHaloW * 16);
-            umma_tf32(tmem_d, da, db + 2u * kk, idesc_main, (t > 0 || kk > 0) ? 1u : 0u);
-            if (NPASS == 3) {
-              const uint64_t dal = make_interleave_desc(lo_base + (uint32_t)(2 * kk) * kPlaneBytes + shift, kPlaneBytes, kHaloW * 16);
-              umma_tf32(tmem_d + 32u, dal, db + 2u * kk, idesc_lo, 1u);
-            }
+            umma_tf32(tmem_d, dat + (uint64_t)(kk * (2 * kPlaneBytes >> 4)), dbt + 2u * kk, idesc_main, (t > 0 || kk > 0) ? 1u : 0u);
+            if (NPASS == 3)
+              umma_tf32(tmem_d + 32u, dat + (uint64_t)((8 + 2 * kk) * (kPlaneBytes >> 4)), dbt + 2u * kk, idesc_lo, 1u);
           }
         }
         umma_commit(cempty(st.stage));
@@ -967,6 +974,17 @@ conv_c32_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
       decode(tile, b, h0, w0);
       const int acc = lt & 1;
       const uint32_t acc_phase = (uint32_t)(lt >> 1) & 1u;
+      // residual operands of this lane's output row are fetched BEFORE the accumulator is waited for: eight dependent
+      // global round trips per tile would otherwise sit on the epilogue's critical path
+      const float scale = tc_row_scale(a, b);
+      const size_t rowoff = (((size_t)b * a.H + (h0 + hl)) * a.W + (w0 + wl)) * 32;
+      float4 r1[8], r2[8];
+      const bool has1 = a.add1 != nullptr, has2 = a.add2 != nullptr;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        r1[j] = has1 ? __ldg(reinterpret_cast<const float4*>(a.add1 + rowoff) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+        r2[j] = has2 ? __ldg(reinterpret_cast<const float4*>(a.add2 + rowoff) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       uint32_t v[32];
@@ -980,12 +998,27 @@ conv_c32_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(acc));            // accumulator is in registers: the next tile may overwrite it
-      const float scale = tc_row_scale(a, b);
-      const size_t rowoff = (((size_t)b * a.H + (h0 + hl)) * a.W + (w0 + wl)) * 32;
 #pragma unroll
-      for (int j = 0; j < 32; j += 4)
-        tc_store4(a, a.out, rowoff + j, j, scale, __uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
-                  __uint_as_float(v[j + 3]));
+      for (int j = 0; j < 8; ++j) {
+        float o[4] = {__uint_as_float(v[4 * j]) * scale, __uint_as_float(v[4 * j + 1]) * scale, __uint_as_float(v[4 * j + 2]) * scale,
+                      __uint_as_float(v[4 * j + 3]) * scale};
+        if (a.bias) {
+          const float4 bb = __ldg(reinterpret_cast<const float4*>(a.bias) + j);
+          o[0] += bb.x; o[1] += bb.y; o[2] += bb.z; o[3] += bb.w;
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) o[e] = mtd_act(o[e], a.pre_act, a.slope);
+        if (a.aux) *(reinterpret_cast<float4*>(a.aux + rowoff) + j) = make_float4(o[0], o[1], o[2], o[3]);
+        o[0] += r1[j].x + r2[j].x; o[1] += r1[j].y + r2[j].y; o[2] += r1[j].z + r2[j].z; o[3] += r1[j].w + r2[j].w;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) o[e] = mtd_act(o[e], a.post_act, a.slope);
+        if (a.mask_src) {
+          const float4 t = __ldg(reinterpret_cast<const float4*>(a.mask_src + rowoff) + j);
+          o[0] *= mtd_act_grad(t.x, a.mask_act, a.slope); o[1] *= mtd_act_grad(t.y, a.mask_act, a.slope);
+          o[2] *= mtd_act_grad(t.z, a.mask_act, a.slope); o[3] *= mtd_act_grad(t.w, a.mask_act, a.slope);
+        }
+        *(reinterpret_cast<float4*>(a.out + rowoff) + j) = make_float4(o[0], o[1], o[2], o[3]);
+      }
     }
   }
 

@@ -1,192 +1,289 @@
-// Frequency branch of the Res-FFT-Conv block, NHWC fp32, shared-memory radix-2 FFTs.
+// Frequency branch of the Res-FFT-Conv block, NHWC fp32 (C = 32 channels).
 //
 //   rfft2(ortho) -> cat[Re,Im] -> 1x1 conv (2C x 2C) + bias + ReLU -> complex -> irfft2(ortho)
 //   (arch/Ours/networks.py:24-29), decomposed as
 //     P1  fft_rows_fwd     : real FFT along W of every (b,h) row, two channels packed per complex
 //                            transform; writes the half spectrum  X1[b][kw][h][c]  (complex)
-//     P2  fft_cols_mix     : one CTA per (b,kw): complex FFT along H in shared memory (DIF, output
-//                            left bit-reversed), per-frequency channel mix + bias + ReLU in that order,
-//                            inverse FFT along H (DIT, takes bit-reversed input) -> X3[b][kw][h][c]
+//     P2  fft_cols_mix     : one CTA per (b,kw): complex FFT along H, per-frequency channel mix + bias + ReLU,
+//                            inverse FFT along H -> X3[b][kw][h][c]
 //     P3  fft_rows_inv     : half-spectrum inverse along W (Im of columns kw=0 and kw=W/2 dropped,
 //                            SURVEY A1) fused with the block's residual adds  out = fft + add1 + add2
 //   Backward: P1 on the incoming gradient, fft_cols_mix_bwd (recomputes the ReLU mask
 //   from the saved X1, accumulates dW/db partials with the column weights w_k, applies M^T), then P3.
 //
-// No bit-reversal pass is ever executed: the channel mix is frequency-local, so it runs on the
-// bit-reversed order DIF leaves behind and DIT undoes it.
+// Every transform is a four-step FFT (fft_core.cuh): two register-resident radix-2 networks of N1 and N2 points
+// around ONE shared-memory exchange, instead of log2(N) barrier-separated shared-memory passes:
+//   * rows: the (q, n2) thread loads its N1 points straight from global memory (16 channel pairs x 2 positions =
+//     256 contiguous bytes per warp load), so the input never passes through shared memory; the exchange buffer is
+//     written in place and read strided; the real-pair separation  A_k = (Z_k + conj Z_{N-k})/2  takes Z_{N-k} from
+//     the partner lane with ONE warp shuffle (threads k1 and N1-k1 of a channel pair are lanes l and l^16);
+//   * columns: lane = channel, so every shared-memory access is a 256-byte row (conflict-free); the spectrum stays
+//     in [k1][k2] order between the forward and the inverse transform -- the channel mix is frequency-local, so no
+//     reordering pass exists.
+// Supported lengths: 64, 128, 256, 512 (8x8, 8x16, 16x16, 16x32).
 #include <algorithm>
 #include "common.cuh"
+#include "fft_core.cuh"
 #include "mtdgan_b200.h"
 
 namespace {
 
-__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
-__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
-  return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
-}
-__device__ __forceinline__ float2 cmulc(float2 a, float2 b) {   // a * conj(b)
-  return make_float2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y);
-}
+using namespace mtdfft;
 
-// tw[k] = exp(-2*pi*i*k/N), k < N/2
+constexpr int kC = 32, kC2 = 64, kQ = 16;          // channels, mix width, channel pairs (complex sequences per row)
+constexpr int kThreadsFft = 256;
+
+// tw[k] = exp(-2*pi*i*k/N), k < N (full circle: indexed with (n2*k1) mod N)
 __device__ __forceinline__ void fill_twiddles(float2* tw, int N) {
-  for (int k = threadIdx.x; k < N / 2; k += blockDim.x) {
+  for (int k = threadIdx.x; k < N; k += blockDim.x) {
     float s, c;
     sincospif(-2.0f * (float)k / (float)N, &s, &c);
     tw[k] = make_float2(c, s);
   }
 }
 
-// Decimation-in-frequency: natural order in, bit-reversed order out.  Q interleaved sequences:
-// element (n, q) lives at Z[n*Q + q].  INV uses conjugated twiddles.  Ends with __syncthreads().
-template <bool INV>
-__device__ __forceinline__ void fft_dif(float2* Z, const float2* tw, int N, int Q) {
-  const int nb = (N >> 1) * Q;
-  const int lq = __ffs(Q) - 1;                     // N, Q, half are powers of two: shifts instead of integer division
-  for (int half = N >> 1; half >= 1; half >>= 1) {
-    const int lh = __ffs(half) - 1;
-    const int tstep = N >> (lh + 1);
-    for (int idx = threadIdx.x; idx < nb; idx += blockDim.x) {
-      int q = idx & (Q - 1), j = idx >> lq;
-      int pos = j & (half - 1), grp = j >> lh;
-      int i0 = (((grp << (lh + 1)) + pos) << lq) + q, i1 = i0 + (half << lq);
-      float2 a = Z[i0], b = Z[i1];
-      float2 d = csub(a, b), w = tw[pos * tstep];
-      Z[i0] = cadd(a, b);
-      Z[i1] = INV ? cmulc(d, w) : cmul(d, w);
-    }
-    __syncthreads();
-  }
+__device__ __forceinline__ float2 shfl_xor2(float2 v, int m) {
+  return make_float2(__shfl_xor_sync(0xffffffffu, v.x, m), __shfl_xor_sync(0xffffffffu, v.y, m));
 }
 
-// Decimation-in-time: bit-reversed order in, natural order out.
-template <bool INV>
-__device__ __forceinline__ void fft_dit(float2* Z, const float2* tw, int N, int Q) {
-  const int nb = (N >> 1) * Q;
-  const int lq = __ffs(Q) - 1;
-  for (int half = 1; half < N; half <<= 1) {
-    const int lh = __ffs(half) - 1;
-    const int tstep = N >> (lh + 1);
-    for (int idx = threadIdx.x; idx < nb; idx += blockDim.x) {
-      int q = idx & (Q - 1), j = idx >> lq;
-      int pos = j & (half - 1), grp = j >> lh;
-      int i0 = (((grp << (lh + 1)) + pos) << lq) + q, i1 = i0 + (half << lq);
-      float2 w = tw[pos * tstep];
-      float2 a = Z[i0], b = INV ? cmulc(Z[i1], w) : cmul(Z[i1], w);
-      Z[i0] = cadd(a, b);
-      Z[i1] = csub(a, b);
-    }
-    __syncthreads();
-  }
-}
+// rows handled per CTA pass: two when both steps of a row need <= 128 threads (W = 64)
+template <int N1, int N2>
+struct RowsCfg {
+  static constexpr int N = N1 * N2;
+  static constexpr int IA = kQ * N2;                 // step-A items per row: (n2, q)
+  static constexpr int IB = kQ * N1;                 // step-B items per row: (k1, q), warp = the pair {k1, N1-k1}
+  static constexpr int RPB = (IA <= 128 && IB <= 128) ? 2 : 1;
+  static constexpr size_t smem = (size_t)RPB * N * kQ * 8 + (size_t)N * 8;
+};
 
-__device__ __forceinline__ int bitrev(int k, int logn) { return (int)(__brev((unsigned)k) >> (32 - logn)); }
+// k1 of step-B lane: warp w of a row holds k1 = w (lanes 0-15) and N1 - w (lanes 16-31); warp 0 holds the two
+// self-conjugate residues 0 and N1/2
+template <int N1>
+__device__ __forceinline__ int pair_k1(int w, int s) { return w == 0 ? (s ? N1 / 2 : 0) : (s ? N1 - w : w); }
 
 // ------------------------------------------------------------------------------------------------
-// P1: rows forward.  grid = B*H, dynamic smem = W*C*4 + (W/2)*8
+// P1: rows forward.  grid = ceil(B*H / RPB)
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) fft_rows_fwd_kernel(const float* __restrict__ x, float2* __restrict__ spec,
-                                                           int H, int W, int C, int logW) {
+template <int N1, int N2>
+__global__ void __launch_bounds__(kThreadsFft) fft_rows_fwd_kernel(const float* __restrict__ x, float2* __restrict__ spec,
+                                                                 int H, int nrows) {
   mtd_pdl_prologue();
+  using Cfg = RowsCfg<N1, N2>;
+  constexpr int N = Cfg::N, Wh = N / 2 + 1;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  float2* Z = reinterpret_cast<float2*>(smem_raw);                 // [W][Q]
-  const int Q = C >> 1, Wh = (W >> 1) + 1;
-  float2* tw = Z + (size_t)W * Q;
-  const int bh = blockIdx.x, b = bh / H, h = bh - b * H;
-  fill_twiddles(tw, W);
-  const float4* src = reinterpret_cast<const float4*>(x + (size_t)bh * W * C);
-  float4* Z4 = reinterpret_cast<float4*>(Z);
-  for (int i = threadIdx.x; i < W * C / 4; i += blockDim.x) Z4[i] = __ldg(src + i);
+  float2* T = reinterpret_cast<float2*>(smem_raw);                 // [RPB][k1][n2][q]
+  float2* tw = T + (size_t)Cfg::RPB * N * kQ;
+  fill_twiddles(tw, N);
   __syncthreads();
-  fft_dif<false>(Z, tw, W, Q);
-  const float sc = rsqrtf((float)W) * 0.5f;
-  const int lq = __ffs(Q) - 1;                      // Q is a power of two (checked by the entry point)
-  for (int idx = threadIdx.x; idx < Wh * Q; idx += blockDim.x) {
-    int q = idx & (Q - 1), k = idx >> lq;
-    float2 zk = Z[bitrev(k, logW) * Q + q];
-    float2 zm = Z[bitrev((W - k) & (W - 1), logW) * Q + q];
-    zm.y = -zm.y;
-    // A = (zk + zm)/2 ; B = -i (zk - zm)/2
-    float4 o = make_float4((zk.x + zm.x) * sc, (zk.y + zm.y) * sc, (zk.y - zm.y) * sc, -(zk.x - zm.x) * sc);
-    size_t dst = (((size_t)b * Wh + k) * H + h) * C + 2 * q;       // float2 index, even -> 16B aligned
-    *reinterpret_cast<float4*>(spec + dst) = o;
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
-// P3: rows inverse + fused adds.  grid = B*H
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) fft_rows_inv_kernel(const float2* __restrict__ spec, const float* __restrict__ add1,
-                                                           const float* __restrict__ add2, float* __restrict__ out, int H,
-                                                           int W, int C, int logW) {
-  mtd_pdl_prologue();
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  float2* Z = reinterpret_cast<float2*>(smem_raw);
-  const int Q = C >> 1, Wh = (W >> 1) + 1;
-  float2* tw = Z + (size_t)W * Q;
-  const int bh = blockIdx.x, b = bh / H, h = bh - b * H;
-  fill_twiddles(tw, W);
-  const int lq = __ffs(Q) - 1;
-  for (int idx = threadIdx.x; idx < Wh * Q; idx += blockDim.x) {
-    int q = idx & (Q - 1), k = idx >> lq;
-    size_t src = (((size_t)b * Wh + k) * H + h) * C + 2 * q;
-    float4 v = __ldg(reinterpret_cast<const float4*>(spec + src));   // A = (v.x, v.y), B = (v.z, v.w)
-    if (k == 0 || k == (W >> 1)) {
-      Z[k * Q + q] = make_float2(v.x, v.z);                          // imaginary parts dropped (A1)
-    } else {
-      Z[k * Q + q] = make_float2(v.x - v.w, v.y + v.z);              // A + iB
-      Z[(W - k) * Q + q] = make_float2(v.x + v.w, v.z - v.y);        // conj(A) + i conj(B)
+  // ---- step A: N1-point FFTs over n1 of x[N2*n1 + n2], straight from global memory
+  for (int it = threadIdx.x; it < Cfg::RPB * Cfg::IA; it += kThreadsFft) {
+    const int r = it / Cfg::IA, rem = it - r * Cfg::IA;
+    const int n2 = rem >> 4, q = rem & 15;
+    const long long row = (long long)blockIdx.x * Cfg::RPB + r;
+    if (row >= nrows) continue;
+    const float2* src = reinterpret_cast<const float2*>(x + (size_t)row * N * kC) + q;
+    float2 v[N1];
+#pragma unroll
+    for (int n1 = 0; n1 < N1; ++n1) v[n1] = __ldg(src + (size_t)(N2 * n1 + n2) * kQ);
+    fft_reg<N1, false>(v);
+#pragma unroll
+    for (int i = 0; i < N1; ++i) {
+      const int k1 = brev_c(i, N1);
+      const float2 w = tw[(n2 * k1) & (N - 1)];
+      T[((r * N1 + k1) * N2 + n2) * kQ + q] = k1 == 0 ? v[i] : cmul(v[i], w);
     }
   }
   __syncthreads();
-  fft_dif<true>(Z, tw, W, Q);
-  const float sc = rsqrtf((float)W);
-  const size_t base = (size_t)bh * W * C;
-  const float4* Z4 = reinterpret_cast<const float4*>(Z);
-  const int C4 = C >> 2;
-  for (int i = threadIdx.x; i < W * C4; i += blockDim.x) {
-    int n = i >> (lq - 1), j = i & (C4 - 1);         // C4 = Q / 2
-    float4 v = Z4[bitrev(n, logW) * C4 + j];
-    v.x *= sc; v.y *= sc; v.z *= sc; v.w *= sc;
-    size_t o = base + (size_t)i * 4;
-    if (add1) { float4 t = __ldg(reinterpret_cast<const float4*>(add1 + o)); v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w; }
-    if (add2) { float4 t = __ldg(reinterpret_cast<const float4*>(add2 + o)); v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w; }
-    *reinterpret_cast<float4*>(out + o) = v;
+  // ---- step B: N2-point FFTs over n2; real-pair separation with the partner lane; store the half spectrum
+  const float sc = rsqrtf((float)N) * 0.5f;
+  for (int it = threadIdx.x; it < Cfg::RPB * Cfg::IB; it += kThreadsFft) {
+    const int r = it / Cfg::IB, rem = it - r * Cfg::IB;
+    const int w = rem >> 5, lane = rem & 31, s = lane >> 4, q = lane & 15;
+    const long long row = (long long)blockIdx.x * Cfg::RPB + r;
+    if (row >= nrows) continue;                       // warp-uniform (IB is a multiple of 32)
+    const int k1 = pair_k1<N1>(w, s);
+    float2 v[N2];
+#pragma unroll
+    for (int n2 = 0; n2 < N2; ++n2) v[n2] = T[((r * N1 + k1) * N2 + n2) * kQ + q];
+    fft_reg<N2, false>(v);                            // v[j] = Z[k1 + N1 * brev(j)]
+    const int b = (int)(row / H), h = (int)(row - (long long)b * H);
+    float2* dst0 = spec + ((size_t)b * Wh * H + h) * kC + 2 * q;
+#pragma unroll
+    for (int j = 0; j < N2; ++j) {
+      const int k2 = brev_c(j, N2);
+      if (k2 > N2 / 2) continue;
+      if (k2 == N2 / 2 && w != 0) continue;           // k = N/2 exists only for k1 = 0
+      const float2 own1 = v[N2 - 1 - j];              // Z[k1 + N1*(N2-1-k2)]
+      float2 zm;
+      if (w == 0) {
+        const float2 own0 = v[brev_c((N2 - k2) % N2, N2)];       // k1 = 0: Z[N1*(N2-k2)]
+        zm = s ? own1 : own0;
+      } else {
+        zm = shfl_xor2(own1, 16);                     // partner lane holds k1' = N1 - k1: its Z[k1' + N1*(N2-1-k2)] = Z[N-k]
+      }
+      if (k2 == N2 / 2 && s != 0) continue;
+      const float2 zk = v[j];
+      zm.y = -zm.y;                                   // conj(Z[N-k])
+      // A = (zk + zm)/2 ; B = -i (zk - zm)/2 ; ortho scale folded into sc
+      const float4 o = make_float4((zk.x + zm.x) * sc, (zk.y + zm.y) * sc, (zk.y - zm.y) * sc, -(zk.x - zm.x) * sc);
+      const int k = k1 + N1 * k2;
+      *reinterpret_cast<float4*>(dst0 + (size_t)k * H * kC) = o;
+    }
   }
 }
 
 // ------------------------------------------------------------------------------------------------
-// P2: columns + channel mix (C == 32 -> 64 x 64 real mix).  grid = B*Wh
-// smem: S[H][32] float2 | Mt[64][64] | bias[64] | tw[H/2]
+// P3: rows inverse + fused adds.  grid = ceil(B*H / RPB)
 // ------------------------------------------------------------------------------------------------
-constexpr int kC = 32, kC2 = 64;
-
-__global__ void __launch_bounds__(256) fft_cols_mix_kernel(const float2* __restrict__ spec_in, float2* __restrict__ spec_out,
-                                                           const float* __restrict__ w, const float* __restrict__ bias,
-                                                           int H) {
+template <int N1, int N2>
+__global__ void __launch_bounds__(kThreadsFft) fft_rows_inv_kernel(const float2* __restrict__ spec, const float* __restrict__ add1,
+                                                                 const float* __restrict__ add2, float* __restrict__ out, int H,
+                                                                 int nrows) {
   mtd_pdl_prologue();
+  using Cfg = RowsCfg<N1, N2>;
+  constexpr int N = Cfg::N, Wh = N / 2 + 1;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  float2* S = reinterpret_cast<float2*>(smem_raw);
-  float* Mt = reinterpret_cast<float*>(S + (size_t)H * kC);          // Mt[j][o] = w[o][j] / sqrt(H)
-  float* bs = Mt + kC2 * kC2;
-  float2* tw = reinterpret_cast<float2*>(bs + kC2);
-  const size_t slice = (size_t)blockIdx.x * H * kC;
-  const float sH = rsqrtf((float)H);
-  fill_twiddles(tw, H);
-  for (int i = threadIdx.x; i < kC2 * kC2; i += blockDim.x) {
-    int o = i >> 6, j = i & 63;
-    Mt[j * kC2 + o] = __ldg(w + i) * sH;
-  }
-  if (threadIdx.x < kC2) bs[threadIdx.x] = __ldg(bias + threadIdx.x);
-  {
-    const float4* src = reinterpret_cast<const float4*>(spec_in + slice);
-    float4* S4 = reinterpret_cast<float4*>(S);
-    for (int i = threadIdx.x; i < H * kC / 2; i += blockDim.x) S4[i] = __ldg(src + i);
+  float2* T = reinterpret_cast<float2*>(smem_raw);                 // [RPB][k1][n2][q]
+  float2* tw = T + (size_t)Cfg::RPB * N * kQ;
+  fill_twiddles(tw, N);
+  __syncthreads();
+  // ---- step A': thread (q, k1) loads its half-spectrum entries, rebuilds Z[k1 + N1*k2] for all k2 (the upper half
+  //      comes from the partner lane: Z[N-k] = conj(A_k) + i conj(B_k)), N2-point inverse FFT over k2
+  for (int it = threadIdx.x; it < Cfg::RPB * Cfg::IB; it += kThreadsFft) {
+    const int r = it / Cfg::IB, rem = it - r * Cfg::IB;
+    const int w = rem >> 5, lane = rem & 31, s = lane >> 4, q = lane & 15;
+    const long long row = (long long)blockIdx.x * Cfg::RPB + r;
+    if (row >= nrows) continue;                       // warp-uniform
+    const int k1 = pair_k1<N1>(w, s);
+    const int b = (int)(row / H), h = (int)(row - (long long)b * H);
+    const float2* src0 = spec + ((size_t)b * Wh * H + h) * kC + 2 * q;
+    float2 z[N2];
+#pragma unroll
+    for (int k2 = 0; k2 < N2 / 2; ++k2) {
+      const int k = k1 + N1 * k2;
+      const float4 v = __ldg(reinterpret_cast<const float4*>(src0 + (size_t)k * H * kC));   // A = (v.x, v.y), B = (v.z, v.w)
+      const float2 zk = make_float2(v.x - v.w, v.y + v.z);          // A + iB
+      const float2 zmir = make_float2(v.x + v.w, v.z - v.y);        // conj(A) + i conj(B) = Z[N-k]
+      if (w == 0) {
+        if (k2 == 0) {
+          // k1 = 0: k = 0, imaginary parts dropped; k1 = N1/2: an ordinary entry
+          z[0] = s ? zk : make_float2(v.x, v.z);
+          if (N2 > 1) z[N2 - 1] = zmir;               // only meaningful for k1 = N1/2 (overwritten below for k1 = 0)
+        } else {
+          z[k2] = zk;
+          // k1 = 0: Z[N - N1*k2] lives at k2' = N2 - k2; k1 = N1/2: at k2' = N2 - 1 - k2
+          if (s) z[N2 - 1 - k2] = zmir; else z[N2 - k2] = zmir;
+        }
+      } else {
+        z[k2] = zk;
+        z[N2 - 1 - k2] = shfl_xor2(zmir, 16);         // partner's mirrored entry is my Z[k1 + N1*(N2-1-k2)]
+      }
+    }
+    if (w == 0) {
+      // k1 = 0 also owns k = N/2 (k2 = N2/2), imaginary parts dropped; for k1 = N1/2 every register is already set
+      const float4 v = __ldg(reinterpret_cast<const float4*>(src0 + (size_t)(N / 2) * H * kC));
+      if (!s) z[N2 / 2] = make_float2(v.x, v.z);
+    }
+    fft_reg<N2, true>(z);                             // z[j] = u[k1][n2 = brev(j)]
+#pragma unroll
+    for (int j = 0; j < N2; ++j) {
+      const int n2 = brev_c(j, N2);
+      const float2 tws = tw[(n2 * k1) & (N - 1)];
+      T[((r * N1 + k1) * N2 + n2) * kQ + q] = cmulc(z[j], tws);     // * conj(W_N^(n2 k1))
+    }
   }
   __syncthreads();
-  fft_dif<false>(S, tw, H, kC);
+  // ---- step B': thread (q, n2): N1-point inverse FFT over k1, scale, fused adds, store
+  const float sc = rsqrtf((float)N);
+  for (int it = threadIdx.x; it < Cfg::RPB * Cfg::IA; it += kThreadsFft) {
+    const int r = it / Cfg::IA, rem = it - r * Cfg::IA;
+    const int n2 = rem >> 4, q = rem & 15;
+    const long long row = (long long)blockIdx.x * Cfg::RPB + r;
+    if (row >= nrows) continue;
+    float2 v[N1];
+#pragma unroll
+    for (int k1 = 0; k1 < N1; ++k1) v[k1] = T[((r * N1 + k1) * N2 + n2) * kQ + q];
+    fft_reg<N1, true>(v);                             // v[i] = z[n2 + N2 * brev(i)]
+    const size_t base = (size_t)row * N * kC + 2 * q;
+#pragma unroll
+    for (int i = 0; i < N1; ++i) {
+      const int n = n2 + N2 * brev_c(i, N1);
+      const size_t o = base + (size_t)n * kC;
+      float2 val = make_float2(v[i].x * sc, v[i].y * sc);
+      if (add1) { const float2 t = __ldg(reinterpret_cast<const float2*>(add1 + o)); val.x += t.x; val.y += t.y; }
+      if (add2) { const float2 t = __ldg(reinterpret_cast<const float2*>(add2 + o)); val.x += t.x; val.y += t.y; }
+      *reinterpret_cast<float2*>(out + o) = val;
+    }
+  }
+}
 
+// ------------------------------------------------------------------------------------------------
+// column transforms on a [H][32] complex slice in shared memory; lane = channel.
+// forward: global (natural h) -> S in [k1][k2] order;  inverse: S in [k1][k2] order -> global (natural h)
+// ------------------------------------------------------------------------------------------------
+template <int N1, int N2>
+__device__ __forceinline__ void cols_forward(const float2* __restrict__ src, float2* S, const float2* tw) {
+  constexpr int N = N1 * N2;
+  for (int it = threadIdx.x; it < kC * N2; it += blockDim.x) {          // step A: thread (c, n2)
+    const int n2 = it >> 5, c = it & 31;
+    float2 v[N1];
+#pragma unroll
+    for (int n1 = 0; n1 < N1; ++n1) v[n1] = __ldg(src + (size_t)(N2 * n1 + n2) * kC + c);
+    fft_reg<N1, false>(v);
+#pragma unroll
+    for (int i = 0; i < N1; ++i) {
+      const int k1 = brev_c(i, N1);
+      S[(k1 * N2 + n2) * kC + c] = k1 == 0 ? v[i] : cmul(v[i], tw[(n2 * k1) & (N - 1)]);
+    }
+  }
+  __syncthreads();
+  for (int it = threadIdx.x; it < kC * N1; it += blockDim.x) {          // step B: thread (c, k1), in place
+    const int k1 = it >> 5, c = it & 31;
+    float2 v[N2];
+#pragma unroll
+    for (int n2 = 0; n2 < N2; ++n2) v[n2] = S[(k1 * N2 + n2) * kC + c];
+    fft_reg<N2, false>(v);
+#pragma unroll
+    for (int j = 0; j < N2; ++j) S[(k1 * N2 + brev_c(j, N2)) * kC + c] = v[j];     // row k1*N2 + k2 holds X[k1 + N1*k2]
+  }
+  __syncthreads();
+}
+
+template <int N1, int N2>
+__device__ __forceinline__ void cols_inverse(float2* S, const float2* tw, float2* __restrict__ dst, float scale) {
+  constexpr int N = N1 * N2;
+  for (int it = threadIdx.x; it < kC * N1; it += blockDim.x) {          // step A': thread (c, k1), in place
+    const int k1 = it >> 5, c = it & 31;
+    float2 v[N2];
+#pragma unroll
+    for (int k2 = 0; k2 < N2; ++k2) v[k2] = S[(k1 * N2 + k2) * kC + c];
+    fft_reg<N2, true>(v);
+#pragma unroll
+    for (int j = 0; j < N2; ++j) {
+      const int n2 = brev_c(j, N2);
+      S[(k1 * N2 + n2) * kC + c] = k1 == 0 ? v[j] : cmulc(v[j], tw[(n2 * k1) & (N - 1)]);
+    }
+  }
+  __syncthreads();
+  for (int it = threadIdx.x; it < kC * N2; it += blockDim.x) {          // step B': thread (c, n2) -> global
+    const int n2 = it >> 5, c = it & 31;
+    float2 v[N1];
+#pragma unroll
+    for (int k1 = 0; k1 < N1; ++k1) v[k1] = S[(k1 * N2 + n2) * kC + c];
+    fft_reg<N1, true>(v);
+#pragma unroll
+    for (int i = 0; i < N1; ++i) {
+      const int h = n2 + N2 * brev_c(i, N1);
+      dst[(size_t)h * kC + c] = make_float2(v[i].x * scale, v[i].y * scale);
+    }
+  }
+}
+
+// out[r][o] = act( bias[o] + sum_j M[o][j] in[r][j] ) on the 64-wide rows of S (row = one frequency: 32 complex channels =
+// [Re 0..31 | Im 0..31] as input index j, same split for the output index o); 4 x 4 register tiles, in place.
+// Mt[j][o] (transposed, pre-scaled).  RELU: apply max(., 0); else raw.
+template <bool RELU>
+__device__ __forceinline__ void mix_rows(float2* S, const float* Mt, const float* bs, int H) {
   const int tr = threadIdx.x >> 4, to = threadIdx.x & 15;
   float* Sw = reinterpret_cast<float*>(S);
   for (int rb = 0; rb < H; rb += 64) {
@@ -194,15 +291,15 @@ __global__ void __launch_bounds__(256) fft_cols_mix_kernel(const float2* __restr
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
-      for (int j = 0; j < 4; ++j) acc[i][j] = bs[to * 4 + j];
+      for (int j = 0; j < 4; ++j) acc[i][j] = bs ? bs[to * 4 + j] : 0.f;
     const int r0 = rb + tr * 4;
 #pragma unroll 4
     for (int c = 0; c < kC; ++c) {
-      float4 mre = *reinterpret_cast<const float4*>(Mt + c * kC2 + to * 4);
-      float4 mim = *reinterpret_cast<const float4*>(Mt + (c + kC) * kC2 + to * 4);
+      const float4 mre = *reinterpret_cast<const float4*>(Mt + c * kC2 + to * 4);
+      const float4 mim = *reinterpret_cast<const float4*>(Mt + (c + kC) * kC2 + to * 4);
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        float2 y = S[(r0 + i) * kC + c];
+        const float2 y = S[(r0 + i) * kC + c];
         acc[i][0] = fmaf(y.x, mre.x, fmaf(y.y, mim.x, acc[i][0]));
         acc[i][1] = fmaf(y.x, mre.y, fmaf(y.y, mim.y, acc[i][1]));
         acc[i][2] = fmaf(y.x, mre.z, fmaf(y.y, mim.z, acc[i][2]));
@@ -214,33 +311,52 @@ __global__ void __launch_bounds__(256) fft_cols_mix_kernel(const float2* __restr
     for (int i = 0; i < 4; ++i)
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        int o = to * 4 + j;
-        Sw[((r0 + i) * kC + (o & 31)) * 2 + (o >> 5)] = fmaxf(acc[i][j], 0.f);
+        const int o = to * 4 + j;
+        Sw[((r0 + i) * kC + (o & 31)) * 2 + (o >> 5)] = RELU ? fmaxf(acc[i][j], 0.f) : acc[i][j];
       }
-  }
-  __syncthreads();
-  fft_dit<true>(S, tw, H, kC);
-  {
-    float4* dst = reinterpret_cast<float4*>(spec_out + slice);
-    const float4* S4 = reinterpret_cast<const float4*>(S);
-    for (int i = threadIdx.x; i < H * kC / 2; i += blockDim.x) {
-      float4 v = S4[i];
-      v.x *= sH; v.y *= sH; v.z *= sH; v.w *= sH;
-      dst[i] = v;
-    }
   }
 }
 
 // ------------------------------------------------------------------------------------------------
+// P2: columns + channel mix.  grid = B*Wh.   smem: S[H][32] float2 | Mt[64][64] | bias[64] | tw[H]
+// ------------------------------------------------------------------------------------------------
+template <int N1, int N2>
+__global__ void __launch_bounds__(kThreadsFft) fft_cols_mix_kernel(const float2* __restrict__ spec_in, float2* __restrict__ spec_out,
+                                                                 const float* __restrict__ w, const float* __restrict__ bias) {
+  mtd_pdl_prologue();
+  constexpr int H = N1 * N2;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float2* S = reinterpret_cast<float2*>(smem_raw);
+  float* Mt = reinterpret_cast<float*>(S + (size_t)H * kC);          // Mt[j][o] = w[o][j] / sqrt(H)
+  float* bs = Mt + kC2 * kC2;
+  float2* tw = reinterpret_cast<float2*>(bs + kC2);
+  const size_t slice = (size_t)blockIdx.x * H * kC;
+  const float sH = rsqrtf((float)H);
+  fill_twiddles(tw, H);
+  for (int i = threadIdx.x; i < kC2 * kC2; i += blockDim.x) {
+    const int o = i >> 6, j = i & 63;
+    Mt[j * kC2 + o] = __ldg(w + i) * sH;
+  }
+  if (threadIdx.x < kC2) bs[threadIdx.x] = __ldg(bias + threadIdx.x);
+  __syncthreads();
+  cols_forward<N1, N2>(spec_in + slice, S, tw);
+  mix_rows<true>(S, Mt, bs, H);
+  __syncthreads();
+  cols_inverse<N1, N2>(S, tw, spec_out + slice, sH);
+}
+
+// ------------------------------------------------------------------------------------------------
 // Backward of P2.  grid = B*Wh
-// smem: S[H][32] | T[H][32] | Mt[64][64] | Mn[64][64] | bias[64] | tw[H/2]
+// smem: S[H][32] | T[H][32] | Mt[64][64] | Mn[64][64] | bias[64] | tw[H]
 // part: per CTA 64*64 dW partial followed by 64 db partial
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) fft_cols_mix_bwd_kernel(const float2* __restrict__ spec_x, const float2* __restrict__ spec_g,
-                                                               float2* __restrict__ spec_out, const float* __restrict__ w,
-                                                               const float* __restrict__ bias, float* __restrict__ part,
-                                                               int H, int Wh, int W) {
+template <int N1, int N2>
+__global__ void __launch_bounds__(kThreadsFft) fft_cols_mix_bwd_kernel(const float2* __restrict__ spec_x, const float2* __restrict__ spec_g,
+                                                                     float2* __restrict__ spec_out, const float* __restrict__ w,
+                                                                     const float* __restrict__ bias, float* __restrict__ part,
+                                                                     int Wh, int W) {
   mtd_pdl_prologue();
+  constexpr int H = N1 * N2;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float2* S = reinterpret_cast<float2*>(smem_raw);
   float2* T = S + (size_t)H * kC;
@@ -254,25 +370,15 @@ __global__ void __launch_bounds__(256) fft_cols_mix_bwd_kernel(const float2* __r
   const float sH = rsqrtf((float)H);
   fill_twiddles(tw, H);
   for (int i = threadIdx.x; i < kC2 * kC2; i += blockDim.x) {
-    int o = i >> 6, j = i & 63;
-    float v = __ldg(w + i);
+    const int o = i >> 6, j = i & 63;
+    const float v = __ldg(w + i);
     Mt[j * kC2 + o] = v * sH;
     Mn[i] = v;
   }
   if (threadIdx.x < kC2) bs[threadIdx.x] = __ldg(bias + threadIdx.x);
-  {
-    const float4* sx = reinterpret_cast<const float4*>(spec_x + slice);
-    const float4* sg = reinterpret_cast<const float4*>(spec_g + slice);
-    float4* S4 = reinterpret_cast<float4*>(S);
-    float4* T4 = reinterpret_cast<float4*>(T);
-    for (int i = threadIdx.x; i < H * kC / 2; i += blockDim.x) {
-      S4[i] = __ldg(sx + i);
-      T4[i] = __ldg(sg + i);
-    }
-  }
   __syncthreads();
-  fft_dif<false>(S, tw, H, kC);
-  fft_dif<false>(T, tw, H, kC);
+  cols_forward<N1, N2>(spec_x + slice, S, tw);        // S = FFT_H(X1) (unscaled), rows in [k1][k2] order
+  cols_forward<N1, N2>(spec_g + slice, T, tw);        // T = FFT_H(G)  -- same row order, so masks / products line up
 
   const int tr = threadIdx.x >> 4, to = threadIdx.x & 15;
   float* Tw = reinterpret_cast<float*>(T);
@@ -287,11 +393,11 @@ __global__ void __launch_bounds__(256) fft_cols_mix_bwd_kernel(const float2* __r
     const int r0 = rb + tr * 4;
 #pragma unroll 4
     for (int c = 0; c < kC; ++c) {
-      float4 mre = *reinterpret_cast<const float4*>(Mt + c * kC2 + to * 4);
-      float4 mim = *reinterpret_cast<const float4*>(Mt + (c + kC) * kC2 + to * 4);
+      const float4 mre = *reinterpret_cast<const float4*>(Mt + c * kC2 + to * 4);
+      const float4 mim = *reinterpret_cast<const float4*>(Mt + (c + kC) * kC2 + to * 4);
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        float2 y = S[(r0 + i) * kC + c];
+        const float2 y = S[(r0 + i) * kC + c];
         acc[i][0] = fmaf(y.x, mre.x, fmaf(y.y, mim.x, acc[i][0]));
         acc[i][1] = fmaf(y.x, mre.y, fmaf(y.y, mim.y, acc[i][1]));
         acc[i][2] = fmaf(y.x, mre.z, fmaf(y.y, mim.z, acc[i][2]));
@@ -302,8 +408,8 @@ __global__ void __launch_bounds__(256) fft_cols_mix_bwd_kernel(const float2* __r
     for (int i = 0; i < 4; ++i)
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        int o = to * 4 + j;
-        int a = ((r0 + i) * kC + (o & 31)) * 2 + (o >> 5);
+        const int o = to * 4 + j;
+        const int a = ((r0 + i) * kC + (o & 31)) * 2 + (o >> 5);
         if (!(acc[i][j] > 0.f)) Tw[a] = 0.f;
       }
   }
@@ -321,12 +427,12 @@ __global__ void __launch_bounds__(256) fft_cols_mix_bwd_kernel(const float2* __r
       float g[4], y[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        int o = o0 + i;
+        const int o = o0 + i;
         g[i] = Tw[(r * kC + (o & 31)) * 2 + (o >> 5)];
       }
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        int jj = j0 + j;
+        const int jj = j0 + j;
         y[j] = Sf[(r * kC + (jj & 31)) * 2 + (jj >> 5)];
       }
 #pragma unroll
@@ -340,7 +446,7 @@ __global__ void __launch_bounds__(256) fft_cols_mix_bwd_kernel(const float2* __r
     const float sW = wk * sH * sH;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      float4 v = make_float4(acc[i][0] * sW, acc[i][1] * sW, acc[i][2] * sW, acc[i][3] * sW);
+      const float4 v = make_float4(acc[i][0] * sW, acc[i][1] * sW, acc[i][2] * sW, acc[i][3] * sW);
       *reinterpret_cast<float4*>(p + (o0 + i) * kC2 + j0) = v;
     }
     if (to == 0) {
@@ -360,11 +466,11 @@ __global__ void __launch_bounds__(256) fft_cols_mix_bwd_kernel(const float2* __r
     const int r0 = rb + tr * 4;
 #pragma unroll 4
     for (int o = 0; o < kC; ++o) {
-      float4 mre = *reinterpret_cast<const float4*>(Mn + o * kC2 + to * 4);
-      float4 mim = *reinterpret_cast<const float4*>(Mn + (o + kC) * kC2 + to * 4);
+      const float4 mre = *reinterpret_cast<const float4*>(Mn + o * kC2 + to * 4);
+      const float4 mim = *reinterpret_cast<const float4*>(Mn + (o + kC) * kC2 + to * 4);
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        float2 g = T[(r0 + i) * kC + o];     // (gz[o], gz[o+32])
+        const float2 g = T[(r0 + i) * kC + o];     // (gz[o], gz[o+32])
         acc[i][0] = fmaf(g.x, mre.x, fmaf(g.y, mim.x, acc[i][0]));
         acc[i][1] = fmaf(g.x, mre.y, fmaf(g.y, mim.y, acc[i][1]));
         acc[i][2] = fmaf(g.x, mre.z, fmaf(g.y, mim.z, acc[i][2]));
@@ -375,22 +481,12 @@ __global__ void __launch_bounds__(256) fft_cols_mix_bwd_kernel(const float2* __r
     for (int i = 0; i < 4; ++i)
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        int jj = to * 4 + j;
+        const int jj = to * 4 + j;
         Sw[((r0 + i) * kC + (jj & 31)) * 2 + (jj >> 5)] = acc[i][j];
       }
   }
   __syncthreads();
-  fft_dit<true>(S, tw, H, kC);
-  {
-    float4* dst = reinterpret_cast<float4*>(spec_out + slice);
-    const float4* S4 = reinterpret_cast<const float4*>(S);
-    const float s2 = sH * sH;
-    for (int i = threadIdx.x; i < H * kC / 2; i += blockDim.x) {
-      float4 v = S4[i];
-      v.x *= s2; v.y *= s2; v.z *= s2; v.w *= s2;
-      dst[i] = v;
-    }
-  }
+  cols_inverse<N1, N2>(S, tw, spec_out + slice, sH * sH);
 }
 
 __global__ void fft_wgrad_reduce_kernel(const float* __restrict__ part, int nparts, float* __restrict__ dw,
@@ -410,12 +506,6 @@ __global__ void fft_wgrad_reduce_kernel(const float* __restrict__ part, int npar
   else db[i - kC2 * kC2] = s;
 }
 
-int ilog2_exact(int n) {
-  int l = 0;
-  while ((1 << l) < n) ++l;
-  return (1 << l) == n ? l : -1;
-}
-
 template <typename K>
 int set_smem(K kernel, size_t bytes) {
   if (bytes > 227 * 1024) return MTD_EINVAL;
@@ -426,6 +516,18 @@ int set_smem(K kernel, size_t bytes) {
   return MTD_OK;
 }
 
+bool fft_len_ok(int n) { return n == 64 || n == 128 || n == 256 || n == 512; }
+
+// dispatch on the transform length: 64 = 8x8, 128 = 8x16, 256 = 16x16, 512 = 16x32
+#define MTD_FFT_DISPATCH(LEN, CALL) \
+  switch (LEN) {                    \
+    case 64: { CALL(8, 8); break; }   \
+    case 128: { CALL(8, 16); break; } \
+    case 256: { CALL(16, 16); break; } \
+    case 512: { CALL(16, 32); break; } \
+    default: return MTD_EINVAL;       \
+  }
+
 }  // namespace
 
 extern "C" {
@@ -434,59 +536,80 @@ long long mtd_fft_spec_elems(int B, int H, int W, int C) { return (long long)B *
 
 long long mtd_fft_bwd_part_elems(int B, int W) { return (long long)B * (W / 2 + 1) * (kC2 * kC2 + kC2); }
 
+/* 1 when (H, W, C) is a geometry the frequency branch supports: C == 32, H and W in {64, 128, 256, 512}. */
+int mtd_fft_supported(int H, int W, int C) { return (C == kC && fft_len_ok(H) && fft_len_ok(W)) ? 1 : 0; }
+
 int mtd_fft_rows_fwd(const float* x, float* spec, int B, int H, int W, int C, void* stream) {
-  int lw = ilog2_exact(W);
-  MTD_REQUIRE(x && spec && B > 0 && H > 0 && lw >= 3 && W <= 1024 && C >= 4 && (C & (C - 1)) == 0);    // C: power of two
+  MTD_REQUIRE(x && spec && B > 0 && H > 0 && fft_len_ok(W) && C == kC);
   MTD_REQUIRE(mtd_aligned16(x) && mtd_aligned16(spec));
-  size_t smem = (size_t)W * C * 4 + (size_t)(W / 2) * 8;
-  int rc = set_smem(fft_rows_fwd_kernel, smem);
-  if (rc) return rc;
-  mtd_launch(fft_rows_fwd_kernel, B * H, 256, smem, (cudaStream_t)stream, x, reinterpret_cast<float2*>(spec), H, W, C, lw);
+  const int nrows = B * H;
+#define CALL(N1_, N2_)                                                                                              \
+  {                                                                                                                 \
+    using Cfg = RowsCfg<N1_, N2_>;                                                                                  \
+    int rc = set_smem(fft_rows_fwd_kernel<N1_, N2_>, Cfg::smem);                                                    \
+    if (rc) return rc;                                                                                              \
+    mtd_launch(fft_rows_fwd_kernel<N1_, N2_>, (nrows + Cfg::RPB - 1) / Cfg::RPB, kThreadsFft, Cfg::smem, (cudaStream_t)stream, x, \
+               reinterpret_cast<float2*>(spec), H, nrows);                                                          \
+  }
+  MTD_FFT_DISPATCH(W, CALL)
+#undef CALL
   MTD_CHECK_LAUNCH();
   return MTD_OK;
 }
 
 int mtd_fft_rows_inv(const float* spec, const float* add1, const float* add2, float* out, int B, int H, int W, int C,
                      void* stream) {
-  int lw = ilog2_exact(W);
-  MTD_REQUIRE(spec && out && B > 0 && H > 0 && lw >= 3 && W <= 1024 && C >= 4 && (C & (C - 1)) == 0);
+  MTD_REQUIRE(spec && out && B > 0 && H > 0 && fft_len_ok(W) && C == kC);
   MTD_REQUIRE(mtd_aligned16(spec) && mtd_aligned16(out) && mtd_aligned16(add1) && mtd_aligned16(add2));
-  size_t smem = (size_t)W * C * 4 + (size_t)(W / 2) * 8;
-  int rc = set_smem(fft_rows_inv_kernel, smem);
-  if (rc) return rc;
-  mtd_launch(fft_rows_inv_kernel, B * H, 256, smem, (cudaStream_t)stream, reinterpret_cast<const float2*>(spec), add1, add2, out,
-                                                                  H, W, C, lw);
+  const int nrows = B * H;
+#define CALL(N1_, N2_)                                                                                              \
+  {                                                                                                                 \
+    using Cfg = RowsCfg<N1_, N2_>;                                                                                  \
+    int rc = set_smem(fft_rows_inv_kernel<N1_, N2_>, Cfg::smem);                                                    \
+    if (rc) return rc;                                                                                              \
+    mtd_launch(fft_rows_inv_kernel<N1_, N2_>, (nrows + Cfg::RPB - 1) / Cfg::RPB, kThreadsFft, Cfg::smem, (cudaStream_t)stream,    \
+               reinterpret_cast<const float2*>(spec), add1, add2, out, H, nrows);                                   \
+  }
+  MTD_FFT_DISPATCH(W, CALL)
+#undef CALL
   MTD_CHECK_LAUNCH();
   return MTD_OK;
 }
 
 int mtd_fft_cols_mix(const float* spec_in, float* spec_out, const float* w, const float* bias, int B, int H, int W,
                      int C, void* stream) {
-  int lh = ilog2_exact(H);
-  MTD_REQUIRE(spec_in && spec_out && w && bias && B > 0 && lh >= 6 && H <= 512 && W >= 2 && C == kC);
+  MTD_REQUIRE(spec_in && spec_out && w && bias && B > 0 && fft_len_ok(H) && W >= 2 && C == kC);
   MTD_REQUIRE(mtd_aligned16(spec_in) && mtd_aligned16(spec_out));
-  size_t smem = (size_t)H * kC * 8 + (size_t)kC2 * kC2 * 4 + kC2 * 4 + (size_t)(H / 2) * 8;
-  int rc = set_smem(fft_cols_mix_kernel, smem);
-  if (rc) return rc;
-  mtd_launch(fft_cols_mix_kernel, B * (W / 2 + 1), 256, smem, (cudaStream_t)stream, 
-      reinterpret_cast<const float2*>(spec_in), reinterpret_cast<float2*>(spec_out), w, bias, H);
+  const size_t smem = (size_t)H * kC * 8 + (size_t)kC2 * kC2 * 4 + kC2 * 4 + (size_t)H * 8;
+#define CALL(N1_, N2_)                                                                                              \
+  {                                                                                                                 \
+    int rc = set_smem(fft_cols_mix_kernel<N1_, N2_>, smem);                                                         \
+    if (rc) return rc;                                                                                              \
+    mtd_launch(fft_cols_mix_kernel<N1_, N2_>, B * (W / 2 + 1), kThreadsFft, smem, (cudaStream_t)stream,             \
+               reinterpret_cast<const float2*>(spec_in), reinterpret_cast<float2*>(spec_out), w, bias);             \
+  }
+  MTD_FFT_DISPATCH(H, CALL)
+#undef CALL
   MTD_CHECK_LAUNCH();
   return MTD_OK;
 }
 
 int mtd_fft_cols_mix_bwd(const float* spec_x, const float* spec_g, float* spec_out, const float* w, const float* bias,
                          float* part, float* dw, float* db, int B, int H, int W, int C, void* stream) {
-  int lh = ilog2_exact(H);
   MTD_REQUIRE(spec_x && spec_g && spec_out && w && bias && part && dw && db);
-  MTD_REQUIRE(B > 0 && lh >= 6 && H <= 256 && W >= 2 && C == kC);
-  size_t smem = (size_t)H * kC * 16 + (size_t)kC2 * kC2 * 8 + kC2 * 4 + (size_t)(H / 2) * 8;
-  int rc = set_smem(fft_cols_mix_bwd_kernel, smem);
-  if (rc) return rc;
+  MTD_REQUIRE(B > 0 && fft_len_ok(H) && H <= 256 && W >= 2 && C == kC);
+  const size_t smem = (size_t)H * kC * 16 + (size_t)kC2 * kC2 * 8 + kC2 * 4 + (size_t)H * 8;
   const int Wh = W / 2 + 1, nparts = B * Wh;
   cudaStream_t st = (cudaStream_t)stream;
-  mtd_launch(fft_cols_mix_bwd_kernel, nparts, 256, smem, st, reinterpret_cast<const float2*>(spec_x),
-                                                     reinterpret_cast<const float2*>(spec_g),
-                                                     reinterpret_cast<float2*>(spec_out), w, bias, part, H, Wh, W);
+#define CALL(N1_, N2_)                                                                                              \
+  {                                                                                                                 \
+    int rc = set_smem(fft_cols_mix_bwd_kernel<N1_, N2_>, smem);                                                     \
+    if (rc) return rc;                                                                                              \
+    mtd_launch(fft_cols_mix_bwd_kernel<N1_, N2_>, nparts, kThreadsFft, smem, st, reinterpret_cast<const float2*>(spec_x), \
+               reinterpret_cast<const float2*>(spec_g), reinterpret_cast<float2*>(spec_out), w, bias, part, Wh, W);  \
+  }
+  MTD_FFT_DISPATCH(H, CALL)
+#undef CALL
   MTD_CHECK_LAUNCH();
   const int per = kC2 * kC2 + kC2;
   mtd_launch(fft_wgrad_reduce_kernel, (per + 127) / 128, 128, 0, st, part, nparts, dw, db);

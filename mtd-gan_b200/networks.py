@@ -48,6 +48,10 @@ def _normal_init(module: nn.Module):
 class FFT_ConvBlock(nn.Module):
     def __init__(self, out_channels):
         super().__init__()
+        if out_channels != 32:
+            # the reference's class takes any width (ResFFT_Generator's default is 96); MTD-GAN and every ablation row
+            # build it with 32 (networks.py:1870, 1943), which is what the fused frequency-branch kernels are built for
+            raise _ext.MtdError(f"FFT_ConvBlock on the B200 path is built for out_channels=32 (got {out_channels})")
         self.img_conv = nn.Conv2d(out_channels, out_channels, kernel_size=3, stride=1, padding=1)
         self.fft_conv = nn.Conv2d(out_channels * 2, out_channels * 2, kernel_size=1, stride=1, padding=0)
 
