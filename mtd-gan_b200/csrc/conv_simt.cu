@@ -59,6 +59,28 @@ __device__ __forceinline__ float conv_epilogue_one(const ConvArgs& a, float v, s
   return v;
 }
 
+// four consecutive output channels of one pixel (idx % 4 == 0, N % 4 == 0, 16-byte aligned tensors)
+__device__ __forceinline__ float4 conv_epilogue_four(const ConvArgs& a, float4 v, size_t idx, int n) {
+  if (a.scale) {
+    const float sc = __ldg(a.scale + (a.scale_span > 0 ? (long long)idx / a.scale_span : 0));
+    v.x *= sc; v.y *= sc; v.z *= sc; v.w *= sc;
+  }
+  if (a.bias) { const float4 t = __ldg(reinterpret_cast<const float4*>(a.bias + n)); v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w; }
+  v.x = mtd_act(v.x, a.pre_act, a.slope); v.y = mtd_act(v.y, a.pre_act, a.slope);
+  v.z = mtd_act(v.z, a.pre_act, a.slope); v.w = mtd_act(v.w, a.pre_act, a.slope);
+  if (a.aux) *reinterpret_cast<float4*>(a.aux + idx) = v;
+  if (a.add1) { const float4 t = __ldg(reinterpret_cast<const float4*>(a.add1 + idx)); v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w; }
+  if (a.add2) { const float4 t = __ldg(reinterpret_cast<const float4*>(a.add2 + idx)); v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w; }
+  v.x = mtd_act(v.x, a.post_act, a.slope); v.y = mtd_act(v.y, a.post_act, a.slope);
+  v.z = mtd_act(v.z, a.post_act, a.slope); v.w = mtd_act(v.w, a.post_act, a.slope);
+  if (a.mask_src) {
+    const float4 t = __ldg(reinterpret_cast<const float4*>(a.mask_src + idx));
+    v.x *= mtd_act_grad(t.x, a.mask_act, a.slope); v.y *= mtd_act_grad(t.y, a.mask_act, a.slope);
+    v.z *= mtd_act_grad(t.z, a.mask_act, a.slope); v.w *= mtd_act_grad(t.w, a.mask_act, a.slope);
+  }
+  return v;
+}
+
 template <int TM, int TN, bool VEC>
 __global__ void __launch_bounds__(256) conv_igemm_kernel(const __grid_constant__ ConvArgs a) {
   mtd_pdl_prologue();
@@ -236,7 +258,7 @@ __global__ void __launch_bounds__(256) conv_igemm_kernel(const __grid_constant__
 //   conv_n1_kernel : N <= 4 outputs            out[p][n] = epi( sum_t sum_c in[p@t][c] * W[n][t][c] )
 //                    (s_/r_dconv61 128->1, generator decoder[0] 32->1; dgrad of every Cin = 1 layer)
 // ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) conv_c1_kernel(const __grid_constant__ ConvArgs a) {
+__global__ void __launch_bounds__(256) conv_c1_kernel(const __grid_constant__ ConvArgs a, int vec4) {
   mtd_pdl_prologue();
   extern __shared__ __align__(16) float wsm[];   // [T][N4]  (N padded to a multiple of 4, zero filled)
   const int N4 = (a.N + 3) & ~3;
@@ -275,6 +297,11 @@ __global__ void __launch_bounds__(256) conv_c1_kernel(const __grid_constant__ Co
       }
     }
     const size_t pix = ((size_t)b * a.outH + (oy * a.omy + a.ooy)) * a.outW + (ox * a.omx + a.oox);
+    if (vec4) {                                     // N % 4 == 0 and 16-byte aligned epilogue operands: one 16-byte store
+      const size_t idx = pix * a.N + nq * 4;
+      *reinterpret_cast<float4*>(a.out + idx) = conv_epilogue_four(a, acc, idx, nq * 4);
+      continue;
+    }
     const float accv[4] = {acc.x, acc.y, acc.z, acc.w};
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
@@ -347,6 +374,61 @@ __global__ void __launch_bounds__(256) conv_n1_kernel(const __grid_constant__ Co
         }
       }
     }
+  }
+}
+
+// N = 1 output channel, 3 x 3 taps, stride 1 (s_dconv61 / r_dconv61 128 -> 1, generator decoder[0] 32 -> 1, data gradient of
+// the 1 -> 64 stem): tile version.  out[p] = sum_t in[p + d_t] . w[t] = sum_t q_t[p + d_t] with q_t[p'] = in[p'] . w[t]:
+// every input pixel of an (8+2) x (64+2) halo tile is read ONCE (float4 per lane, Ctot/4 lanes per pixel, the lane's 36
+// weights in registers), its nine per-tap dot products go to shared memory, then each output pixel gathers nine scalars.
+// The pixel-major kernel above re-reads every input pixel nine times through L1/L2 (130 us for 84 MB at B = 40).
+constexpr int kN1TileH = 8, kN1TileW = 64, kN1HaloW = kN1TileW + 2, kN1HaloPix = (kN1TileH + 2) * kN1HaloW;
+
+__global__ void __launch_bounds__(256) conv_n1t_kernel(const __grid_constant__ ConvArgs a, int lpp) {
+  mtd_pdl_prologue();
+  __shared__ float q[kN1HaloPix * 9];
+  const int Ctot = a.C1 + a.C2;
+  const int tiles_x = a.W / kN1TileW, tiles_y = a.H / kN1TileH;
+  int tile = blockIdx.x;
+  const int tx = tile % tiles_x; tile /= tiles_x;
+  const int ty = tile % tiles_y;
+  const int b = tile / tiles_y;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int ppw = 32 / lpp, sub = lane / lpp, l = lane - sub * lpp;
+  const int c = l * 4;
+  const float* src = c < a.C1 ? a.src1 + c : a.src2 + (c - a.C1);
+  const int Cs = c < a.C1 ? a.C1 : a.C2;
+  float4 w[9];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) w[t] = __ldg(reinterpret_cast<const float4*>(a.wp + (size_t)t * Ctot + c));
+  const int y0 = ty * kN1TileH - 1, x0 = tx * kN1TileW - 1;
+  for (int hp0 = warp * ppw; hp0 < kN1HaloPix; hp0 += 8 * ppw) {
+    const int hp = hp0 + sub;
+    const int hy = hp / kN1HaloW, hx = hp - hy * kN1HaloW;
+    const int y = y0 + hy, x = x0 + hx;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (hp < kN1HaloPix && y >= 0 && y < a.H && x >= 0 && x < a.W)
+      v = __ldg(reinterpret_cast<const float4*>(src + (((size_t)b * a.H + y) * a.W + x) * Cs));
+    float s[9];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) s[t] = fmaf(v.x, w[t].x, fmaf(v.y, w[t].y, fmaf(v.z, w[t].z, v.w * w[t].w)));
+#pragma unroll
+    for (int t = 0; t < 9; ++t)
+      for (int o = lpp >> 1; o > 0; o >>= 1) s[t] += __shfl_xor_sync(0xffffffffu, s[t], o);
+    if (hp < kN1HaloPix) {
+#pragma unroll
+      for (int t = 0; t < 9; ++t)
+        if (l == (t & (lpp - 1))) q[hp * 9 + t] = s[t];      // lpp >= 8: lane t (lane 0 also takes t = 8 when lpp == 8)
+    }
+  }
+  __syncthreads();
+  for (int op = threadIdx.x; op < kN1TileH * kN1TileW; op += blockDim.x) {
+    const int oy = op / kN1TileW, ox = op - oy * kN1TileW;
+    float acc = 0.f;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) acc += q[((oy + 1 + a.dy[t]) * kN1HaloW + (ox + 1 + a.dx[t])) * 9 + t];
+    const size_t idx = ((size_t)b * a.H + (ty * kN1TileH + oy)) * a.W + (tx * kN1TileW + ox);
+    a.out[idx] = conv_epilogue_one(a, acc, idx, 0);
   }
 }
 
@@ -444,9 +526,24 @@ int launch_conv(ConvArgs& a, cudaStream_t st) {
   if (Ctot == 1 && a.T * a.N * sizeof(float) <= 40 * 1024) {                 // single-channel source: streaming kernel
     size_t work = (size_t)M * ((a.N + 3) / 4);
     int blocks = (int)std::min<size_t>((work + 255) / 256, (size_t)mtd_sm_count() * 16);
-    mtd_launch(conv_c1_kernel, blocks, 256, a.T * ((a.N + 3) & ~3) * sizeof(float), st, a);
+    auto al = [](const void* p) { return p == nullptr || mtd_aligned16(p); };
+    const int vec4 = (a.N % 4 == 0 && mtd_aligned16(a.out) && al(a.bias) && al(a.add1) && al(a.add2) && al(a.mask_src) && al(a.aux) &&
+                      (a.scale_span == 0 || a.scale_span % 4 == 0)) ? 1 : 0;
+    mtd_launch(conv_c1_kernel, blocks, 256, a.T * ((a.N + 3) & ~3) * sizeof(float), st, a, vec4);
     MTD_CHECK_LAUNCH();
     return MTD_OK;
+  }
+  {   // N = 1, 3 x 3 neighbourhood, stride 1, dense output: halo-tile kernel (every input pixel read once)
+    bool nb = a.N == 1 && a.T == 9 && a.sy == 1 && a.sx == 1 && a.Ho == a.H && a.Wo == a.W && a.outH == a.H && a.outW == a.W &&
+              a.omy == 1 && a.omx == 1 && a.ooy == 0 && a.oox == 0 && vec && (Ctot == 32 || Ctot == 64 || Ctot == 128) &&
+              a.W % kN1TileW == 0 && a.H % kN1TileH == 0;
+    for (int t = 0; nb && t < 9; ++t) nb = a.dy[t] >= -1 && a.dy[t] <= 1 && a.dx[t] >= -1 && a.dx[t] <= 1;
+    if (nb) {
+      const int tiles = a.B * (a.H / kN1TileH) * (a.W / kN1TileW);
+      mtd_launch(conv_n1t_kernel, tiles, 256, 0, st, a, Ctot / 4);
+      MTD_CHECK_LAUNCH();
+      return MTD_OK;
+    }
   }
   if (a.N <= 4 && vec && Ctot >= 8 && (size_t)a.N * a.T * Ctot * sizeof(float) <= 40 * 1024) {   // few outputs, many channels
     int lpp = 1;
@@ -711,6 +808,43 @@ __global__ void __launch_bounds__(256) finish_dot_kernel(const FinSeg* __restric
   if (threadIdx.x == 0) atomicAdd(dots + s.slot, acc);
 }
 
+// Accumulate, for one chunk of whole packed rows, every forward instance of the weight into shared memory at the
+// reference-layout position.  TT > 0: compile-time tap count; CPOW2: channel count is a power of two.
+template <int TT, bool CPOW2>
+__device__ __forceinline__ void fin_accumulate(const FinSeg* __restrict__ segs, int2 ck, const double* __restrict__ dots, float* sm,
+                                               int cnt, int C, int n0) {
+  const int T = TT > 0 ? TT : (int)segs[ck.x].T;
+  const int row = T * C;
+  const int lc = CPOW2 ? (__ffs(C) - 1) : 0;
+  long long si = ck.x;
+  while (si >= 0) {                                   // every forward instance (and batched group) that used this weight
+    const FinSeg& s = segs[si];
+    const float* gp = s.gp + ck.y;
+    if (s.inv_sigma) {
+      const float alpha = __ldg(s.inv_sigma);
+      // <G, W~> = <G, W_orig> / sigma; from the activations it is alpha^-1 * sum dz.(y_pre - b) * alpha = that sum itself
+      const float beta = s.dot_zw ? (float)(*s.dot_zw) : (float)dots[s.slot] * alpha;
+      const float coef = alpha * beta;                // dW = a_gp * gp - coef * u v^T
+      const bool nogp = (s.flip & kFinNoGp) != 0;     // correction-only instance (its gp is part of another instance's)
+      const float a_gp = (s.flip & kFinPrescaled) ? 1.f : alpha;
+      for (int j = threadIdx.x; j < cnt; j += blockDim.x) {
+        const int c = CPOW2 ? (j & (C - 1)) : (j % C), r = CPOW2 ? (j >> lc) : (j / C);
+        const int nl = r / T, t = r - nl * T;
+        const int col = c * T + t;                    // reference (Cout, Cin*kh*kw) matrix view: row = n, col = c*T + t
+        const float g = (nogp ? 0.f : a_gp * gp[j]) - coef * __ldg(s.u + n0 + nl) * __ldg(s.v + col);
+        sm[fin_pad(nl * row + col)] += g;
+      }
+    } else {
+      for (int j = threadIdx.x; j < cnt; j += blockDim.x) {
+        const int c = CPOW2 ? (j & (C - 1)) : (j % C), r = CPOW2 ? (j >> lc) : (j / C);
+        const int nl = r / T, t = r - nl * T;
+        sm[fin_pad(nl * row + c * T + t)] += gp[j];
+      }
+    }
+    si = s.next;
+  }
+}
+
 __global__ void __launch_bounds__(256) finish_unpack_kernel(const FinSeg* __restrict__ segs, const int2* __restrict__ chunks,
                                                             const double* __restrict__ dots) {
   mtd_pdl_prologue();
@@ -720,36 +854,18 @@ __global__ void __launch_bounds__(256) finish_unpack_kernel(const FinSeg* __rest
   const size_t total = (size_t)head.N * head.T * head.C;
   const size_t end = min(total, (size_t)ck.y + (size_t)fin_chunk_elems(head.T, head.C));
   if (fin_row_major(head)) {
-    // Conv2d / Linear layout, whole packed rows: 32-bit index arithmetic only, per-instance constants hoisted out of
-    // the element loop, sums accumulated in shared memory at the element's REFERENCE position, one coalesced store.
-    const int cnt = (int)(end - ck.y), T = (int)head.T, C = (int)head.C, row = T * C;
-    const int n0 = (int)(ck.y / (size_t)row);
+    // Conv2d / Linear layout, whole packed rows: sums accumulated in shared memory at the element's REFERENCE position,
+    // one coalesced store.  The (t, c) decomposition of the packed index is the inner loop of a 60-140 MB pass per
+    // backward sweep, so it is compiled for the tap counts the model has (1, 9, 16: constant divisions) and uses shifts
+    // for power-of-two channel counts.
+    const int cnt = (int)(end - ck.y), T = (int)head.T, C = (int)head.C;
+    const int n0 = (int)(ck.y / (size_t)(T * C));
     for (int j = threadIdx.x; j < cnt; j += blockDim.x) sm[fin_pad(j)] = 0.f;      // each thread owns its j's throughout
-    long long si = ck.x;
-    while (si >= 0) {                                   // every forward instance (and batched group) that used this weight
-      const FinSeg& s = segs[si];
-      const float* gp = s.gp + ck.y;
-      if (s.inv_sigma) {
-        const float alpha = __ldg(s.inv_sigma);
-        // <G, W~> = <G, W_orig> / sigma; from the activations it is alpha^-1 * sum dz.(y_pre - b) * alpha = that sum itself
-        const float beta = s.dot_zw ? (float)(*s.dot_zw) : (float)dots[s.slot] * alpha;
-        const float coef = alpha * beta;                // dW = a_gp * gp - coef * u v^T
-        const bool nogp = (s.flip & kFinNoGp) != 0;     // correction-only instance (its gp is part of another instance's)
-        const float a_gp = (s.flip & kFinPrescaled) ? 1.f : alpha;
-        for (int j = threadIdx.x; j < cnt; j += blockDim.x) {
-          const int c = j % C, r = j / C, t = r % T, nl = r / T;
-          const int col = c * T + t;                    // reference (Cout, Cin*kh*kw) matrix view: row = n, col = c*T + t
-          const float g = (nogp ? 0.f : a_gp * gp[j]) - coef * __ldg(s.u + n0 + nl) * __ldg(s.v + col);
-          sm[fin_pad(nl * row + col)] += g;
-        }
-      } else {
-        for (int j = threadIdx.x; j < cnt; j += blockDim.x) {
-          const int c = j % C, r = j / C, t = r % T, nl = r / T;
-          sm[fin_pad(nl * row + c * T + t)] += gp[j];
-        }
-      }
-      si = s.next;
-    }
+    const bool cpow2 = (C & (C - 1)) == 0;
+    if (T == 9 && cpow2) fin_accumulate<9, true>(segs, ck, dots, sm, cnt, C, n0);
+    else if (T == 16 && cpow2) fin_accumulate<16, true>(segs, ck, dots, sm, cnt, C, n0);
+    else if (T == 1 && cpow2) fin_accumulate<1, true>(segs, ck, dots, sm, cnt, C, n0);
+    else fin_accumulate<0, false>(segs, ck, dots, sm, cnt, C, n0);
     __syncthreads();
     for (int j = threadIdx.x; j < cnt; j += blockDim.x) head.dw[ck.y + j] = sm[fin_pad(j)];
     return;

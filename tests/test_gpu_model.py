@@ -503,5 +503,8 @@ def test_captured_step_follows_lr_schedule():
         moved = torch.cat([(v - w0[k]).abs().flatten() for k, v in m.state_dict().items()
                            if k.endswith(("weight_orig", "weight")) and v.dim() == 4])
         res.append(float(moved.mean()))
+        big = [(k, float((v - w0[k]).abs().max())) for k, v in m.state_dict().items()
+               if not k.endswith(("weight_u", "weight_v")) and float((v - w0[k]).abs().max()) > 2.5 * 3e-5]
+        print("graph" if use_graph else "eager", "parameters that moved by more than 2.5 x lr:", len(big), big[:8])
     print("mean |dw| after one step at lr 3e-5: eager %.3e, graph %.3e" % tuple(res))
     assert abs(res[1] - res[0]) <= 0.05 * res[0] and res[0] < 5e-5
