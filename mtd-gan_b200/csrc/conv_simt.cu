@@ -384,42 +384,53 @@ __global__ void __launch_bounds__(256) conv_n1_kernel(const __grid_constant__ Co
 // The pixel-major kernel above re-reads every input pixel nine times through L1/L2 (130 us for 84 MB at B = 40).
 constexpr int kN1TileH = 8, kN1TileW = 64, kN1HaloW = kN1TileW + 2, kN1HaloPix = (kN1TileH + 2) * kN1HaloW;
 
-__global__ void __launch_bounds__(256) conv_n1t_kernel(const __grid_constant__ ConvArgs a, int lpp) {
+// One THREAD per halo pixel: its Ctot channels are consecutive in memory (NHWC), read as float4s with several loads in
+// flight; the nine tap weights of a channel quad come from shared memory as warp-wide broadcasts.  No cross-lane
+// reduction: the nine dot products of a pixel live in nine registers of its thread.
+__global__ void __launch_bounds__(256) conv_n1t_kernel(const __grid_constant__ ConvArgs a) {
   mtd_pdl_prologue();
-  __shared__ float q[kN1HaloPix * 9];
-  const int Ctot = a.C1 + a.C2;
+  extern __shared__ __align__(16) float n1_smem[];
+  const int Ctot = a.C1 + a.C2, C4 = Ctot >> 2;
+  float4* w4 = reinterpret_cast<float4*>(n1_smem);                  // [9][Ctot/4]
+  float* q = n1_smem + 9 * Ctot;                                    // [halo pixel][9]
+  for (int i = threadIdx.x; i < 9 * C4; i += blockDim.x) w4[i] = __ldg(reinterpret_cast<const float4*>(a.wp) + i);
   const int tiles_x = a.W / kN1TileW, tiles_y = a.H / kN1TileH;
   int tile = blockIdx.x;
   const int tx = tile % tiles_x; tile /= tiles_x;
   const int ty = tile % tiles_y;
   const int b = tile / tiles_y;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int ppw = 32 / lpp, sub = lane / lpp, l = lane - sub * lpp;
-  const int c = l * 4;
-  const float* src = c < a.C1 ? a.src1 + c : a.src2 + (c - a.C1);
-  const int Cs = c < a.C1 ? a.C1 : a.C2;
-  float4 w[9];
-#pragma unroll
-  for (int t = 0; t < 9; ++t) w[t] = __ldg(reinterpret_cast<const float4*>(a.wp + (size_t)t * Ctot + c));
   const int y0 = ty * kN1TileH - 1, x0 = tx * kN1TileW - 1;
-  for (int hp0 = warp * ppw; hp0 < kN1HaloPix; hp0 += 8 * ppw) {
-    const int hp = hp0 + sub;
+  __syncthreads();
+  for (int hp = threadIdx.x; hp < kN1HaloPix; hp += blockDim.x) {
     const int hy = hp / kN1HaloW, hx = hp - hy * kN1HaloW;
     const int y = y0 + hy, x = x0 + hx;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (hp < kN1HaloPix && y >= 0 && y < a.H && x >= 0 && x < a.W)
-      v = __ldg(reinterpret_cast<const float4*>(src + (((size_t)b * a.H + y) * a.W + x) * Cs));
     float s[9];
 #pragma unroll
-    for (int t = 0; t < 9; ++t) s[t] = fmaf(v.x, w[t].x, fmaf(v.y, w[t].y, fmaf(v.z, w[t].z, v.w * w[t].w)));
+    for (int t = 0; t < 9; ++t) s[t] = 0.f;
+    if (y >= 0 && y < a.H && x >= 0 && x < a.W) {
+      const size_t pix = ((size_t)b * a.H + y) * a.W + x;
+      for (int src = 0; src < 2; ++src) {
+        const int Cs = src == 0 ? a.C1 : a.C2;
+        if (Cs == 0) continue;
+        const float4* p = reinterpret_cast<const float4*>((src == 0 ? a.src1 : a.src2) + pix * Cs);
+        const float4* wq = w4 + (src == 0 ? 0 : (a.C1 >> 2));
+        for (int c0 = 0; c0 < (Cs >> 2); c0 += 4) {          // Cs is a multiple of 16 (32 / 64 / 128 channel layers)
+          float4 v[4];
 #pragma unroll
-    for (int t = 0; t < 9; ++t)
-      for (int o = lpp >> 1; o > 0; o >>= 1) s[t] += __shfl_xor_sync(0xffffffffu, s[t], o);
-    if (hp < kN1HaloPix) {
+          for (int u = 0; u < 4; ++u) v[u] = __ldg(p + c0 + u);
 #pragma unroll
-      for (int t = 0; t < 9; ++t)
-        if (l == (t & (lpp - 1))) q[hp * 9 + t] = s[t];      // lpp >= 8: lane t (lane 0 also takes t = 8 when lpp == 8)
+          for (int u = 0; u < 4; ++u) {
+#pragma unroll
+            for (int t = 0; t < 9; ++t) {
+              const float4 w = wq[t * C4 + c0 + u];
+              s[t] = fmaf(v[u].x, w.x, fmaf(v[u].y, w.y, fmaf(v[u].z, w.z, fmaf(v[u].w, w.w, s[t]))));
+            }
+          }
+        }
+      }
     }
+#pragma unroll
+    for (int t = 0; t < 9; ++t) q[hp * 9 + t] = s[t];
   }
   __syncthreads();
   for (int op = threadIdx.x; op < kN1TileH * kN1TileW; op += blockDim.x) {
@@ -535,12 +546,12 @@ int launch_conv(ConvArgs& a, cudaStream_t st) {
   }
   {   // N = 1, 3 x 3 neighbourhood, stride 1, dense output: halo-tile kernel (every input pixel read once)
     bool nb = a.N == 1 && a.T == 9 && a.sy == 1 && a.sx == 1 && a.Ho == a.H && a.Wo == a.W && a.outH == a.H && a.outW == a.W &&
-              a.omy == 1 && a.omx == 1 && a.ooy == 0 && a.oox == 0 && vec && (Ctot == 32 || Ctot == 64 || Ctot == 128) &&
+              a.omy == 1 && a.omx == 1 && a.ooy == 0 && a.oox == 0 && vec && a.C1 % 16 == 0 && a.C2 % 16 == 0 && Ctot <= 256 &&
               a.W % kN1TileW == 0 && a.H % kN1TileH == 0;
     for (int t = 0; nb && t < 9; ++t) nb = a.dy[t] >= -1 && a.dy[t] <= 1 && a.dx[t] >= -1 && a.dx[t] <= 1;
     if (nb) {
       const int tiles = a.B * (a.H / kN1TileH) * (a.W / kN1TileW);
-      mtd_launch(conv_n1t_kernel, tiles, 256, 0, st, a, Ctot / 4);
+      mtd_launch(conv_n1t_kernel, tiles, 256, (size_t)(9 * Ctot + kN1HaloPix * 9) * sizeof(float), st, a);
       MTD_CHECK_LAUNCH();
       return MTD_OK;
     }
@@ -860,7 +871,8 @@ __global__ void __launch_bounds__(256) finish_unpack_kernel(const FinSeg* __rest
     // for power-of-two channel counts.
     const int cnt = (int)(end - ck.y), T = (int)head.T, C = (int)head.C;
     const int n0 = (int)(ck.y / (size_t)(T * C));
-    for (int j = threadIdx.x; j < cnt; j += blockDim.x) sm[fin_pad(j)] = 0.f;      // each thread owns its j's throughout
+    for (int j = threadIdx.x; j < cnt; j += blockDim.x) sm[fin_pad(j)] = 0.f;
+    __syncthreads();        // the accumulation below writes PERMUTED positions (another thread's j): zeroing must be complete
     const bool cpow2 = (C & (C - 1)) == 0;
     if (T == 9 && cpow2) fin_accumulate<9, true>(segs, ck, dots, sm, cnt, C, n0);
     else if (T == 16 && cpow2) fin_accumulate<16, true>(segs, ck, dots, sm, cnt, C, n0);

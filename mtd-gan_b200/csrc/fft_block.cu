@@ -489,21 +489,34 @@ __global__ void __launch_bounds__(kThreadsFft) fft_cols_mix_bwd_kernel(const flo
   cols_inverse<N1, N2>(S, tw, spec_out + slice, sH * sH);
 }
 
-__global__ void fft_wgrad_reduce_kernel(const float* __restrict__ part, int nparts, float* __restrict__ dw,
-                                        float* __restrict__ db) {
+// dW / db = ordered sum of the per-CTA partials.  32 output elements per block, 8 lanes of partial index per element:
+// lane g sums partials p = g, g + 8, ... (Kahan), the eight lane sums are added in lane order -- deterministic, and 8 x
+// the parallelism of one thread per element (660 partials of 16.6 KB at B = 20).
+__global__ void __launch_bounds__(256) fft_wgrad_reduce_kernel(const float* __restrict__ part, int nparts, float* __restrict__ dw,
+                                                              float* __restrict__ db) {
   mtd_pdl_prologue();
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  __shared__ float sh[8][33];
   const int per = kC2 * kC2 + kC2;
-  if (i >= per) return;
+  const int e = threadIdx.x & 31, g = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + e;
   float s = 0.f, comp = 0.f;     // Kahan: hundreds of partials of mixed sign
-  for (int p = 0; p < nparts; ++p) {
-    float v = __ldg(part + (size_t)p * per + i) - comp;
-    float t = s + v;
-    comp = (t - s) - v;
-    s = t;
+  if (i < per) {
+    for (int p = g; p < nparts; p += 8) {
+      const float v = __ldg(part + (size_t)p * per + i) - comp;
+      const float t = s + v;
+      comp = (t - s) - v;
+      s = t;
+    }
   }
-  if (i < kC2 * kC2) dw[i] = s;
-  else db[i - kC2 * kC2] = s;
+  sh[g][e] = s;
+  __syncthreads();
+  if (g == 0 && i < per) {
+    float tot = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) tot += sh[k][e];
+    if (i < kC2 * kC2) dw[i] = tot;
+    else db[i - kC2 * kC2] = tot;
+  }
 }
 
 template <typename K>
@@ -612,7 +625,7 @@ int mtd_fft_cols_mix_bwd(const float* spec_x, const float* spec_g, float* spec_o
 #undef CALL
   MTD_CHECK_LAUNCH();
   const int per = kC2 * kC2 + kC2;
-  mtd_launch(fft_wgrad_reduce_kernel, (per + 127) / 128, 128, 0, st, part, nparts, dw, db);
+  mtd_launch(fft_wgrad_reduce_kernel, (per + 31) / 32, 256, 0, st, part, nparts, dw, db);
   MTD_CHECK_LAUNCH();
   return MTD_OK;
 }

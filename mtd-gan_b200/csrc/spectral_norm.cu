@@ -40,26 +40,35 @@ __global__ void __launch_bounds__(256) sn_wtu_kernel(const SnLayer* __restrict__
   t_ws[L.poff + (long long)(wk.z / kRowsPerWtu) * L.cols + col] = acc;
 }
 
-// one CTA per layer: v = t / max(|t|, eps)
-__global__ void __launch_bounds__(256) sn_norm_v_kernel(const SnLayer* __restrict__ tab, const float* __restrict__ t_ws,
-                                                        float* __restrict__ v_snap, float eps) {
+// t = W^T u: ordered sum of the row-block partials, one thread per column (work items with row0 == 0 do the work, so
+// the reduction runs on as many CTAs as the layer has 256-column chunks); staged in the snapshot slot.
+__global__ void __launch_bounds__(256) sn_reduce_t_kernel(const SnLayer* __restrict__ tab, const int4* __restrict__ work,
+                                                          const float* __restrict__ t_ws, float* __restrict__ v_snap) {
+  mtd_pdl_prologue();
+  const int4 wk = work[blockIdx.x];
+  if (wk.z != 0) return;
+  const SnLayer L = tab[wk.x];
+  const long long col = wk.y + threadIdx.x;
+  if (col >= L.cols) return;
+  const float* part = t_ws + L.poff + col;
+  const int nrb = (int)((L.rows + kRowsPerWtu - 1) / kRowsPerWtu);
+  float x = 0.f;
+  for (int rb = 0; rb < nrb; ++rb) x += part[(long long)rb * L.cols];      // fixed order
+  v_snap[L.voff + col] = x;
+}
+
+// one CTA per layer: v = t / max(|t|, eps)   (t staged in the snapshot slot, normalised in place)
+__global__ void __launch_bounds__(256) sn_norm_v_kernel(const SnLayer* __restrict__ tab, float* __restrict__ v_snap, float eps) {
   mtd_pdl_prologue();
   __shared__ float sh[32];
   const SnLayer L = tab[blockIdx.x];
-  const float* part = t_ws + L.poff;
-  const int nrb = (int)((L.rows + kRowsPerWtu - 1) / kRowsPerWtu);
-  float* t = v_snap + L.voff;                      // t = W^T u staged in the snapshot slot, normalised in place below
+  float* t = v_snap + L.voff;
   float ss = 0.f;
-  for (int k = threadIdx.x; k < L.cols; k += blockDim.x) {
-    float x = 0.f;
-    for (int rb = 0; rb < nrb; ++rb) x += part[(long long)rb * L.cols + k];      // fixed order
-    t[k] = x;
-    ss = fmaf(x, x, ss);
-  }
+  for (int k = threadIdx.x; k < L.cols; k += blockDim.x) { const float x = t[k]; ss = fmaf(x, x, ss); }
   ss = block_sum(ss, sh, true);
   const float inv = 1.f / fmaxf(sqrtf(ss), eps);
-  for (int k = threadIdx.x; k < L.cols; k += blockDim.x) {     // each thread re-reads only what it wrote
-    float x = t[k] * inv;
+  for (int k = threadIdx.x; k < L.cols; k += blockDim.x) {
+    const float x = t[k] * inv;
     L.v[k] = x;
     t[k] = x;
   }
@@ -139,7 +148,9 @@ int mtd_sn_power_iter(const void* layer_tab, int n_layers, const void* work_wtu,
     MTD_REQUIRE(work_wtu && t_ws && n_wtu > 0 && t_elems > 0);
     mtd_launch(sn_wtu_kernel, n_wtu, 256, 0, st, tab, reinterpret_cast<const int4*>(work_wtu), t_ws);
     MTD_CHECK_LAUNCH();
-    mtd_launch(sn_norm_v_kernel, n_layers, 256, 0, st, tab, t_ws, v_snap, eps);
+    mtd_launch(sn_reduce_t_kernel, n_wtu, 256, 0, st, tab, reinterpret_cast<const int4*>(work_wtu), t_ws, v_snap);
+    MTD_CHECK_LAUNCH();
+    mtd_launch(sn_norm_v_kernel, n_layers, 256, 0, st, tab, v_snap, eps);
     MTD_CHECK_LAUNCH();
   } else {
     mtd_launch(sn_copy_v_kernel, n_layers, 256, 0, st, tab, v_snap);

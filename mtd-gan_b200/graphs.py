@@ -35,13 +35,17 @@ class GraphedTrainStep:
         self._last = list(D.last_shared_parameters())
         self._post_g_backward = post_g_backward      # e.g. the generator-gradient all-reduce at N > 1
         self._d_params = list(D.parameters())
+        # Re-packing is restricted to THIS model's parameters: the pack registry is process-wide, and a captured step must
+        # never contain writes into the pack buffers of another (possibly soon-to-be-freed) model -- a replay would then
+        # write into memory that has been handed to someone else.
+        self._all_params = list(model.parameters())
         self.graph = None
         self.x = self.y = None
         self.out = None
 
     def eager_step(self, x, y):
         m, D, G = self.model, self.model.Discriminator, self.model.Generator
-        ops.repack_stale()                    # all weights changed in the previous step: one batched re-pack
+        ops.repack_stale(self._all_params)    # all weights changed in the previous step: one batched re-pack
         self.opt_D.zero_grad(); D.zero_grad()
         d_losses, d_det = m.d_loss(x, y)
         self.wm.backward(losses=d_losses, shared_parameters=self._shared, task_specific_parameters=self._ts,

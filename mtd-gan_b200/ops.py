@@ -82,7 +82,10 @@ def _packed(weight: torch.Tensor, kind: str, cfg: "ConvCfg") -> torch.Tensor:
     if ent is not None and ent[0] == tag:
         return ent[1]
     w = weight.detach()
-    out = _empty((w.numel() * (2 if kind.endswith("_tf32x3") else 1),), w)
+    n = w.numel() * (2 if kind.endswith("_tf32x3") else 1)
+    # A stale entry is re-packed IN PLACE: a captured CUDA graph holds the buffer's address (its convolutions read it,
+    # its batched re-pack writes it), so the buffer must live exactly as long as the weight does
+    out = ent[1] if (ent is not None and ent[1] is not None and ent[1].numel() == n and ent[1].device == w.device) else _empty((n,), w)
     _pack_into(w, kind, cfg, out)
     slot[key] = (tag, out, weakref.ref(weight), kind, cfg)
     return out
