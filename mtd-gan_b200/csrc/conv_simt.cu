@@ -269,13 +269,13 @@ __global__ void __launch_bounds__(256) conv_c1_kernel(const __grid_constant__ Co
   __syncthreads();
   const int NQ = N4 >> 2;
   const int HoWo = a.Ho * a.Wo;
-  const size_t total = (size_t)a.B * HoWo * NQ;
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  const unsigned total = (unsigned)a.B * HoWo * NQ;            // < 2^32 (checked by the launcher): 32-bit index arithmetic
+  unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned stride = gridDim.x * blockDim.x;
   for (; i < total; i += stride) {
-    const int nq = (int)(i % NQ);
-    const size_t m = i / NQ;
-    const int b = (int)(m / HoWo), r = (int)(m - (size_t)b * HoWo);
+    const int nq = (int)(i % (unsigned)NQ);
+    const unsigned m = i / (unsigned)NQ;
+    const int b = (int)(m / (unsigned)HoWo), r = (int)(m - (unsigned)b * HoWo);
     const int oy = r / a.Wo, ox = r - oy * a.Wo;
     const float* img = a.src1 + (size_t)b * a.H * a.W;
     float v[kMaxTaps];
@@ -534,7 +534,7 @@ int launch_conv(ConvArgs& a, cudaStream_t st) {
   bool vec = (a.C1 % 4 == 0) && (a.C2 % 4 == 0) && mtd_aligned16(a.src1) && mtd_aligned16(a.wp) &&
              (a.C2 == 0 || mtd_aligned16(a.src2));
   a.splits = 1;
-  if (Ctot == 1 && a.T * a.N * sizeof(float) <= 40 * 1024) {                 // single-channel source: streaming kernel
+  if (Ctot == 1 && a.T * a.N * sizeof(float) <= 40 * 1024 && (size_t)M * ((a.N + 3) / 4) < (1ull << 31)) {   // single-channel source
     size_t work = (size_t)M * ((a.N + 3) / 4);
     int blocks = (int)std::min<size_t>((work + 255) / 256, (size_t)mtd_sm_count() * 16);
     auto al = [](const void* p) { return p == nullptr || mtd_aligned16(p); };

@@ -285,8 +285,9 @@ __device__ __forceinline__ void cols_inverse(float2* S, const float2* tw, float2
 template <bool RELU>
 __device__ __forceinline__ void mix_rows(float2* S, const float* Mt, const float* bs, int H) {
   const int tr = threadIdx.x >> 4, to = threadIdx.x & 15;
+  const int rows_per_pass = (blockDim.x >> 4) * 4;         // 64 rows with 256 threads, 128 with 512
   float* Sw = reinterpret_cast<float*>(S);
-  for (int rb = 0; rb < H; rb += 64) {
+  for (int rb = 0; rb < H; rb += rows_per_pass) {
     float acc[4][4];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
@@ -320,9 +321,11 @@ __device__ __forceinline__ void mix_rows(float2* S, const float* Mt, const float
 // ------------------------------------------------------------------------------------------------
 // P2: columns + channel mix.  grid = B*Wh.   smem: S[H][32] float2 | Mt[64][64] | bias[64] | tw[H]
 // ------------------------------------------------------------------------------------------------
-template <int N1, int N2>
-__global__ void __launch_bounds__(kThreadsFft) fft_cols_mix_kernel(const float2* __restrict__ spec_in, float2* __restrict__ spec_out,
-                                                                 const float* __restrict__ w, const float* __restrict__ bias) {
+// THREADS: 256 for H <= 128; 512 for the 256- / 512-point columns, where one CTA owns the SM (128 KB slice) and the
+// transform phases are latency-bound on too few warps otherwise
+template <int N1, int N2, int THREADS>
+__global__ void __launch_bounds__(THREADS) fft_cols_mix_kernel(const float2* __restrict__ spec_in, float2* __restrict__ spec_out,
+                                                             const float* __restrict__ w, const float* __restrict__ bias) {
   mtd_pdl_prologue();
   constexpr int H = N1 * N2;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -596,9 +599,10 @@ int mtd_fft_cols_mix(const float* spec_in, float* spec_out, const float* w, cons
   const size_t smem = (size_t)H * kC * 8 + (size_t)kC2 * kC2 * 4 + kC2 * 4 + (size_t)H * 8;
 #define CALL(N1_, N2_)                                                                                              \
   {                                                                                                                 \
-    int rc = set_smem(fft_cols_mix_kernel<N1_, N2_>, smem);                                                         \
+    constexpr int TH = (N1_ * N2_ >= 256) ? 512 : 256;                                                              \
+    int rc = set_smem(fft_cols_mix_kernel<N1_, N2_, TH>, smem);                                                     \
     if (rc) return rc;                                                                                              \
-    mtd_launch(fft_cols_mix_kernel<N1_, N2_>, B * (W / 2 + 1), kThreadsFft, smem, (cudaStream_t)stream,             \
+    mtd_launch(fft_cols_mix_kernel<N1_, N2_, TH>, B * (W / 2 + 1), TH, smem, (cudaStream_t)stream,                  \
                reinterpret_cast<const float2*>(spec_in), reinterpret_cast<float2*>(spec_out), w, bias);             \
   }
   MTD_FFT_DISPATCH(H, CALL)

@@ -44,20 +44,54 @@ __global__ void __launch_bounds__(256) pcgrad_gram_kernel(const Seg* __restrict_
 #pragma unroll
   for (int i = 0; i < kMaxTasks * (kMaxTasks + 1) / 2; ++i) dacc[i] = 0.0;
   int since = 0;
-  for (long long i = ck.y + threadIdx.x; i < end; i += blockDim.x) {
-    float v[kMaxTasks];
-#pragma unroll
-    for (int t = 0; t < kMaxTasks; ++t) v[t] = (t < T && s.g[t]) ? __ldg(s.g[t] + i) : 0.f;
+  auto accumulate = [&](const float (&v)[kMaxTasks]) {
     int p = 0;
 #pragma unroll
     for (int a = 0; a < kMaxTasks; ++a)
 #pragma unroll
       for (int b = a; b < kMaxTasks; ++b) acc[p] = fmaf(v[a], v[b], acc[p]), ++p;
-    if (++since == 8) {       // flush short fp32 runs into fp64 (task-2 norms are ~1e-5 of task-0's)
-      since = 0;
+  };
+  auto flush = [&]() {       // flush short fp32 runs into fp64 (task-2 norms are ~1e-5 of task-0's)
 #pragma unroll
-      for (int q = 0; q < kMaxTasks * (kMaxTasks + 1) / 2; ++q) dacc[q] += (double)acc[q], acc[q] = 0.f;
+    for (int q = 0; q < kMaxTasks * (kMaxTasks + 1) / 2; ++q) dacc[q] += (double)acc[q], acc[q] = 0.f;
+  };
+  bool vec = true;
+#pragma unroll
+  for (int t = 0; t < kMaxTasks; ++t)
+    if (t < T && s.g[t] && (((uintptr_t)s.g[t]) & 15u)) vec = false;
+  long long i0 = ck.y;
+  if (vec) {      // 16-byte loads: four elements of every task gradient per iteration (chunk starts are multiples of 4)
+    const long long n4 = (end - ck.y) >> 2;
+    for (long long q = threadIdx.x; q < n4; q += blockDim.x) {
+      float4 v4[kMaxTasks];
+#pragma unroll
+      for (int t = 0; t < kMaxTasks; ++t)
+        v4[t] = (t < T && s.g[t]) ? __ldg(reinterpret_cast<const float4*>(s.g[t] + ck.y) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+      float v[kMaxTasks];
+#pragma unroll
+      for (int t = 0; t < kMaxTasks; ++t) v[t] = v4[t].x;
+      accumulate(v);
+#pragma unroll
+      for (int t = 0; t < kMaxTasks; ++t) v[t] = v4[t].y;
+      accumulate(v);
+#pragma unroll
+      for (int t = 0; t < kMaxTasks; ++t) v[t] = v4[t].z;
+      accumulate(v);
+#pragma unroll
+      for (int t = 0; t < kMaxTasks; ++t) v[t] = v4[t].w;
+      accumulate(v);
+      if (++since == 2) { since = 0; flush(); }
     }
+    i0 = ck.y + (n4 << 2);
+    since = 0;
+    flush();
+  }
+  for (long long i = i0 + threadIdx.x; i < end; i += blockDim.x) {
+    float v[kMaxTasks];
+#pragma unroll
+    for (int t = 0; t < kMaxTasks; ++t) v[t] = (t < T && s.g[t]) ? __ldg(s.g[t] + i) : 0.f;
+    accumulate(v);
+    if (++since == 8) { since = 0; flush(); }
   }
 #pragma unroll
   for (int q = 0; q < kMaxTasks * (kMaxTasks + 1) / 2; ++q) dacc[q] += (double)acc[q];
@@ -111,7 +145,26 @@ __global__ void __launch_bounds__(256) pcgrad_combine_kernel(const Seg* __restri
   float c[kMaxTasks];
 #pragma unroll
   for (int t = 0; t < kMaxTasks; ++t) c[t] = (t < T) ? __ldg(coef + t) * scale : 0.f;
-  for (long long i = ck.y + threadIdx.x; i < end; i += blockDim.x) {
+  bool vec = (((uintptr_t)s.out) & 15u) == 0;
+#pragma unroll
+  for (int t = 0; t < kMaxTasks; ++t)
+    if (t < T && s.g[t] && (((uintptr_t)s.g[t]) & 15u)) vec = false;
+  long long i0 = ck.y;
+  if (vec) {
+    const long long n4 = (end - ck.y) >> 2;
+    for (long long q = threadIdx.x; q < n4; q += blockDim.x) {
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int t = 0; t < kMaxTasks; ++t)
+        if (t < T && s.g[t]) {
+          const float4 g = __ldg(reinterpret_cast<const float4*>(s.g[t] + ck.y) + q);
+          v.x = fmaf(c[t], g.x, v.x); v.y = fmaf(c[t], g.y, v.y); v.z = fmaf(c[t], g.z, v.z); v.w = fmaf(c[t], g.w, v.w);
+        }
+      reinterpret_cast<float4*>(s.out + ck.y)[q] = v;
+    }
+    i0 = ck.y + (n4 << 2);
+  }
+  for (long long i = i0 + threadIdx.x; i < end; i += blockDim.x) {
     float v = 0.f;
 #pragma unroll
     for (int t = 0; t < kMaxTasks; ++t)
