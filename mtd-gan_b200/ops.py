@@ -623,9 +623,15 @@ class FFTConvBlockFn(Function):
         spec2 = _empty(spec.shape, x) if need_graph else spec          # in place when nothing is saved
         call("mtd_fft_cols_mix", fptr(spec), fptr(spec2), fptr(fft_w.detach()), fptr(fft_b.detach()), B, H, W, C, st)
         img = _empty(x.shape, x)
-        _conv_forward_launch(x, None, img_w, img_b.detach(), None, img, None, None, None, cfg)
         out = _empty(x.shape, x)
-        call("mtd_fft_rows_inv", fptr(spec2), fptr(x), fptr(img), fptr(out), B, H, W, C, st)
+        if need_graph:
+            _conv_forward_launch(x, None, img_w, img_b.detach(), None, img, None, None, None, cfg)
+            call("mtd_fft_rows_inv", fptr(spec2), fptr(x), fptr(img), fptr(out), B, H, W, C, st)
+        else:
+            # inference: the identity branch rides in the conv epilogue (img = relu(conv(x)) + x), so the inverse row pass
+            # reads ONE residual operand instead of two (33.5 MB less HBM traffic per block at 512 x 512)
+            _conv_forward_launch(x, None, img_w, img_b.detach(), None, img, None, x, None, cfg)
+            call("mtd_fft_rows_inv", fptr(spec2), fptr(img), None, fptr(out), B, H, W, C, st)
         if need_graph:
             ctx.img_w_obj = img_w
             ctx.save_for_backward(x, img_w, fft_w, fft_b, spec, img)
