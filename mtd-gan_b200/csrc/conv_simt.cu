@@ -480,7 +480,6 @@ __global__ void __launch_bounds__(256) thin_wgrad_kernel(const __grid_constant__
     for (int e = 0; e < E; ++e) acc[t][e] = 0.f;
   if (pl < npl) {
     const int j = jl * E;
-#pragma unroll 4          // no stores inside: four pixels' loads (1 vector + T scalars each) are in flight together
     for (long long p = p0 + pl; p < p1; p += npl) {
       float v[E];
       if (VEC4) {
