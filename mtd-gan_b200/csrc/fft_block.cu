@@ -221,7 +221,8 @@ __global__ void __launch_bounds__(kThreadsFft) fft_rows_inv_kernel(const float2*
 // column transforms on a [H][32] complex slice in shared memory; lane = channel.
 // forward: global (natural h) -> S in [k1][k2] order;  inverse: S in [k1][k2] order -> global (natural h)
 // ------------------------------------------------------------------------------------------------
-template <int N1, int N2>
+// RS: row stride of S in float2 (32 = dense; 34 = padded so that the mma fragment loads of the channel mix are conflict-free)
+template <int N1, int N2, int RS = kC>
 __device__ __forceinline__ void cols_forward(const float2* __restrict__ src, float2* S, const float2* tw) {
   constexpr int N = N1 * N2;
   for (int it = threadIdx.x; it < kC * N2; it += blockDim.x) {          // step A: thread (c, n2)
@@ -233,7 +234,7 @@ __device__ __forceinline__ void cols_forward(const float2* __restrict__ src, flo
 #pragma unroll
     for (int i = 0; i < N1; ++i) {
       const int k1 = brev_c(i, N1);
-      S[(k1 * N2 + n2) * kC + c] = k1 == 0 ? v[i] : cmul(v[i], tw[(n2 * k1) & (N - 1)]);
+      S[(k1 * N2 + n2) * RS + c] = k1 == 0 ? v[i] : cmul(v[i], tw[(n2 * k1) & (N - 1)]);
     }
   }
   __syncthreads();
@@ -241,27 +242,27 @@ __device__ __forceinline__ void cols_forward(const float2* __restrict__ src, flo
     const int k1 = it >> 5, c = it & 31;
     float2 v[N2];
 #pragma unroll
-    for (int n2 = 0; n2 < N2; ++n2) v[n2] = S[(k1 * N2 + n2) * kC + c];
+    for (int n2 = 0; n2 < N2; ++n2) v[n2] = S[(k1 * N2 + n2) * RS + c];
     fft_reg<N2, false>(v);
 #pragma unroll
-    for (int j = 0; j < N2; ++j) S[(k1 * N2 + brev_c(j, N2)) * kC + c] = v[j];     // row k1*N2 + k2 holds X[k1 + N1*k2]
+    for (int j = 0; j < N2; ++j) S[(k1 * N2 + brev_c(j, N2)) * RS + c] = v[j];     // row k1*N2 + k2 holds X[k1 + N1*k2]
   }
   __syncthreads();
 }
 
-template <int N1, int N2>
+template <int N1, int N2, int RS = kC>
 __device__ __forceinline__ void cols_inverse(float2* S, const float2* tw, float2* __restrict__ dst, float scale) {
   constexpr int N = N1 * N2;
   for (int it = threadIdx.x; it < kC * N1; it += blockDim.x) {          // step A': thread (c, k1), in place
     const int k1 = it >> 5, c = it & 31;
     float2 v[N2];
 #pragma unroll
-    for (int k2 = 0; k2 < N2; ++k2) v[k2] = S[(k1 * N2 + k2) * kC + c];
+    for (int k2 = 0; k2 < N2; ++k2) v[k2] = S[(k1 * N2 + k2) * RS + c];
     fft_reg<N2, true>(v);
 #pragma unroll
     for (int j = 0; j < N2; ++j) {
       const int n2 = brev_c(j, N2);
-      S[(k1 * N2 + n2) * kC + c] = k1 == 0 ? v[j] : cmulc(v[j], tw[(n2 * k1) & (N - 1)]);
+      S[(k1 * N2 + n2) * RS + c] = k1 == 0 ? v[j] : cmulc(v[j], tw[(n2 * k1) & (N - 1)]);
     }
   }
   __syncthreads();
@@ -269,7 +270,7 @@ __device__ __forceinline__ void cols_inverse(float2* S, const float2* tw, float2
     const int n2 = it >> 5, c = it & 31;
     float2 v[N1];
 #pragma unroll
-    for (int k1 = 0; k1 < N1; ++k1) v[k1] = S[(k1 * N2 + n2) * kC + c];
+    for (int k1 = 0; k1 < N1; ++k1) v[k1] = S[(k1 * N2 + n2) * RS + c];
     fft_reg<N1, true>(v);
 #pragma unroll
     for (int i = 0; i < N1; ++i) {
@@ -318,6 +319,122 @@ __device__ __forceinline__ void mix_rows(float2* S, const float* Mt, const float
   }
 }
 
+// ---- channel mix on the tensor cores (legacy warp-level path: mma.sync m16n8k8 TF32, error-compensated 3xTF32) -----------
+// A row of S is one frequency: 64 floats [Re c0, Im c0, Re c1, Im c1, ...] = the K index kk (input j = pi(kk) =
+// (kk >> 1) + 32 (kk & 1) of the reference's cat[Re, Im] order); the outputs are produced in the same interleaved order.
+// Bhi / Blo: [nn][kk] (row stride kMixLd), B[kk][nn] = w[pi(nn)][pi(kk)] / sqrt(H) split into tf32 hi / lo.
+// Rows are padded to 68 floats so that the A fragments (rows g, g+8; columns t, t+4) and the B fragments hit 32 banks.
+constexpr int kMixLd = 68, kRSmma = kMixLd / 2;
+__device__ __forceinline__ int mix_pi(int kk) { return (kk >> 1) + 32 * (kk & 1); }
+__device__ __forceinline__ uint32_t tf32_rna(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void mix_prepare(const float* __restrict__ w, const float* __restrict__ bias, float scale, float* Bhi,
+                                            float* Blo, float* bsI) {
+  for (int i = threadIdx.x; i < kC2 * kC2; i += blockDim.x) {
+    const int nn = i >> 6, kk = i & 63;
+    const float v = __ldg(w + mix_pi(nn) * kC2 + mix_pi(kk)) * scale;
+    const uint32_t h = tf32_rna(v);
+    Bhi[nn * kMixLd + kk] = __uint_as_float(h);
+    Blo[nn * kMixLd + kk] = __uint_as_float(tf32_rna(v - __uint_as_float(h)));
+  }
+  if (threadIdx.x < kC2) bsI[threadIdx.x] = __ldg(bias + mix_pi(threadIdx.x));
+}
+
+// Bt[kk][nn] = w[pi(nn)][pi(kk)] (transposed, unscaled): the B operand of dy = gz W in the backward kernel
+__device__ __forceinline__ void mix_prepare_t(const float* __restrict__ w, float* Bhi, float* Blo) {
+  for (int i = threadIdx.x; i < kC2 * kC2; i += blockDim.x) {
+    const int kk = i >> 6, nn = i & 63;
+    const float v = __ldg(w + mix_pi(nn) * kC2 + mix_pi(kk));
+    const uint32_t h = tf32_rna(v);
+    Bhi[kk * kMixLd + nn] = __uint_as_float(h);
+    Blo[kk * kMixLd + nn] = __uint_as_float(tf32_rna(v - __uint_as_float(h)));
+  }
+}
+
+// out[r][nn] = relu( bias + sum_kk S[r][kk] B[kk][nn] ), in place on the padded rows of S.  Work item = (16-row block, NT/8
+// of the 8 column tiles); a warp's items are processed in rounds with a block barrier between compute and store when two
+// warps share rows (H = 64), so no warp overwrites a row another warp still reads.
+// MODE 0: Out = relu(bias + A B), Out may alias A (forward mix);  MODE 1: Out[r][n] = 0 where !(bias + A B > 0)
+// (ReLU mask of the recomputed pre-activation applied to the gradient rows);  MODE 2: Out = A B (no bias).
+template <int H, int THREADS, int MODE>
+__device__ __forceinline__ void mix_mma(const float2* A, float2* Out, const float* Bhi, const float* Blo, const float* bsI) {
+  constexpr int NW = THREADS / 32, RB = H / 16;
+  constexpr int NSPLIT = RB >= NW ? 1 : NW / RB;           // column split when there are fewer row blocks than warps
+  constexpr int NT = 8 / NSPLIT;                           // 8-column tiles per item
+  constexpr int ITEMS = RB * NSPLIT, ROUNDS = (ITEMS + NW - 1) / NW;
+  static_assert(NSPLIT == 1 || NSPLIT == 2 || NSPLIT == 4, "column split");
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const float* Sf = reinterpret_cast<const float*>(A);
+  float* Of = reinterpret_cast<float*>(Out);
+#pragma unroll 1
+  for (int round = 0; round < ROUNDS; ++round) {
+    const int item = round * NW + warp;
+    const bool active = item < ITEMS;
+    const int rb = active ? item / NSPLIT : 0, n0 = (item % NSPLIT) * NT;
+    float acc[NT][4], acc2[NT][4];
+#pragma unroll
+    for (int n = 0; n < NT; ++n) {
+      const float b0 = MODE == 2 ? 0.f : bsI[(n0 + n) * 8 + 2 * t], b1 = MODE == 2 ? 0.f : bsI[(n0 + n) * 8 + 2 * t + 1];
+      acc[n][0] = b0; acc[n][1] = b1; acc[n][2] = b0; acc[n][3] = b1;
+      acc2[n][0] = acc2[n][1] = acc2[n][2] = acc2[n][3] = 0.f;
+    }
+    const float* r0 = Sf + (size_t)(rb * 16 + g) * kMixLd;
+    const float* r1 = r0 + 8 * kMixLd;
+    if (active) {
+#pragma unroll 2
+      for (int k0 = 0; k0 < kC2; k0 += 8) {
+        const float av[4] = {r0[k0 + t], r1[k0 + t], r0[k0 + t + 4], r1[k0 + t + 4]};
+        uint32_t ah[4], al[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          ah[i] = tf32_rna(av[i]);
+          al[i] = tf32_rna(av[i] - __uint_as_float(ah[i]));
+        }
+#pragma unroll
+        for (int n = 0; n < NT; ++n) {
+          const float* bh = Bhi + ((n0 + n) * 8 + g) * kMixLd + k0 + t;
+          const float* bl = Blo + ((n0 + n) * 8 + g) * kMixLd + k0 + t;
+          const uint32_t bh0 = __float_as_uint(bh[0]), bh1 = __float_as_uint(bh[4]);
+          const uint32_t bl0 = __float_as_uint(bl[0]), bl1 = __float_as_uint(bl[4]);
+          mma_tf32(acc2[n], al, bh0, bh1);
+          mma_tf32(acc2[n], ah, bl0, bl1);
+          mma_tf32(acc[n], ah, bh0, bh1);
+        }
+      }
+    }
+    if (MODE == 0) { if (NSPLIT > 1) __syncthreads(); else __syncwarp(); }      // in place: all reads of these rows are done
+    if (active) {
+      float* w0 = Of + (size_t)(rb * 16 + g) * kMixLd;
+      float* w1 = w0 + 8 * kMixLd;
+#pragma unroll
+      for (int n = 0; n < NT; ++n) {
+        const int col = (n0 + n) * 8 + 2 * t;
+        const float v0 = acc[n][0] + acc2[n][0], v1 = acc[n][1] + acc2[n][1], v2 = acc[n][2] + acc2[n][2], v3 = acc[n][3] + acc2[n][3];
+        if (MODE == 0) {
+          *reinterpret_cast<float2*>(w0 + col) = make_float2(fmaxf(v0, 0.f), fmaxf(v1, 0.f));
+          *reinterpret_cast<float2*>(w1 + col) = make_float2(fmaxf(v2, 0.f), fmaxf(v3, 0.f));
+        } else if (MODE == 1) {
+          if (!(v0 > 0.f)) w0[col] = 0.f;
+          if (!(v1 > 0.f)) w0[col + 1] = 0.f;
+          if (!(v2 > 0.f)) w1[col] = 0.f;
+          if (!(v3 > 0.f)) w1[col + 1] = 0.f;
+        } else {
+          *reinterpret_cast<float2*>(w0 + col) = make_float2(v0, v1);
+          *reinterpret_cast<float2*>(w1 + col) = make_float2(v2, v3);
+        }
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // P2: columns + channel mix.  grid = B*Wh.   smem: S[H][32] float2 | Mt[64][64] | bias[64] | tw[H]
 // ------------------------------------------------------------------------------------------------
@@ -329,23 +446,20 @@ __global__ void __launch_bounds__(THREADS) fft_cols_mix_kernel(const float2* __r
   mtd_pdl_prologue();
   constexpr int H = N1 * N2;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  float2* S = reinterpret_cast<float2*>(smem_raw);
-  float* Mt = reinterpret_cast<float*>(S + (size_t)H * kC);          // Mt[j][o] = w[o][j] / sqrt(H)
-  float* bs = Mt + kC2 * kC2;
+  float2* S = reinterpret_cast<float2*>(smem_raw);                   // [H][kRSmma] (rows padded to 68 floats)
+  float* Bhi = reinterpret_cast<float*>(S + (size_t)H * kRSmma);     // [64][68] tf32 hi of w[pi(nn)][pi(kk)] / sqrt(H)
+  float* Blo = Bhi + kC2 * kMixLd;
+  float* bs = Blo + kC2 * kMixLd;                                    // bias in interleaved output order
   float2* tw = reinterpret_cast<float2*>(bs + kC2);
   const size_t slice = (size_t)blockIdx.x * H * kC;
   const float sH = rsqrtf((float)H);
   fill_twiddles(tw, H);
-  for (int i = threadIdx.x; i < kC2 * kC2; i += blockDim.x) {
-    const int o = i >> 6, j = i & 63;
-    Mt[j * kC2 + o] = __ldg(w + i) * sH;
-  }
-  if (threadIdx.x < kC2) bs[threadIdx.x] = __ldg(bias + threadIdx.x);
+  mix_prepare(w, bias, sH, Bhi, Blo, bs);
   __syncthreads();
-  cols_forward<N1, N2>(spec_in + slice, S, tw);
-  mix_rows<true>(S, Mt, bs, H);
+  cols_forward<N1, N2, kRSmma>(spec_in + slice, S, tw);
+  mix_mma<H, THREADS, 0>(S, S, Bhi, Blo, bs);
   __syncthreads();
-  cols_inverse<N1, N2>(S, tw, spec_out + slice, sH);
+  cols_inverse<N1, N2, kRSmma>(S, tw, spec_out + slice, sH);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -357,67 +471,37 @@ template <int N1, int N2>
 __global__ void __launch_bounds__(kThreadsFft) fft_cols_mix_bwd_kernel(const float2* __restrict__ spec_x, const float2* __restrict__ spec_g,
                                                                      float2* __restrict__ spec_out, const float* __restrict__ w,
                                                                      const float* __restrict__ bias, float* __restrict__ part,
-                                                                     int Wh, int W) {
+                                                                     const float* __restrict__ bw, int Wh, int W) {
   mtd_pdl_prologue();
   constexpr int H = N1 * N2;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  float2* S = reinterpret_cast<float2*>(smem_raw);
-  float2* T = S + (size_t)H * kC;
-  float* Mt = reinterpret_cast<float*>(T + (size_t)H * kC);          // Mt[j][o] = w[o][j]/sqrt(H)
-  float* Mn = Mt + kC2 * kC2;                                        // Mn[o][j] = w[o][j]
-  float* bs = Mn + kC2 * kC2;
+  float2* S = reinterpret_cast<float2*>(smem_raw);                   // [H][kRSmma]
+  float2* T = S + (size_t)H * kRSmma;
+  float* bs = reinterpret_cast<float*>(T + (size_t)H * kRSmma);
   float2* tw = reinterpret_cast<float2*>(bs + kC2);
+  // tf32 hi / lo mix operands, prepared once per call by fft_mix_prepare_kernel (L1 / L2 resident, shared by all CTAs):
+  // forward operand (scaled by 1/sqrt(H)) and the transposed, unscaled one for dy = gz W
+  const float* Bhi = bw;
+  const float* Blo = Bhi + kC2 * kMixLd;
+  const float* Thi = Blo + kC2 * kMixLd;
+  const float* Tlo = Thi + kC2 * kMixLd;
   const size_t slice = (size_t)blockIdx.x * H * kC;
   const int kw = blockIdx.x % Wh;
   const float wk = (kw == 0 || kw == (W >> 1)) ? 1.f : 2.f;
   const float sH = rsqrtf((float)H);
   fill_twiddles(tw, H);
-  for (int i = threadIdx.x; i < kC2 * kC2; i += blockDim.x) {
-    const int o = i >> 6, j = i & 63;
-    const float v = __ldg(w + i);
-    Mt[j * kC2 + o] = v * sH;
-    Mn[i] = v;
-  }
-  if (threadIdx.x < kC2) bs[threadIdx.x] = __ldg(bias + threadIdx.x);
+  if (threadIdx.x < kC2) bs[threadIdx.x] = __ldg(bias + mix_pi(threadIdx.x));
   __syncthreads();
-  cols_forward<N1, N2>(spec_x + slice, S, tw);        // S = FFT_H(X1) (unscaled), rows in [k1][k2] order
-  cols_forward<N1, N2>(spec_g + slice, T, tw);        // T = FFT_H(G)  -- same row order, so masks / products line up
+  cols_forward<N1, N2, kRSmma>(spec_x + slice, S, tw);        // S = FFT_H(X1) (unscaled), rows in [k1][k2] order
+  cols_forward<N1, N2, kRSmma>(spec_g + slice, T, tw);        // T = FFT_H(G)  -- same row order, so masks / products line up
 
-  const int tr = threadIdx.x >> 4, to = threadIdx.x & 15;
-  float* Tw = reinterpret_cast<float*>(T);
-  const float* Sf = reinterpret_cast<const float*>(S);
-  // 1) ReLU mask from the recomputed pre-activation; gz = mask * G2 (left unscaled) written in place
-  for (int rb = 0; rb < H; rb += 64) {
-    float acc[4][4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) acc[i][j] = bs[to * 4 + j];
-    const int r0 = rb + tr * 4;
-#pragma unroll 4
-    for (int c = 0; c < kC; ++c) {
-      const float4 mre = *reinterpret_cast<const float4*>(Mt + c * kC2 + to * 4);
-      const float4 mim = *reinterpret_cast<const float4*>(Mt + (c + kC) * kC2 + to * 4);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float2 y = S[(r0 + i) * kC + c];
-        acc[i][0] = fmaf(y.x, mre.x, fmaf(y.y, mim.x, acc[i][0]));
-        acc[i][1] = fmaf(y.x, mre.y, fmaf(y.y, mim.y, acc[i][1]));
-        acc[i][2] = fmaf(y.x, mre.z, fmaf(y.y, mim.z, acc[i][2]));
-        acc[i][3] = fmaf(y.x, mre.w, fmaf(y.y, mim.w, acc[i][3]));
-      }
-    }
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int o = to * 4 + j;
-        const int a = ((r0 + i) * kC + (o & 31)) * 2 + (o >> 5);
-        if (!(acc[i][j] > 0.f)) Tw[a] = 0.f;
-      }
-  }
+  // 1) ReLU mask from the recomputed pre-activation; gz = mask * G2 (left unscaled) written in place (tensor cores)
+  mix_mma<H, kThreadsFft, 1>(S, T, Bhi, Blo, bs);
   __syncthreads();
   // 2) dW / db partials: dW[o][j] = wk/H * sum_r gz[r][o] * y[r][j]; db[o] = wk/sqrt(H) * sum_r gz[r][o]
+  const int tr = threadIdx.x >> 4, to = threadIdx.x & 15;
+  const float* Tw = reinterpret_cast<const float*>(T);
+  const float* Sf = reinterpret_cast<const float*>(S);
   {
     const int o0 = tr * 4, j0 = to * 4;
     float acc[4][4];
@@ -431,12 +515,12 @@ __global__ void __launch_bounds__(kThreadsFft) fft_cols_mix_bwd_kernel(const flo
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int o = o0 + i;
-        g[i] = Tw[(r * kC + (o & 31)) * 2 + (o >> 5)];
+        g[i] = Tw[(r * kRSmma + (o & 31)) * 2 + (o >> 5)];
       }
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int jj = j0 + j;
-        y[j] = Sf[(r * kC + (jj & 31)) * 2 + (jj >> 5)];
+        y[j] = Sf[(r * kRSmma + (jj & 31)) * 2 + (jj >> 5)];
       }
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
@@ -458,38 +542,25 @@ __global__ void __launch_bounds__(kThreadsFft) fft_cols_mix_bwd_kernel(const flo
     }
   }
   __syncthreads();
-  // 3) dy[r][j] = sum_o gz[r][o] * w[o][j]   (unscaled; 1/H applied at the store)  -> S
-  float* Sw = reinterpret_cast<float*>(S);
-  for (int rb = 0; rb < H; rb += 64) {
-    float acc[4][4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-    const int r0 = rb + tr * 4;
-#pragma unroll 4
-    for (int o = 0; o < kC; ++o) {
-      const float4 mre = *reinterpret_cast<const float4*>(Mn + o * kC2 + to * 4);
-      const float4 mim = *reinterpret_cast<const float4*>(Mn + (o + kC) * kC2 + to * 4);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float2 g = T[(r0 + i) * kC + o];     // (gz[o], gz[o+32])
-        acc[i][0] = fmaf(g.x, mre.x, fmaf(g.y, mim.x, acc[i][0]));
-        acc[i][1] = fmaf(g.x, mre.y, fmaf(g.y, mim.y, acc[i][1]));
-        acc[i][2] = fmaf(g.x, mre.z, fmaf(g.y, mim.z, acc[i][2]));
-        acc[i][3] = fmaf(g.x, mre.w, fmaf(g.y, mim.w, acc[i][3]));
-      }
-    }
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int jj = to * 4 + j;
-        Sw[((r0 + i) * kC + (jj & 31)) * 2 + (jj >> 5)] = acc[i][j];
-      }
-  }
+  // 3) dy[r][j] = sum_o gz[r][o] * w[o][j]   (unscaled; 1/H applied at the store)  -> S (tensor cores)
+  mix_mma<H, kThreadsFft, 2>(T, S, Thi, Tlo, nullptr);
   __syncthreads();
-  cols_inverse<N1, N2>(S, tw, spec_out + slice, sH * sH);
+  cols_inverse<N1, N2, kRSmma>(S, tw, spec_out + slice, sH * sH);
+}
+
+// one block: the four tf32 operand matrices of the backward kernel's tensor-core phases -> bw[4][64][kMixLd]
+__global__ void __launch_bounds__(256) fft_mix_prepare_kernel(const float* __restrict__ w, float scale, float* __restrict__ bw) {
+  mtd_pdl_prologue();
+  float* Bhi = bw;
+  float* Blo = Bhi + kC2 * kMixLd;
+  for (int i = threadIdx.x; i < kC2 * kC2; i += blockDim.x) {
+    const int nn = i >> 6, kk = i & 63;
+    const float v = __ldg(w + mix_pi(nn) * kC2 + mix_pi(kk)) * scale;
+    const uint32_t h = tf32_rna(v);
+    Bhi[nn * kMixLd + kk] = __uint_as_float(h);
+    Blo[nn * kMixLd + kk] = __uint_as_float(tf32_rna(v - __uint_as_float(h)));
+  }
+  mix_prepare_t(w, Blo + kC2 * kMixLd, Blo + 2 * kC2 * kMixLd);
 }
 
 // dW / db = ordered sum of the per-CTA partials.  32 output elements per block, 8 lanes of partial index per element:
@@ -550,7 +621,8 @@ extern "C" {
 
 long long mtd_fft_spec_elems(int B, int H, int W, int C) { return (long long)B * (W / 2 + 1) * H * C * 2; }
 
-long long mtd_fft_bwd_part_elems(int B, int W) { return (long long)B * (W / 2 + 1) * (kC2 * kC2 + kC2); }
+// per-CTA dW / db partials followed by the four tf32 mix operands of the backward kernel
+long long mtd_fft_bwd_part_elems(int B, int W) { return (long long)B * (W / 2 + 1) * (kC2 * kC2 + kC2) + 4LL * kC2 * kMixLd; }
 
 /* 1 when (H, W, C) is a geometry the frequency branch supports: C == 32, H and W in {64, 128, 256, 512}. */
 int mtd_fft_supported(int H, int W, int C) { return (C == kC && fft_len_ok(H) && fft_len_ok(W)) ? 1 : 0; }
@@ -596,7 +668,7 @@ int mtd_fft_cols_mix(const float* spec_in, float* spec_out, const float* w, cons
                      int C, void* stream) {
   MTD_REQUIRE(spec_in && spec_out && w && bias && B > 0 && fft_len_ok(H) && W >= 2 && C == kC);
   MTD_REQUIRE(mtd_aligned16(spec_in) && mtd_aligned16(spec_out));
-  const size_t smem = (size_t)H * kC * 8 + (size_t)kC2 * kC2 * 4 + kC2 * 4 + (size_t)H * 8;
+  const size_t smem = (size_t)H * kRSmma * 8 + (size_t)2 * kC2 * kMixLd * 4 + kC2 * 4 + (size_t)H * 8;
 #define CALL(N1_, N2_)                                                                                              \
   {                                                                                                                 \
     constexpr int TH = (N1_ * N2_ >= 256) ? 512 : 256;                                                              \
@@ -615,15 +687,18 @@ int mtd_fft_cols_mix_bwd(const float* spec_x, const float* spec_g, float* spec_o
                          float* part, float* dw, float* db, int B, int H, int W, int C, void* stream) {
   MTD_REQUIRE(spec_x && spec_g && spec_out && w && bias && part && dw && db);
   MTD_REQUIRE(B > 0 && fft_len_ok(H) && H <= 256 && W >= 2 && C == kC);
-  const size_t smem = (size_t)H * kC * 16 + (size_t)kC2 * kC2 * 8 + kC2 * 4 + (size_t)H * 8;
+  const size_t smem = (size_t)H * kRSmma * 16 + kC2 * 4 + (size_t)H * 8;
   const int Wh = W / 2 + 1, nparts = B * Wh;
   cudaStream_t st = (cudaStream_t)stream;
+  float* bw = part + (size_t)nparts * (kC2 * kC2 + kC2);
+  mtd_launch(fft_mix_prepare_kernel, 1, 256, 0, st, w, 1.0f / sqrtf((float)H), bw);
+  MTD_CHECK_LAUNCH();
 #define CALL(N1_, N2_)                                                                                              \
   {                                                                                                                 \
     int rc = set_smem(fft_cols_mix_bwd_kernel<N1_, N2_>, smem);                                                     \
     if (rc) return rc;                                                                                              \
     mtd_launch(fft_cols_mix_bwd_kernel<N1_, N2_>, nparts, kThreadsFft, smem, st, reinterpret_cast<const float2*>(spec_x), \
-               reinterpret_cast<const float2*>(spec_g), reinterpret_cast<float2*>(spec_out), w, bias, part, Wh, W);  \
+               reinterpret_cast<const float2*>(spec_g), reinterpret_cast<float2*>(spec_out), w, bias, part, bw, Wh, W); \
   }
   MTD_FFT_DISPATCH(H, CALL)
 #undef CALL
