@@ -499,46 +499,54 @@ __global__ void __launch_bounds__(kThreadsFft) fft_cols_mix_bwd_kernel(const flo
   mix_mma<H, kThreadsFft, 1>(S, T, Bhi, Blo, bs);
   __syncthreads();
   // 2) dW / db partials: dW[o][j] = wk/H * sum_r gz[r][o] * y[r][j]; db[o] = wk/sqrt(H) * sum_r gz[r][o]
-  const int tr = threadIdx.x >> 4, to = threadIdx.x & 15;
-  const float* Tw = reinterpret_cast<const float*>(T);
-  const float* Sf = reinterpret_cast<const float*>(S);
+  //    on the tensor cores: D[nn][kk] = sum_r T[r][nn] S[r][kk] in the interleaved index space (both operands are data:
+  //    both are split into tf32 hi / lo); warp w owns output rows 16 (w >> 1) .. +15 and columns 32 (w & 1) .. +31
   {
-    const int o0 = tr * 4, j0 = to * 4;
-    float acc[4][4];
-    float accb[4] = {0.f, 0.f, 0.f, 0.f};
+    const float* Tf = reinterpret_cast<const float*>(T);
+    const float* Sf = reinterpret_cast<const float*>(S);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    const int m0 = (warp >> 1) * 16, nb = (warp & 1) * 32;
+    float acc[4][4], acc2[4][4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int n = 0; n < 4; ++n)
 #pragma unroll
-      for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-    for (int r = 0; r < H; ++r) {
-      float g[4], y[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int o = o0 + i;
-        g[i] = Tw[(r * kRSmma + (o & 31)) * 2 + (o >> 5)];
-      }
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int jj = j0 + j;
-        y[j] = Sf[(r * kRSmma + (jj & 31)) * 2 + (jj >> 5)];
-      }
+      for (int e = 0; e < 4; ++e) acc[n][e] = acc2[n][e] = 0.f;
+#pragma unroll 2
+    for (int k0 = 0; k0 < H; k0 += 8) {
+      const float* ta = Tf + (size_t)(k0 + t) * kMixLd + m0 + g;
+      const float av[4] = {ta[0], ta[8], ta[4 * kMixLd], ta[4 * kMixLd + 8]};      // (m, k) = (g, t), (g+8, t), (g, t+4), (g+8, t+4)
+      uint32_t ah[4], al[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        accb[i] += g[i];
+        ah[i] = tf32_rna(av[i]);
+        al[i] = tf32_rna(av[i] - __uint_as_float(ah[i]));
+      }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(g[i], y[j], acc[i][j]);
+      for (int n = 0; n < 4; ++n) {
+        const float* sb = Sf + (size_t)(k0 + t) * kMixLd + nb + n * 8 + g;         // (k, n) = (t, g), (t+4, g)
+        const float b0 = sb[0], b1 = sb[4 * kMixLd];
+        const uint32_t bh0 = tf32_rna(b0), bh1 = tf32_rna(b1);
+        const uint32_t bl0 = tf32_rna(b0 - __uint_as_float(bh0)), bl1 = tf32_rna(b1 - __uint_as_float(bh1));
+        mma_tf32(acc2[n], al, bh0, bh1);
+        mma_tf32(acc2[n], ah, bl0, bl1);
+        mma_tf32(acc[n], ah, bh0, bh1);
       }
     }
     float* p = part + (size_t)blockIdx.x * (kC2 * kC2 + kC2);
     const float sW = wk * sH * sH;
+    const int o0 = mix_pi(m0 + g), o1 = mix_pi(m0 + g + 8);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float4 v = make_float4(acc[i][0] * sW, acc[i][1] * sW, acc[i][2] * sW, acc[i][3] * sW);
-      *reinterpret_cast<float4*>(p + (o0 + i) * kC2 + j0) = v;
+    for (int n = 0; n < 4; ++n) {
+      const int j0 = mix_pi(nb + n * 8 + 2 * t), j1 = mix_pi(nb + n * 8 + 2 * t + 1);
+      p[o0 * kC2 + j0] = (acc[n][0] + acc2[n][0]) * sW;
+      p[o0 * kC2 + j1] = (acc[n][1] + acc2[n][1]) * sW;
+      p[o1 * kC2 + j0] = (acc[n][2] + acc2[n][2]) * sW;
+      p[o1 * kC2 + j1] = (acc[n][3] + acc2[n][3]) * sW;
     }
-    if (to == 0) {
-#pragma unroll
-      for (int i = 0; i < 4; ++i) p[kC2 * kC2 + o0 + i] = accb[i] * wk * sH;
+    if (threadIdx.x < kC2) {                                     // db: column sums of gz
+      float sum = 0.f;
+      for (int r = 0; r < H; ++r) sum += Tf[(size_t)r * kMixLd + threadIdx.x];
+      p[kC2 * kC2 + mix_pi(threadIdx.x)] = sum * wk * sH;
     }
   }
   __syncthreads();
