@@ -527,6 +527,60 @@ __global__ void conv_epilogue_kernel(const __grid_constant__ ConvArgs a, size_t 
   }
 }
 
+// conv_c1 with 16 output channels per thread (N % 16 == 0, vector epilogue): the nine source loads and their bounds
+// arithmetic are shared by four float4 groups instead of being repeated by each of them.
+__global__ void __launch_bounds__(256) conv_c1x16_kernel(const __grid_constant__ ConvArgs a) {
+  mtd_pdl_prologue();
+  extern __shared__ __align__(16) float wsm[];   // [T][N]
+  for (int i = threadIdx.x; i < a.T * a.N; i += blockDim.x) {
+    int t = i / a.N, n = i - t * a.N;
+    wsm[i] = __ldg(a.wp + (size_t)n * a.T + t);
+  }
+  __syncthreads();
+  const int NG = a.N >> 4;
+  const int HoWo = a.Ho * a.Wo;
+  const unsigned total = (unsigned)a.B * HoWo * NG;
+  unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned stride = gridDim.x * blockDim.x;
+  for (; i < total; i += stride) {
+    const int ng = (int)(i % (unsigned)NG);
+    const unsigned m = i / (unsigned)NG;
+    const int b = (int)(m / (unsigned)HoWo), r = (int)(m - (unsigned)b * HoWo);
+    const int oy = r / a.Wo, ox = r - oy * a.Wo;
+    const float* img = a.src1 + (size_t)b * a.H * a.W;
+    float v[kMaxTaps];
+#pragma unroll
+    for (int t = 0; t < kMaxTaps; ++t) {
+      v[t] = 0.f;
+      if (t < a.T) {
+        const int iy = oy * a.sy + a.dy[t], ix = ox * a.sx + a.dx[t];
+        if (iy >= 0 && iy < a.H && ix >= 0 && ix < a.W) v[t] = __ldg(img + (size_t)iy * a.W + ix);
+      }
+    }
+    float4 acc[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int t = 0; t < kMaxTaps; ++t) {
+      if (t < a.T) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float4 w = *reinterpret_cast<const float4*>(wsm + t * a.N + ng * 16 + q * 4);
+          acc[q].x = fmaf(v[t], w.x, acc[q].x); acc[q].y = fmaf(v[t], w.y, acc[q].y);
+          acc[q].z = fmaf(v[t], w.z, acc[q].z); acc[q].w = fmaf(v[t], w.w, acc[q].w);
+        }
+      }
+    }
+    const size_t pix = ((size_t)b * a.outH + (oy * a.omy + a.ooy)) * a.outW + (ox * a.omx + a.oox);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int n = ng * 16 + q * 4;
+      const size_t idx = pix * a.N + n;
+      *reinterpret_cast<float4*>(a.out + idx) = conv_epilogue_four(a, acc[q], idx, n);
+    }
+  }
+}
+
 int launch_conv(ConvArgs& a, cudaStream_t st) {
   const int Ctot = a.C1 + a.C2;
   const int M = a.B * a.Ho * a.Wo;
@@ -540,7 +594,13 @@ int launch_conv(ConvArgs& a, cudaStream_t st) {
     auto al = [](const void* p) { return p == nullptr || mtd_aligned16(p); };
     const int vec4 = (a.N % 4 == 0 && mtd_aligned16(a.out) && al(a.bias) && al(a.add1) && al(a.add2) && al(a.mask_src) && al(a.aux) &&
                       (a.scale_span == 0 || a.scale_span % 4 == 0)) ? 1 : 0;
-    mtd_launch(conv_c1_kernel, blocks, 256, a.T * ((a.N + 3) & ~3) * sizeof(float), st, a, vec4);
+    if (vec4 && a.N % 16 == 0 && (size_t)M * (a.N / 16) >= (size_t)mtd_sm_count() * 256 * 4) {
+      work = (size_t)M * (a.N / 16);
+      blocks = (int)std::min<size_t>((work + 255) / 256, (size_t)mtd_sm_count() * 16);
+      mtd_launch(conv_c1x16_kernel, blocks, 256, a.T * a.N * sizeof(float), st, a);
+    } else {
+      mtd_launch(conv_c1_kernel, blocks, 256, a.T * ((a.N + 3) & ~3) * sizeof(float), st, a, vec4);
+    }
     MTD_CHECK_LAUNCH();
     return MTD_OK;
   }

@@ -46,6 +46,8 @@ CONV_CASES = [
     (3, 64, 64, 64, 64, 1, 3, 1, 1, 0, 2, 0, False),     # s_dconv61 on cat[up, skip]: halo-tile N = 1 kernel, two sources
     (1, 64, 64, 32, 0, 1, 3, 1, 1, 1, 0, 1, True),       # generator decoder[0] (ConvTranspose 32 -> 1, skip add): N = 1 tile kernel
     (2, 64, 64, 1, 0, 64, 3, 1, 1, 0, 2, 0, False),      # conv11 1 -> 64: vectorised Cin = 1 kernel; its dgrad is the N = 1 tile kernel
+    (4, 128, 128, 1, 0, 64, 3, 1, 1, 0, 2, 0, False),    # large enough for the 16-channels-per-thread Cin = 1 kernel
+    (8, 128, 128, 1, 0, 32, 3, 1, 1, 0, 1, 0, False),    # the same kernel, generator conv_first shape
 ]
 
 
