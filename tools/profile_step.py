@@ -45,15 +45,11 @@ def main():
     shared, ts, last = list(D.shared_parameters()), list(D.task_specific_parameters()), list(D.last_shared_parameters())
     x, y = (t.to(dev) for t in synthetic_pair(args.batch, 64, seed=1234))
 
-    def step():
-        opt_D.zero_grad(); D.zero_grad()
-        d_losses, _ = model.d_loss(x, y)
-        wm.backward(losses=d_losses, shared_parameters=shared, task_specific_parameters=ts, last_shared_parameters=last)
-        opt_D.step()
-        opt_G.zero_grad(); G.zero_grad()
-        g_loss, _ = model.g_loss(x, y)
-        g_loss.backward()
-        opt_G.step()
+    from mtdgan_b200.graphs import GraphedTrainStep
+    graphed = GraphedTrainStep(model, opt_D, opt_G, wm)
+
+    def step():                               # exactly the kernel sequence bench.py captures into its CUDA graph
+        graphed.eager_step(x, y)
 
     for _ in range(args.warm):
         step()
