@@ -246,22 +246,47 @@ __device__ __forceinline__ void sk_reduce_rows(const TcArgs& a, int BN, int K, i
   const int mh = m % a.n_ht, mb = m / a.n_ht;
   int ncols, nloc;
   float* outp = tc_out_of(a, nt * BN, ncols, nloc);
-  for (int i = r_begin * c4n + tid; i < r_end * c4n; i += nthr) {
-    const int c = (i % c4n) * 4;
-    const int r = i / c4n;
-    const int bl = r / (a.TH * a.TW), rem = r - bl * (a.TH * a.TW);
-    const int hl = rem / a.TW, wl = rem - hl * a.TW;
-    const int b = mb * a.TB + bl;
-    if (b >= a.B) continue;
-    const float* wsp = a.ws + ((size_t)st * a.sk_P * kBM + r) * BN + c;
-    float4 sum = __ldcg(reinterpret_cast<const float4*>(wsp));
-    for (int p = 1; p <= last - first; ++p) {
-      const float4 t = __ldcg(reinterpret_cast<const float4*>(wsp + (size_t)p * kBM * BN));
-      sum.x += t.x; sum.y += t.y; sum.z += t.z; sum.w += t.w;
+  // U items x 4 pieces of loads in flight per thread: the pass is a chain of L2 latencies otherwise
+  constexpr int U = 4;
+  const int P = last - first + 1, i_end = r_end * c4n;
+  const size_t pstride = (size_t)kBM * BN;
+  for (int i0 = r_begin * c4n + tid; i0 < i_end; i0 += nthr * U) {
+    const float* wsp[U];
+    float4 sum[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int i = min(i0 + u * nthr, i_end - 1);          // clamped lanes load a valid address and are not stored
+      wsp[u] = a.ws + ((size_t)st * a.sk_P * kBM + i / c4n) * BN + (i % c4n) * 4;
     }
-    const size_t rowoff = (((size_t)b * a.outH + ((mh * a.TH + hl) * a.omy + ooy)) * a.outW +
-                           ((mw * a.TW + wl) * a.omx + oox)) * ncols + nloc;
-    tc_store4(a, outp, rowoff + c, nt * BN + c, tc_row_scale(a, b), sum.x, sum.y, sum.z, sum.w);
+#pragma unroll
+    for (int u = 0; u < U; ++u) sum[u] = __ldcg(reinterpret_cast<const float4*>(wsp[u]));
+    for (int p = 1; p < P; p += 4) {
+      float4 t[4][U];
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+          t[q][u] = __ldcg(reinterpret_cast<const float4*>(wsp[u] + (size_t)min(p + q, P - 1) * pstride));
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (p + q < P) {                                     // pieces added strictly in order
+#pragma unroll
+          for (int u = 0; u < U; ++u) { sum[u].x += t[q][u].x; sum[u].y += t[q][u].y; sum[u].z += t[q][u].z; sum[u].w += t[q][u].w; }
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int i = i0 + u * nthr;
+      if (i >= i_end) continue;
+      const int c = (i % c4n) * 4, r = i / c4n;
+      const int bl = r / (a.TH * a.TW), rem = r - bl * (a.TH * a.TW);
+      const int hl = rem / a.TW, wl = rem - hl * a.TW;
+      const int b = mb * a.TB + bl;
+      if (b >= a.B) continue;
+      const size_t rowoff = (((size_t)b * a.outH + ((mh * a.TH + hl) * a.omy + ooy)) * a.outW +
+                             ((mw * a.TW + wl) * a.omx + oox)) * ncols + nloc;
+      tc_store4(a, outp, rowoff + c, nt * BN + c, tc_row_scale(a, b), sum[u].x, sum[u].y, sum[u].z, sum[u].w);
+    }
   }
 }
 
@@ -445,7 +470,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
     const int hl = rem / a.TW, wl = rem - hl * a.TW;
     WorkIter wi(a, kiters);
     Work wk;
-    int pend[2], npend = 0;                        // stream-K tiles this CTA holds a piece of (sk_per < K: at most two)
+    int pend0 = -1, pend1 = -1;                    // stream-K tiles this CTA holds a piece of (sk_per < K: at most two)
     for (int lt = 0; wi.next(a, kiters, wk); ++lt) {
       int b0, h0, w0, n0, cls;
       decode_tile(wk.tile, b0, h0, w0, n0, cls);
@@ -488,7 +513,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
         asm volatile("bar.sync 1, 128;" ::: "memory");
         const int st = wk.tile - a.n_dp;
         if (r == 0) atomicAdd(a.sk_cnt + st, 1u);
-        if (npend < 2) pend[npend++] = st;
+        if (pend0 < 0) pend0 = st; else pend1 = st;
       }
     }
     if (a.sk_cnt != nullptr) {
@@ -496,8 +521,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
       // once every piece of a tile has arrived, each of its P piece owners reduces 128 / P rows of it, pieces in order.
       // All CTAs of the launch are co-resident (grid <= #SM, one CTA per SM), which makes the wait safe; it is bounded
       // (trap) like every other wait of this kernel.
-      for (int k = 0; k < npend; ++k) {
-        const int st = pend[k];
+      for (int k = 0; k < 2; ++k) {
+        const int st = k == 0 ? pend0 : pend1;
+        if (st < 0) break;
         const int first = (st * kiters) / a.sk_per, last = ((st + 1) * kiters - 1) / a.sk_per;
         const unsigned P = (unsigned)(last - first + 1);
         const int pi = (int)blockIdx.x - first;
@@ -507,8 +533,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
             unsigned seen;
             asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(a.sk_cnt + st) : "memory");
             if (seen >= P) break;
-            __nanosleep(40);
-            if (++spins > (1 << 21)) __trap();
+            if (++spins > 64) __nanosleep(32);
+            if (spins > (1 << 21)) __trap();
           }
         }
         __syncwarp();

@@ -280,45 +280,6 @@ __device__ __forceinline__ void cols_inverse(float2* S, const float2* tw, float2
   }
 }
 
-// out[r][o] = act( bias[o] + sum_j M[o][j] in[r][j] ) on the 64-wide rows of S (row = one frequency: 32 complex channels =
-// [Re 0..31 | Im 0..31] as input index j, same split for the output index o); 4 x 4 register tiles, in place.
-// Mt[j][o] (transposed, pre-scaled).  RELU: apply max(., 0); else raw.
-template <bool RELU>
-__device__ __forceinline__ void mix_rows(float2* S, const float* Mt, const float* bs, int H) {
-  const int tr = threadIdx.x >> 4, to = threadIdx.x & 15;
-  const int rows_per_pass = (blockDim.x >> 4) * 4;         // 64 rows with 256 threads, 128 with 512
-  float* Sw = reinterpret_cast<float*>(S);
-  for (int rb = 0; rb < H; rb += rows_per_pass) {
-    float acc[4][4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) acc[i][j] = bs ? bs[to * 4 + j] : 0.f;
-    const int r0 = rb + tr * 4;
-#pragma unroll 4
-    for (int c = 0; c < kC; ++c) {
-      const float4 mre = *reinterpret_cast<const float4*>(Mt + c * kC2 + to * 4);
-      const float4 mim = *reinterpret_cast<const float4*>(Mt + (c + kC) * kC2 + to * 4);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float2 y = S[(r0 + i) * kC + c];
-        acc[i][0] = fmaf(y.x, mre.x, fmaf(y.y, mim.x, acc[i][0]));
-        acc[i][1] = fmaf(y.x, mre.y, fmaf(y.y, mim.y, acc[i][1]));
-        acc[i][2] = fmaf(y.x, mre.z, fmaf(y.y, mim.z, acc[i][2]));
-        acc[i][3] = fmaf(y.x, mre.w, fmaf(y.y, mim.w, acc[i][3]));
-      }
-    }
-    __syncwarp();      // the 16 threads sharing rows r0..r0+3 are in this warp: reads done before writes
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int o = to * 4 + j;
-        Sw[((r0 + i) * kC + (o & 31)) * 2 + (o >> 5)] = RELU ? fmaxf(acc[i][j], 0.f) : acc[i][j];
-      }
-  }
-}
-
 // ---- channel mix on the tensor cores (legacy warp-level path: mma.sync m16n8k8 TF32, error-compensated 3xTF32) -----------
 // A row of S is one frequency: 64 floats [Re c0, Im c0, Re c1, Im c1, ...] = the K index kk (input j = pi(kk) =
 // (kk >> 1) + 32 (kk & 1) of the reference's cat[Re, Im] order); the outputs are produced in the same interleaved order.
