@@ -253,20 +253,23 @@ __device__ __forceinline__ void sk_reduce_rows(const TcArgs& a, int BN, int K, i
   for (int i0 = r_begin * c4n + tid; i0 < i_end; i0 += nthr * U) {
     const float* wsp[U];
     float4 sum[U];
+    bool ok[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const int i = min(i0 + u * nthr, i_end - 1);          // clamped lanes load a valid address and are not stored
+      const int i = i0 + u * nthr;
+      ok[u] = i < i_end;
       wsp[u] = a.ws + ((size_t)st * a.sk_P * kBM + i / c4n) * BN + (i % c4n) * 4;
     }
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-    for (int u = 0; u < U; ++u) sum[u] = __ldcg(reinterpret_cast<const float4*>(wsp[u]));
+    for (int u = 0; u < U; ++u) sum[u] = ok[u] ? __ldcg(reinterpret_cast<const float4*>(wsp[u])) : zero;
     for (int p = 1; p < P; p += 4) {
       float4 t[4][U];
 #pragma unroll
       for (int q = 0; q < 4; ++q)
 #pragma unroll
         for (int u = 0; u < U; ++u)
-          t[q][u] = __ldcg(reinterpret_cast<const float4*>(wsp[u] + (size_t)min(p + q, P - 1) * pstride));
+          t[q][u] = (ok[u] && p + q < P) ? __ldcg(reinterpret_cast<const float4*>(wsp[u] + (size_t)(p + q) * pstride)) : zero;
 #pragma unroll
       for (int q = 0; q < 4; ++q)
         if (p + q < P) {                                     // pieces added strictly in order
@@ -1381,10 +1384,11 @@ int launch_v2(const CUtensorMap& mA1, const CUtensorMap& mA2, const CUtensorMap&
   return MTD_OK;
 }
 
-// Fused stream-K reduction (default on; mtd_tc_set_sk_fused(0) restores the separate tc_sk_finish_kernel launch): the
+// Fused stream-K reduction (mtd_tc_set_sk_fused(1); default off -- measured 0.7 ms / step SLOWER than the separate
+// tc_sk_finish_kernel launch, whose latency programmatic dependent launch already hides): the
 // counters are allocated once per device, zeroed, and left zero by every launch.  They cannot be allocated while the
 // stream is being captured into a CUDA graph -- such a call simply takes the two-launch path.
-int g_sk_fused = 1;
+int g_sk_fused = 0;
 unsigned* g_sk_cnt[64] = {};
 
 unsigned* sk_counters(cudaStream_t st) {
@@ -1885,7 +1889,7 @@ int mtd_tc_set_tuning(int bn, int sk_per) {
   return MTD_OK;
 }
 
-// 1 (default): the stream-K wave of the general kernel reduces its own pieces; 0: separate tc_sk_finish_kernel launch.
+// 1: the stream-K wave of the general kernel reduces its own pieces; 0 (default): separate tc_sk_finish_kernel launch.
 int mtd_tc_set_sk_fused(int enabled) {
   const int prev = g_sk_fused;
   g_sk_fused = enabled ? 1 : 0;
