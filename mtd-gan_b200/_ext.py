@@ -70,8 +70,6 @@ def load():
     _lib = lib
     if os.environ.get("MTD_PDL", "1") == "0":       # A/B switch for the programmatic-dependent-launch path
         lib.mtd_set_pdl(0)
-    if os.environ.get("MTD_SK_FUSED", "0") == "1":  # A/B switch: stream-K pieces reduced inside the conv kernel
-        lib.mtd_tc_set_sk_fused(1)
     return lib
 
 

@@ -77,8 +77,6 @@ struct TcArgs {
   float* ws;
   long long ws_floats;          // host side only: capacity of ws
   int grid;                     // host side only: CTAs to launch
-  // fused stream-K reduction (sk_cnt != nullptr): arrivals / completions per stream-K tile, all zero between launches
-  unsigned* sk_cnt;
 };
 
 // ---------------------------------------------------------------------------------------------------
@@ -230,70 +228,6 @@ struct WorkIter {
     return false;
   }
 };
-
-// out rows [r_begin, r_end) of stream-K tile `st` = epilogue( sum over the tile's pieces, in piece order ).  `tid` of
-// `nthr` threads; one thread per 4 output channels, consecutive threads walk a row (coalesced workspace reads / stores).
-__device__ __forceinline__ void sk_reduce_rows(const TcArgs& a, int BN, int K, int st, int r_begin, int r_end, int tid, int nthr) {
-  const int c4n = BN >> 2;
-  const int first = (st * K) / a.sk_per, last = ((st + 1) * K - 1) / a.sk_per;
-  int tile = a.n_dp + st, cls = 0;
-  if (a.n_cls > 1) { cls = tile / a.tiles_per_cls; tile -= cls * a.tiles_per_cls; }
-  const int ooy = a.n_cls > 1 ? (cls >> 1) : a.ooy, oox = a.n_cls > 1 ? (cls & 1) : a.oox;
-  const int nt = tile % a.n_nt;
-  int m = tile / a.n_nt;
-  const int mw = m % a.n_wt;
-  m /= a.n_wt;
-  const int mh = m % a.n_ht, mb = m / a.n_ht;
-  int ncols, nloc;
-  float* outp = tc_out_of(a, nt * BN, ncols, nloc);
-  // U items x 4 pieces of loads in flight per thread: the pass is a chain of L2 latencies otherwise
-  constexpr int U = 4;
-  const int P = last - first + 1, i_end = r_end * c4n;
-  const size_t pstride = (size_t)kBM * BN;
-  for (int i0 = r_begin * c4n + tid; i0 < i_end; i0 += nthr * U) {
-    const float* wsp[U];
-    float4 sum[U];
-    bool ok[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int i = i0 + u * nthr;
-      ok[u] = i < i_end;
-      wsp[u] = a.ws + ((size_t)st * a.sk_P * kBM + i / c4n) * BN + (i % c4n) * 4;
-    }
-    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-    for (int u = 0; u < U; ++u) sum[u] = ok[u] ? __ldcg(reinterpret_cast<const float4*>(wsp[u])) : zero;
-    for (int p = 1; p < P; p += 4) {
-      float4 t[4][U];
-#pragma unroll
-      for (int q = 0; q < 4; ++q)
-#pragma unroll
-        for (int u = 0; u < U; ++u)
-          t[q][u] = (ok[u] && p + q < P) ? __ldcg(reinterpret_cast<const float4*>(wsp[u] + (size_t)(p + q) * pstride)) : zero;
-#pragma unroll
-      for (int q = 0; q < 4; ++q)
-        if (p + q < P) {                                     // pieces added strictly in order
-#pragma unroll
-          for (int u = 0; u < U; ++u) { sum[u].x += t[q][u].x; sum[u].y += t[q][u].y; sum[u].z += t[q][u].z; sum[u].w += t[q][u].w; }
-        }
-    }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int i = i0 + u * nthr;
-      if (i >= i_end) continue;
-      const int c = (i % c4n) * 4, r = i / c4n;
-      const int bl = r / (a.TH * a.TW), rem = r - bl * (a.TH * a.TW);
-      const int hl = rem / a.TW, wl = rem - hl * a.TW;
-      const int b = mb * a.TB + bl;
-      if (b >= a.B) continue;
-      const size_t rowoff = (((size_t)b * a.outH + ((mh * a.TH + hl) * a.omy + ooy)) * a.outW +
-                             ((mw * a.TW + wl) * a.omx + oox)) * ncols + nloc;
-      tc_store4(a, outp, rowoff + c, nt * BN + c, tc_row_scale(a, b), sum[u].x, sum[u].y, sum[u].z, sum[u].w);
-    }
-  }
-}
-
-constexpr int kSkCntStride = 256;      // sk_cnt[st] = arrivals, sk_cnt[kSkCntStride + st] = completed reducers (st < #SM <= 256)
 
 struct PipeState {
   int stage = 0;
@@ -473,7 +407,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
     const int hl = rem / a.TW, wl = rem - hl * a.TW;
     WorkIter wi(a, kiters);
     Work wk;
-    int pend0 = -1, pend1 = -1;                    // stream-K tiles this CTA holds a piece of (sk_per < K: at most two)
     for (int lt = 0; wi.next(a, kiters, wk); ++lt) {
       int b0, h0, w0, n0, cls;
       decode_tile(wk.tile, b0, h0, w0, n0, cls);
@@ -510,47 +443,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(acc));
-      if (a.sk_cnt != nullptr && wk.slot >= 0) {
-        // fused reduction, step 1: publish this piece (stores -> fence -> barrier of the 4 epilogue warps -> one arrival)
-        __threadfence();
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        const int st = wk.tile - a.n_dp;
-        if (r == 0) atomicAdd(a.sk_cnt + st, 1u);
-        if (pend0 < 0) pend0 = st; else pend1 = st;
-      }
-    }
-    if (a.sk_cnt != nullptr) {
-      // fused reduction, step 2 (after ALL of this CTA's pieces are published, so no CTA ever waits on a CTA that waits):
-      // once every piece of a tile has arrived, each of its P piece owners reduces 128 / P rows of it, pieces in order.
-      // All CTAs of the launch are co-resident (grid <= #SM, one CTA per SM), which makes the wait safe; it is bounded
-      // (trap) like every other wait of this kernel.
-      for (int k = 0; k < 2; ++k) {
-        const int st = k == 0 ? pend0 : pend1;
-        if (st < 0) break;
-        const int first = (st * kiters) / a.sk_per, last = ((st + 1) * kiters - 1) / a.sk_per;
-        const unsigned P = (unsigned)(last - first + 1);
-        const int pi = (int)blockIdx.x - first;
-        if (lane == 0) {
-          int spins = 0;
-          while (true) {
-            unsigned seen;
-            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(a.sk_cnt + st) : "memory");
-            if (seen >= P) break;
-            if (++spins > 64) __nanosleep(32);
-            if (spins > (1 << 21)) __trap();
-          }
-        }
-        __syncwarp();
-        sk_reduce_rows(a, BN, kiters, st, (pi * kBM) / (int)P, ((pi + 1) * kBM) / (int)P, r, 128);
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (r == 0) {
-          const unsigned done = atomicAdd(a.sk_cnt + kSkCntStride + st, 1u);
-          if (done == P - 1) {                     // every owner has read the counter: reset both for the next launch
-            a.sk_cnt[st] = 0u;
-            a.sk_cnt[kSkCntStride + st] = 0u;
-          }
-        }
-      }
     }
   }
 
@@ -1143,10 +1035,37 @@ conv_c32_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
 // writes are coalesced.
 __global__ void __launch_bounds__(256) tc_sk_finish_kernel(const __grid_constant__ TcArgs a, int BN, int K) {
   mtd_pdl_prologue();
-  // blockIdx.y = stream-K tile; the blocks of a tile split its 128 rows
-  const int per = (kBM + (int)gridDim.x - 1) / (int)gridDim.x;
-  const int r0 = (int)blockIdx.x * per, r1 = min(kBM, r0 + per);
-  if (r0 < r1) sk_reduce_rows(a, BN, K, (int)blockIdx.y, r0, r1, threadIdx.x, blockDim.x);
+  const int c4n = BN >> 2;
+  const long long total = (long long)a.sk_tiles * kBM * c4n;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % c4n) * 4;
+    const int r = (int)((i / c4n) % kBM);
+    const int st = (int)(i / ((long long)c4n * kBM));
+    const int first = (st * K) / a.sk_per, last = ((st + 1) * K - 1) / a.sk_per;
+    int tile = a.n_dp + st, cls = 0;
+    if (a.n_cls > 1) { cls = tile / a.tiles_per_cls; tile -= cls * a.tiles_per_cls; }
+    const int ooy = a.n_cls > 1 ? (cls >> 1) : a.ooy, oox = a.n_cls > 1 ? (cls & 1) : a.oox;
+    const int nt = tile % a.n_nt;
+    int m = tile / a.n_nt;
+    const int mw = m % a.n_wt;
+    m /= a.n_wt;
+    const int mh = m % a.n_ht, mb = m / a.n_ht;
+    const int bl = r / (a.TH * a.TW), rem = r - bl * (a.TH * a.TW);
+    const int hl = rem / a.TW, wl = rem - hl * a.TW;
+    const int b = mb * a.TB + bl;
+    if (b >= a.B) continue;
+    const float* wsp = a.ws + ((size_t)st * a.sk_P * kBM + r) * BN + c;
+    float4 sum = __ldcg(reinterpret_cast<const float4*>(wsp));
+    for (int p = 1; p <= last - first; ++p) {
+      const float4 t = __ldcg(reinterpret_cast<const float4*>(wsp + (size_t)p * kBM * BN));
+      sum.x += t.x; sum.y += t.y; sum.z += t.z; sum.w += t.w;
+    }
+    int ncols, nloc;
+    float* outp = tc_out_of(a, nt * BN, ncols, nloc);
+    const size_t rowoff = (((size_t)b * a.outH + ((mh * a.TH + hl) * a.omy + ooy)) * a.outW +
+                           ((mw * a.TW + wl) * a.omx + oox)) * ncols + nloc;
+    tc_store4(a, outp, rowoff + c, nt * BN + c, tc_row_scale(a, b), sum.x, sum.y, sum.z, sum.w);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -1384,26 +1303,6 @@ int launch_v2(const CUtensorMap& mA1, const CUtensorMap& mA2, const CUtensorMap&
   return MTD_OK;
 }
 
-// Fused stream-K reduction (mtd_tc_set_sk_fused(1); default off -- measured 0.7 ms / step SLOWER than the separate
-// tc_sk_finish_kernel launch, whose latency programmatic dependent launch already hides): the
-// counters are allocated once per device, zeroed, and left zero by every launch.  They cannot be allocated while the
-// stream is being captured into a CUDA graph -- such a call simply takes the two-launch path.
-int g_sk_fused = 0;
-unsigned* g_sk_cnt[64] = {};
-
-unsigned* sk_counters(cudaStream_t st) {
-  int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
-  if (g_sk_cnt[dev]) return g_sk_cnt[dev];
-  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
-  if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) return nullptr;
-  unsigned* p = nullptr;
-  if (cudaMalloc(&p, 2 * kSkCntStride * sizeof(unsigned)) != cudaSuccess) { cudaGetLastError(); return nullptr; }
-  if (cudaMemset(p, 0, 2 * kSkCntStride * sizeof(unsigned)) != cudaSuccess) { cudaGetLastError(); cudaFree(p); return nullptr; }
-  g_sk_cnt[dev] = p;
-  return p;
-}
-
 // v1 kernel: whole-tile waves + one stream-K wave (choose_schedule), partial sums through a.ws, no atomics.
 int launch_tc_v1(const float* x1, const float* x2, const float* wp, int passes, TcArgs& a, cudaStream_t st) {
   const int m_tiles = a.n_wt * a.n_ht * a.n_bt;
@@ -1418,10 +1317,6 @@ int launch_tc_v1(const float* x1, const float* x2, const float* wp, int passes, 
   a.n_tiles = a.tiles_per_cls * a.n_cls;
   a.n_dp = sc.n_dp; a.sk_tiles = sc.sk_tiles; a.sk_per = sc.sk_per; a.sk_P = sc.sk_P; a.grid = sc.grid;
   a.ksplit = 1; a.kper = kiters;
-  a.sk_cnt = nullptr;
-  // every piece shorter than a tile (so a CTA touches at most two stream-K tiles), all CTAs co-resident
-  if (g_sk_fused && a.sk_tiles > 0 && a.sk_tiles <= kSkCntStride && a.sk_per < kiters && a.grid <= mtd_sm_count())
-    a.sk_cnt = sk_counters(st);
   CUtensorMap mA1, mA2, mB;
   if (a.es < 1) { a.es = 1; a.inH = a.H; a.inW = a.W; }
   int rc = make_act_map(&mA1, x1, a.C1, a.inW, a.inH, a.B, a.TW, a.TH, a.TB, false, a.es);
@@ -1444,9 +1339,11 @@ int launch_tc_v1(const float* x1, const float* x2, const float* wp, int passes, 
   else { TC_DISPATCH(32); }
 #undef TC_DISPATCH
   if (rc) return rc;
-  if (a.sk_tiles > 0 && a.sk_cnt == nullptr) {
-    const int bx = (kBM * (BN / 4) + 255) / 256;            // one float4 per thread
-    mtd_launch(tc_sk_finish_kernel, dim3(bx, a.sk_tiles), 256, 0, st, a, BN, kiters);
+  if (a.sk_tiles > 0) {
+    const long long work = (long long)a.sk_tiles * kBM * (BN / 4);
+    int blocks = (int)((work + 255) / 256);
+    if (blocks > mtd_sm_count() * 8) blocks = mtd_sm_count() * 8;
+    mtd_launch(tc_sk_finish_kernel, blocks, 256, 0, st, a, BN, kiters);
     MTD_CHECK_LAUNCH();
   }
   return MTD_OK;
@@ -1887,13 +1784,6 @@ int mtd_tc_set_tuning(int bn, int sk_per) {
   if (bn != 0 && bn != 32 && bn != 64 && bn != 128) return MTD_EINVAL;
   g_tune_bn = bn; g_tune_per = sk_per;
   return MTD_OK;
-}
-
-// 1: the stream-K wave of the general kernel reduces its own pieces; 0 (default): separate tc_sk_finish_kernel launch.
-int mtd_tc_set_sk_fused(int enabled) {
-  const int prev = g_sk_fused;
-  g_sk_fused = enabled ? 1 : 0;
-  return prev;
 }
 
 // 1 (default): 32 -> 32 channel 3x3 layers run on the halo-tile kernel (conv_c32_kernel); 0: on the general kernel.

@@ -581,51 +581,3 @@ def test_halo_tile_kernel_equals_general_kernel(passes):
     finally:
         ops.set_conv_mode("auto", 3)
 
-
-SK_CASES = [
-    # B, H, W, C1, C2, N, k, stride   (layers whose tile count is not a multiple of the SM count: a stream-K wave exists)
-    (20, 8, 8, 256, 0, 512, 3, 1),
-    (20, 4, 4, 512, 512, 512, 3, 1),
-    (20, 16, 16, 128, 0, 256, 3, 1),
-    (20, 32, 32, 64, 64, 64, 3, 1),
-    (20, 16, 16, 128, 0, 256, 4, 2),       # its data gradient is the four-parity-class launch
-    (3, 16, 16, 64, 0, 128, 3, 1),
-]
-
-
-@pytest.mark.parametrize("case", SK_CASES, ids=lambda c: "x".join(map(str, c)))
-def test_fused_streamk_reduction_is_bit_identical(case):
-    """The stream-K wave of the general tcgen05 kernel reduces its pieces either inside the kernel (each piece owner sums
-    128 / P rows once every piece has arrived) or in a second launch; both add the pieces in the same order, so outputs
-    and data gradients are bit-identical -- also over repeated launches (the arrival counters reset themselves)."""
-    from mtdgan_b200 import _ext, ops
-    B, H, W, C1, C2, N, k, s = case
-    C = C1 + C2
-    ops.set_conv_mode("auto", 3)
-    lib = _ext.load()
-    pad = 1
-    xc = nhwc(_rand(B, C, H, W, seed=11).float()).to(DEV)
-    x1 = xc[..., :C1].contiguous().requires_grad_(True)
-    x2 = xc[..., C1:].contiguous().requires_grad_(True) if C2 else None
-    w = _rand(N, C, k, k, seed=12, scale=1.0 / math.sqrt(C * k * k)).float().to(DEV).requires_grad_(True)
-    b = _rand(N, seed=13, scale=0.1).float().to(DEV).requires_grad_(True)
-    Ho = (H + 2 * pad - k) // s + 1
-    g = nhwc(_rand(B, N, Ho, Ho, seed=14).float()).to(DEV)
-    cfg = ops.ConvCfg(cin=C, cout=N, kh=k, kw=k, stride=s, pad=pad, pre_act=ops.ACT_LEAKY)
-
-    def run():
-        y = ops.conv(x1, w, b, cfg, x2=x2)
-        gr = torch.autograd.grad(y, [x1] + ([x2] if C2 else []), g)
-        return [y.detach().clone()] + [t.clone() for t in gr]
-
-    prev = lib.mtd_tc_set_sk_fused(0)
-    try:
-        ref = run()
-        lib.mtd_tc_set_sk_fused(1)
-        for _ in range(20):
-            got = run()
-            for a_, b_ in zip(got, ref):
-                assert torch.equal(a_, b_)
-    finally:
-        lib.mtd_tc_set_sk_fused(prev)
-    torch.cuda.synchronize()
