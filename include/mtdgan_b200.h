@@ -121,6 +121,7 @@ int mtd_tc_set_version(int version);
  * tiles only) of the forward/dgrad tensor-core kernel; 0 = chosen by the built-in cost model (the default).     */
 int mtd_tc_set_tuning(int bn, int sk_per);
 int mtd_tc_set_c32(int enabled);   /* 1 (default): 32->32 3x3 layers on the halo-tile kernel; returns the previous value */
+int mtd_tc_set_halo(int enabled);  /* 1 (default): 3x3 stride-1 layers with > 32 channels on the streamed-weight halo-tile kernel; returns the previous value */
 /* in-place round-to-nearest fp32 -> tf32 of a packed weight buffer (tcgen05 truncates its operands)  */
 int mtd_round_tf32(float* p, long long n, void* stream);
 /* ws / ws_floats (both TC entry points): caller-owned fp32 scratch (contents undefined before and after; one per

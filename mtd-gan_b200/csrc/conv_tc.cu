@@ -1030,6 +1030,303 @@ conv_c32_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
   }
 }
 
+// =====================================================================================================
+// General 3x3 / stride-1 layers (any multiple of 32 input channels from one or two sources, Cout tile BN = 32/64/128):
+// the halo-tile scheme of conv_c32_kernel with the weights STREAMED instead of resident -- every 3x3 layer of the
+// U-Net discriminator at 16x16 ... 64x64 resolution, forward and data gradient.
+//
+// The tap-streaming kernel (conv_tc_kernel) is bound by shared-memory bandwidth (ncu: tensor-core operand reads 46 % +
+// LSU 40 % of the data pipe, tensor pipe 48 % busy): per 32-channel k-step it moves 192 KB through shared memory -- 48 KB
+// of TMA writes, 48 KB of operand splitting (the SAME pixels re-split for each of the nine taps) and 96 KB of tensor-core
+// reads.  Here, per 32-channel chunk of a 16 x 8 pixel tile,
+//   * ONE halo box (18 x 10 pixels, 23 KB) is loaded and split ONCE into tf32 hi / lo planes; its nine taps are nine
+//     descriptor start addresses (see conv_c32_kernel): operand-split traffic and A loads drop 9 x 128 / 180 = 6.4-fold;
+//   * the hi | lo weight tile of a (chunk, tap) is ONE B operand of 2*BN rows: a_hi * [w_hi | w_lo] is one N = 2*BN MMA
+//     (the A slice is read once for both products), a_lo * w_hi a second N = BN MMA into the upper accumulator half;
+//     the epilogue adds the halves.  Tensor-core operand reads per k-step: 80 KB instead of 96 KB (BN = 128).
+// Shared-memory traffic per k-step: ~120 KB instead of 192 KB; L2 -> SM traffic 34.6 KB instead of 48 KB.
+// k index of this kernel: it = chunk * 9 + tap (chunk-major: a halo is used for nine consecutive k-steps); the work
+// decomposition (whole tiles + one stream-K wave, tc_sk_finish_kernel) is the one of conv_tc_kernel.
+// =====================================================================================================
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(done)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return done != 0;
+}
+
+// chunk segments of a CTA's work list, in order: (tile, chunk = it / 9, taps [it % 9, ...)) -- one halo each
+struct SegIter {
+  WorkIter wi;
+  Work wk;
+  int it;
+  bool ok;
+  __device__ __forceinline__ SegIter(const TcArgs& a, int K) : wi(a, K) {
+    ok = wi.next(a, K, wk);
+    it = ok ? wk.kb : 0;
+  }
+  __device__ __forceinline__ void advance(const TcArgs& a, int K) {
+    it = (it / 9 + 1) * 9;
+    if (it >= wk.ke) {
+      ok = wi.next(a, K, wk);
+      it = ok ? wk.kb : 0;
+    }
+  }
+};
+
+template <int BN, int NPASS>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_halo_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUtensorMap mapA2,
+                 const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapBlo,
+                 const __grid_constant__ TcArgs a) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  constexpr int kNA = NPASS == 3 ? 2 : 1;
+  constexpr int kBStage = kNA * BN * 128;                            // [w_hi | w_lo] of one (chunk, tap)
+  constexpr uint32_t kAccCols = NPASS == 3 ? 2 * BN : BN;            // main | cross-term accumulator
+  constexpr uint32_t kTmemCols = 2 * kAccCols < 32 ? 32 : 2 * kAccCols;
+  const int R = a.ra, S = a.stages;                                  // raw halo stages (1 or 2), weight ring depth
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t raw_base = base;
+  const uint32_t cv_base = raw_base + (uint32_t)R * kRawStage;       // 2 split stages (8 hi planes | 8 lo planes)
+  const uint32_t b_base = cv_base + 2u * kCvStage;                   // kCvStage = 45 * 1024: 1024-aligned
+  const uint32_t bar_base = b_base + (uint32_t)S * kBStage;
+  auto rfull = [&](int s) { return bar_base + 8u * s; };
+  auto rempty = [&](int s) { return bar_base + 8u * (2 + s); };
+  auto cfull = [&](int s) { return bar_base + 8u * (4 + s); };
+  auto cempty = [&](int s) { return bar_base + 8u * (6 + s); };
+  auto tfull_bar = [&](int i) { return bar_base + 8u * (8 + i); };
+  auto tempty_bar = [&](int i) { return bar_base + 8u * (10 + i); };
+  auto bfull = [&](int s) { return bar_base + 8u * (12 + s); };
+  auto bempty = [&](int s) { return bar_base + 8u * (12 + S + s); };
+  const uint32_t tmem_slot = bar_base + 8u * (12 + 2 * S);
+  unsigned char* gen_base = smem_raw + (base - smem_u32(smem_raw));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kchunks = a.kc1 + a.kc2;
+  const int kiters = 9 * kchunks;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&mapA1);
+    if (a.kc2) prefetch_tmap(&mapA2);
+    prefetch_tmap(&mapB);
+    if (NPASS == 3) prefetch_tmap(&mapBlo);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(rfull(s), 1);
+      mbar_init(rempty(s), 4);
+      mbar_init(cfull(s), 4);
+      mbar_init(cempty(s), 1);
+      mbar_init(tfull_bar(s), 1);
+      mbar_init(tempty_bar(s), 4);
+    }
+    for (int s = 0; s < S; ++s) {
+      mbar_init(bfull(s), 1);
+      mbar_init(bempty(s), 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(kTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gen_base + (tmem_slot - base));
+  mtd_pdl_prologue();
+
+  // tile -> (sample, first row, first column, first output channel); pixel tiles are 16 rows x 8 columns of one sample
+  auto decode_tile = [&](int tile, int& b, int& h0, int& w0, int& n0) {
+    const int nt = tile % a.n_nt;
+    int m = tile / a.n_nt;
+    const int mw = m % a.n_wt;
+    m /= a.n_wt;
+    const int mh = m % a.n_ht;
+    b = m / a.n_ht; h0 = mh * 16; w0 = mw * 8; n0 = nt * BN;
+  };
+
+  if (warp == 0) {
+    // ===== TMA producer: weight tiles in k order; halo boxes as early as the raw stages allow =====
+    if (lane == 0) {
+      SegIter hs(a, kiters);
+      PipeState hr, bs;
+      int issued = 0, needed = 0;
+      auto issue_halo = [&]() {             // caller has made sure (or accepts waiting until) the raw stage is free
+        int b, h0, w0, n0;
+        decode_tile(hs.wk.tile, b, h0, w0, n0);
+        const int cc = hs.it / 9;
+        mbar_wait(rempty(hr.stage), hr.phase ^ 1u);
+        mbar_expect_tx(rfull(hr.stage), kRawBytes);
+        const uint32_t dst = raw_base + (uint32_t)hr.stage * kRawStage;
+        if (cc < a.kc1) tma_load_4d(&mapA1, dst, rfull(hr.stage), cc * 32, w0 - 1, h0 - 1, b);
+        else tma_load_4d(&mapA2, dst, rfull(hr.stage), (cc - a.kc1) * 32, w0 - 1, h0 - 1, b);
+        hr.advance(R);
+        hs.advance(a, kiters);
+        ++issued;
+      };
+      WorkIter wi(a, kiters);
+      Work wk;
+      while (wi.next(a, kiters, wk)) {
+        int b, h0, w0, n0;
+        decode_tile(wk.tile, b, h0, w0, n0);
+        const int nblk = n0 >> 5;
+        for (int it = wk.kb; it < wk.ke; ++it) {
+          const int cc = it / 9, t = it - cc * 9;
+          if (it == wk.kb || t == 0) {
+            ++needed;                                              // the MMA cannot pass this k-step without its halo
+            while (issued < needed) issue_halo();
+          } else if (hs.ok && mbar_test(rempty(hr.stage), hr.phase ^ 1u)) {
+            issue_halo();                                          // a raw stage is free: prefetch the next chunk's halo
+          }
+          mbar_wait(bempty(bs.stage), bs.phase ^ 1u);
+          mbar_expect_tx(bfull(bs.stage), kBStage);
+          const uint32_t sb = b_base + (uint32_t)bs.stage * kBStage;
+          tma_load_4d(&mapB, sb, bfull(bs.stage), 0, 0, t * kchunks + cc, nblk);
+          if (NPASS == 3) tma_load_4d(&mapBlo, sb + BN * 128, bfull(bs.stage), 0, 0, t * kchunks + cc, nblk);
+          bs.advance(S);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      PipeState cs, bs;
+      constexpr uint32_t idesc_main = make_idesc((int)kAccCols), idesc_lo = make_idesc(BN);
+      const uint64_t da_stage[2] = {make_interleave_desc(cv_base, kPlaneBytes, kHaloW * 16),
+                                    make_interleave_desc(cv_base + kCvStage, kPlaneBytes, kHaloW * 16)};
+      uint64_t da_hi = da_stage[0];
+      WorkIter wi(a, kiters);
+      Work wk;
+      for (int lt = 0; wi.next(a, kiters, wk); ++lt) {
+        const int acc = lt & 1;
+        const uint32_t acc_phase = (uint32_t)(lt >> 1) & 1u;
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)acc * kAccCols;
+        for (int it = wk.kb; it < wk.ke; ++it) {
+          const int cc = it / 9, t = it - cc * 9;
+          if (it == wk.kb || t == 0) {
+            mbar_wait(cfull(cs.stage), cs.phase);
+            da_hi = cs.stage ? da_stage[1] : da_stage[0];
+          }
+          mbar_wait(bfull(bs.stage), bs.phase);
+          tc_fence_after();
+          // descriptor start-address arithmetic in 16-byte units: + tap shift, + 2 planes per K = 8 slice, lo planes after
+          // the 8 hi planes; the K slices of the weight tile are 32 B apart
+          const uint64_t dat = da_hi + (uint64_t)((a.dy[t] + 1) * kHaloW + (a.dx[t] + 1));
+          const uint64_t dbt = make_sw128_desc(b_base + (uint32_t)bs.stage * kBStage);
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            umma_tf32(tmem_d, dat + (uint64_t)(kk * (2 * kPlaneBytes >> 4)), dbt + 2u * kk, idesc_main, (it > wk.kb || kk > 0) ? 1u : 0u);
+            if (NPASS == 3)
+              umma_tf32(tmem_d + BN, dat + (uint64_t)((8 + 2 * kk) * (kPlaneBytes >> 4)), dbt + 2u * kk, idesc_lo, 1u);
+          }
+          umma_commit(bempty(bs.stage));
+          bs.advance(S);
+          if (it == wk.ke - 1 || t == 8) {
+            umma_commit(cempty(cs.stage));
+            cs.advance(2);
+          }
+        }
+        umma_commit(tfull_bar(acc));
+      }
+    }
+  } else if (warp < 6) {
+    // ===== operand split: raw halo (pixel-major, swizzled) -> tf32 hi / lo planes (chunk-major), once per chunk segment =====
+    const int ct = threadIdx.x - 64;               // 0..127
+    PipeState sr, sc;
+    for (SegIter sg(a, kiters); sg.ok; sg.advance(a, kiters)) {
+      mbar_wait(rfull(sr.stage), sr.phase);
+      mbar_wait(cempty(sc.stage), sc.phase ^ 1u);
+      const unsigned char* raw = gen_base + (raw_base - base) + (size_t)sr.stage * kRawStage;
+      unsigned char* hip = gen_base + (cv_base - base) + (size_t)sc.stage * kCvStage;
+      unsigned char* lop = hip + 8 * kPlaneBytes;
+#pragma unroll 4
+      for (int i = ct; i < 8 * kHaloPix; i += 128) {
+        const int kc = i / kHaloPix, p = i - kc * kHaloPix;           // consecutive lanes: consecutive halo pixels, same chunk
+        const uint4 v = *reinterpret_cast<const uint4*>(raw + (size_t)p * 128 + ((kc ^ (p & 7)) << 4));
+        uint4 h;
+        h.x = (v.x + 0x1000u) & 0xffffe000u; h.y = (v.y + 0x1000u) & 0xffffe000u;
+        h.z = (v.z + 0x1000u) & 0xffffe000u; h.w = (v.w + 0x1000u) & 0xffffe000u;
+        *reinterpret_cast<uint4*>(hip + (size_t)kc * kPlaneBytes + (size_t)p * 16) = h;
+        if (NPASS == 3) {
+          uint4 l;
+          l.x = (__float_as_uint(__uint_as_float(v.x) - __uint_as_float(h.x)) + 0x1000u) & 0xffffe000u;
+          l.y = (__float_as_uint(__uint_as_float(v.y) - __uint_as_float(h.y)) + 0x1000u) & 0xffffe000u;
+          l.z = (__float_as_uint(__uint_as_float(v.z) - __uint_as_float(h.z)) + 0x1000u) & 0xffffe000u;
+          l.w = (__float_as_uint(__uint_as_float(v.w) - __uint_as_float(h.w)) + 0x1000u) & 0xffffe000u;
+          *reinterpret_cast<uint4*>(lop + (size_t)kc * kPlaneBytes + (size_t)p * 16) = l;
+        }
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> tensor-core (async proxy) reads
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(cfull(sc.stage));
+        mbar_arrive(rempty(sr.stage));
+      }
+      sr.advance(R);
+      sc.advance(2);
+    }
+  } else {
+    // ===== epilogue =====
+    const int q = warp & 3;                        // TMEM lane group this warp may access
+    const int r = q * 32 + lane;                   // accumulator row: pixel (hl, wl) = (r / 8, r % 8) of the tile
+    const int hl = r >> 3, wl = r & 7;
+    WorkIter wi(a, kiters);
+    Work wk;
+    for (int lt = 0; wi.next(a, kiters, wk); ++lt) {
+      int b, h0, w0, n0;
+      decode_tile(wk.tile, b, h0, w0, n0);
+      const int acc = lt & 1;
+      const uint32_t acc_phase = (uint32_t)(lt >> 1) & 1u;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const float scale = tc_row_scale(a, b);
+      int ncols, nloc;
+      float* outp = tc_out_of(a, n0, ncols, nloc);
+      const size_t rowoff = (((size_t)b * a.outH + (h0 + hl)) * a.outW + (w0 + wl)) * ncols + nloc;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t v[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * kAccCols + (uint32_t)c0;
+        tmem_ld32(taddr, v);
+        if (NPASS == 3) {
+          uint32_t u[32];
+          tmem_ld32(taddr + BN, u);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(u[j]));
+        }
+        if (wk.slot >= 0) {
+          float* wrow = a.ws + ((size_t)wk.slot * kBM + r) * BN + c0;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<float4*>(wrow + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                                                               __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            tc_store4(a, outp, rowoff + c0 + j, n0 + c0 + j, scale, __uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                      __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+  }
+}
+
 // second phase of a stream-K launch (v1 kernel): out tile = epilogue( sum over the tile's pieces, in piece order ).
 // One thread per 4 output channels of one tile row; consecutive threads walk a row, so workspace reads and output
 // writes are coalesced.
@@ -1396,6 +1693,97 @@ int launch_c32(const float* x, const float* wp, int passes, TcArgs& a, cudaStrea
   return passes == 3 ? launch_c32_n<3>(mA, mB, mBlo, a, st) : launch_c32_n<1>(mA, mB, mBlo, a, st);
 }
 
+// ---- general halo-tile kernel (3x3 / stride 1, C and N multiples of 32): host side ------------------------------------
+int g_halo_enabled = 1;     // mtd_tc_set_halo(0) routes these layers through the tap-streaming kernel (A/B measurements)
+
+bool taps_are_3x3(const TcArgs& a) {
+  if (a.T != 9) return false;
+  bool seen[9] = {};
+  for (int t = 0; t < 9; ++t) {       // exactly the 3 x 3 neighbourhood (any order)
+    if (a.dy[t] < -1 || a.dy[t] > 1 || a.dx[t] < -1 || a.dx[t] > 1) return false;
+    seen[(a.dy[t] + 1) * 3 + a.dx[t] + 1] = true;
+  }
+  for (bool s_ : seen) if (!s_) return false;
+  return true;
+}
+
+bool halo_eligible(const TcArgs& a) {
+  if (!g_halo_enabled || g_tc_version != 1) return false;
+  if (a.C1 % 32 || a.C2 % 32 || a.N % 32 || a.es > 1 || a.n_cls > 1) return false;
+  if (a.omy != 1 || a.omx != 1 || a.ooy != 0 || a.oox != 0 || a.outH != a.H || a.outW != a.W) return false;
+  if (a.H % 16 || a.W % 8) return false;
+  return taps_are_3x3(a);
+}
+
+template <int BN, int NPASS>
+int launch_halo_bn(const CUtensorMap& mA1, const CUtensorMap& mA2, const CUtensorMap& mB, const CUtensorMap& mBlo, TcArgs& a,
+                   cudaStream_t st) {
+  constexpr int kBStage = (NPASS == 3 ? 2 : 1) * BN * 128;
+  const int avail = 227 * 1024 - 1024 - 512 - 2 * kCvStage;
+  a.ra = (avail - 2 * kRawStage) / kBStage >= 3 ? 2 : 1;          // two raw halo stages unless that starves the weight ring
+  int stages = (avail - a.ra * kRawStage) / kBStage;
+  if (stages > 6) stages = 6;
+  if (stages < 2) return MTD_EINVAL;
+  a.stages = stages;
+  const size_t smem = 1024 + (size_t)a.ra * kRawStage + 2 * kCvStage + (size_t)stages * kBStage + 8 * (13 + 2 * stages) + 16;
+  static bool attr_set = false;
+  if (!attr_set) {
+    MTD_CUDA(cudaFuncSetAttribute(conv_halo_kernel<BN, NPASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  mtd_launch(conv_halo_kernel<BN, NPASS>, a.grid, kThreads, smem, st, mA1, mA2, mB, mBlo, a);
+  MTD_CHECK_LAUNCH();
+  return MTD_OK;
+}
+
+int launch_halo(const float* x1, const float* x2, const float* wp, int passes, TcArgs& a, cudaStream_t st) {
+  a.TW = 8; a.TH = 16; a.TB = 1;
+  a.n_wt = a.W / 8; a.n_ht = a.H / 16; a.n_bt = a.B;
+  const int m_tiles = a.n_wt * a.n_ht * a.n_bt;
+  a.m_tiles = m_tiles;
+  a.kc1 = a.C1 / 32; a.kc2 = a.C2 / 32;
+  const int kiters = 9 * (a.kc1 + a.kc2);
+  if (a.ws && !mtd_aligned16(a.ws)) return MTD_EALIGN;
+  a.n_cls = 1;
+  const Schedule sc = choose_schedule(m_tiles, a.N, kiters, passes, a.ws ? a.ws_floats : 0, a.n_split);
+  if (sc.cost >= 1e30) return MTD_EINVAL;
+  const int BN = sc.bn;
+  a.n_nt = a.N / BN;
+  a.tiles_per_cls = m_tiles * a.n_nt;
+  a.n_tiles = a.tiles_per_cls;
+  a.n_dp = sc.n_dp; a.sk_tiles = sc.sk_tiles; a.sk_per = sc.sk_per; a.sk_P = sc.sk_P; a.grid = sc.grid;
+  a.ksplit = 1; a.kper = kiters;
+  a.es = 1; a.inH = a.H; a.inW = a.W;
+  CUtensorMap mA1, mA2, mB;
+  int rc = make_act_map(&mA1, x1, a.C1, a.W, a.H, a.B, kHaloW, kHaloH, 1, false, 1);
+  if (rc) return rc;
+  if (a.C2) { rc = make_act_map(&mA2, x2, a.C2, a.W, a.H, a.B, kHaloW, kHaloH, 1, false, 1); if (rc) return rc; }
+  else mA2 = mA1;
+  const long long K = 9LL * (a.C1 + a.C2);
+  rc = make_w_map(&mB, wp, K, a.N, BN);
+  if (rc) return rc;
+  CUtensorMap mBlo = mB;
+  if (passes == 3) {
+    rc = make_w_map(&mBlo, wp + (size_t)a.wrows_total * K, K, a.N, BN);
+    if (rc) return rc;
+  }
+#define HALO_DISPATCH(BN_)                                                                \
+  rc = passes == 3 ? launch_halo_bn<BN_, 3>(mA1, mA2, mB, mBlo, a, st) : launch_halo_bn<BN_, 1>(mA1, mA2, mB, mBlo, a, st)
+  if (BN == 128) { HALO_DISPATCH(128); }
+  else if (BN == 64) { HALO_DISPATCH(64); }
+  else { HALO_DISPATCH(32); }
+#undef HALO_DISPATCH
+  if (rc) return rc;
+  if (a.sk_tiles > 0) {
+    const long long work = (long long)a.sk_tiles * kBM * (BN / 4);
+    int blocks = (int)((work + 255) / 256);
+    if (blocks > mtd_sm_count() * 8) blocks = mtd_sm_count() * 8;
+    mtd_launch(tc_sk_finish_kernel, blocks, 256, 0, st, a, BN, kiters);
+    MTD_CHECK_LAUNCH();
+  }
+  return MTD_OK;
+}
+
 // wp: packed weights, tile-major (mtd_conv_pack_*_blocked); for passes == 3 the buffer holds [hi | lo].
 // v2 kernel only: `finish` = run the split-K finishing pass here (false when the caller batches several launches into
 // one output, e.g. the four parity classes of a stride-2 dgrad); the chosen ksplit is returned through a.ksplit.
@@ -1407,6 +1795,7 @@ int launch_tc(const float* x1, const float* x2, const float* wp, int passes, TcA
       (a.bias && !mtd_aligned16(a.bias)))
     return MTD_EALIGN;
   if (c32_eligible(a)) return launch_c32(x1, wp, passes, a, st);
+  if (halo_eligible(a)) return launch_halo(x1, x2, wp, passes, a, st);
   a.n_wt = a.W / a.TW; a.n_ht = a.H / a.TH; a.n_bt = (a.B + a.TB - 1) / a.TB;
   const int m_tiles = a.n_wt * a.n_ht * a.n_bt;
   a.kc1 = a.C1 / 32; a.kc2 = a.C2 / 32;
@@ -1784,6 +2173,14 @@ int mtd_tc_set_tuning(int bn, int sk_per) {
   if (bn != 0 && bn != 32 && bn != 64 && bn != 128) return MTD_EINVAL;
   g_tune_bn = bn; g_tune_per = sk_per;
   return MTD_OK;
+}
+
+// 1 (default): 3x3 / stride-1 layers with more than 32 channels run on the general halo-tile kernel (conv_halo_kernel);
+// 0: on the tap-streaming kernel.
+int mtd_tc_set_halo(int enabled) {
+  const int prev = g_halo_enabled;
+  g_halo_enabled = enabled ? 1 : 0;
+  return prev;
 }
 
 // 1 (default): 32 -> 32 channel 3x3 layers run on the halo-tile kernel (conv_c32_kernel); 0: on the general kernel.

@@ -117,6 +117,11 @@ TC_CASES = [
     (5, 16, 8, 32, 0, 32, 3, 1, 0, 1, 0, False),         # halo-tile kernel: one 16 x 8 tile per image (all four borders padded)
     (1, 512, 512, 32, 0, 32, 3, 1, 1, 0, 1, True),       # halo-tile kernel at the inference geometry (2048 tiles, 14 per CTA)
     (3, 64, 32, 32, 0, 32, 3, 1, 0, 1, 0, False),        # halo-tile kernel, 4 x 4 tiles per image, ragged over 148 CTAs
+    (20, 32, 32, 128, 0, 128, 3, 1, 0, 2, 0, False),     # streamed-weight halo kernel: 160 tiles = one wave + a stream-K wave
+    (20, 16, 16, 256, 0, 256, 3, 1, 0, 2, 0, False),     # streamed-weight halo kernel: 80 tiles, all stream-K pieces
+    (4, 64, 64, 64, 0, 64, 3, 1, 1, 0, 1, True),         # streamed-weight halo kernel, BN = 64, ConvTranspose + skip + relu
+    (2, 16, 16, 64, 0, 96, 3, 1, 0, 1, 0, False),        # streamed-weight halo kernel, BN = 32 (Cout = 96)
+    (3, 16, 8, 96, 32, 64, 3, 1, 0, 2, 0, False),        # streamed-weight halo kernel, unequal two sources, one tile per image
 ]
 
 
@@ -581,3 +586,50 @@ def test_halo_tile_kernel_equals_general_kernel(passes):
     finally:
         ops.set_conv_mode("auto", 3)
 
+
+
+HALO_EQ_CASES = [
+    # B, H, W, C1, C2, N
+    (4, 64, 64, 64, 0, 64),
+    (20, 32, 32, 128, 0, 128),
+    (20, 16, 16, 256, 0, 256),
+    (20, 32, 32, 64, 64, 128),
+    (20, 16, 16, 512, 0, 256),
+    (2, 16, 8, 64, 0, 32),
+]
+
+
+@pytest.mark.parametrize("passes", [1, 3], ids=["tf32", "tf32x3"])
+@pytest.mark.parametrize("case", HALO_EQ_CASES, ids=lambda c: "x".join(map(str, c)))
+def test_streamed_halo_kernel_equals_tap_streaming_kernel(case, passes):
+    """3x3 / stride-1 layers with more than 32 channels: the streamed-weight halo-tile kernel and the tap-streaming kernel
+    evaluate the same tf32 products (same operand rounding); they differ in summation order only (chunk-major k order,
+    cross terms in their own accumulator).  Forward and both data gradients of a two-source layer."""
+    from mtdgan_b200 import _ext, ops
+    B, H, W, C1, C2, N = case
+    C = C1 + C2
+    ops.set_conv_mode("auto", passes)
+    lib = _ext.load()
+    try:
+        xc = nhwc(_rand(B, C, H, W, seed=21).float()).to(DEV)
+        x1 = xc[..., :C1].contiguous().requires_grad_(True)
+        x2 = xc[..., C1:].contiguous().requires_grad_(True) if C2 else None
+        w = _rand(N, C, 3, 3, seed=22, scale=1.0 / math.sqrt(9 * C)).float().to(DEV).requires_grad_(True)
+        b = _rand(N, seed=23, scale=0.1).float().to(DEV).requires_grad_(True)
+        g = nhwc(_rand(B, N, H, W, seed=25).float()).to(DEV)
+        cfg = ops.ConvCfg(cin=C, cout=N, kh=3, kw=3, stride=1, pad=1, pre_act=ops.ACT_LEAKY)
+        res = []
+        for enabled in (1, 0):
+            prev = lib.mtd_tc_set_halo(enabled)
+            try:
+                y = ops.conv(x1, w, b, cfg, x2=x2)
+                grads = torch.autograd.grad(y, [x1] + ([x2] if C2 else []), g)
+                res.append([y.detach().clone()] + [t.clone() for t in grads])
+            finally:
+                lib.mtd_tc_set_halo(prev)
+        torch.cuda.synchronize()
+        tol = 5e-6 if passes == 3 else 3e-5
+        for got, ref in zip(res[0], res[1]):
+            assert rel_err(got, ref) <= tol
+    finally:
+        ops.set_conv_mode("auto", 3)
