@@ -120,7 +120,7 @@ TC_CASES = [
     (20, 32, 32, 128, 0, 128, 3, 1, 0, 2, 0, False),     # streamed-weight halo kernel: 160 tiles = one wave + a stream-K wave
     (20, 16, 16, 256, 0, 256, 3, 1, 0, 2, 0, False),     # streamed-weight halo kernel: 80 tiles, all stream-K pieces
     (4, 64, 64, 64, 0, 64, 3, 1, 1, 0, 1, True),         # streamed-weight halo kernel, BN = 64, ConvTranspose + skip + relu
-    (2, 16, 16, 64, 0, 96, 3, 1, 0, 1, 0, False),        # streamed-weight halo kernel, BN = 32 (Cout = 96)
+    (2, 16, 16, 64, 0, 32, 3, 1, 0, 1, 0, False),        # streamed-weight halo kernel, BN = 32
     (3, 16, 8, 96, 32, 64, 3, 1, 0, 2, 0, False),        # streamed-weight halo kernel, unequal two sources, one tile per image
 ]
 
