@@ -14,7 +14,7 @@ case $w in
 smoke)
   timeout 600 python -c "import __graft_entry__ as g; g.smoke()" > $O/${TAG}_smoke.log 2>&1; echo "smoke rc=$?"; tail -2 $O/${TAG}_smoke.log ;;
 ktests)
-  timeout 1200 python -m pytest tests/test_gpu_kernels.py -m gpu -x -q -k "tcgen05_forward or halo" > $O/${TAG}_ktests.log 2>&1; echo "ktests rc=$?"
+  timeout 1200 python -m pytest tests/test_gpu_kernels.py -m gpu -x -q -k "tcgen05_forward or halo or streamed" > $O/${TAG}_ktests.log 2>&1; echo "ktests rc=$?"
   tail -4 $O/${TAG}_ktests.log ;;
 tests)
   rm -f $O/${TAG}_tally.jsonl
@@ -34,7 +34,7 @@ launches)
   python tools/launch_summary.py $O/${TAG}_launches_infer.csv 60 > $O/${TAG}_launches_infer.txt 2>&1 ;;
 ncu)
   i=0
-  for spec in "conv_tc_kernel:8" "conv_c32_kernel:6" "wgrad_tc_kernel:6" "fft_:12" "sn_:8" "pcgrad:4" "adamw:3" "conv_c1|conv_n1|thin_wgrad:9" \
+  for spec in "conv_tc_kernel:8" "conv_halo_kernel:8" "conv_c32_kernel:6" "wgrad_tc_kernel:6" "fft_:12" "sn_:8" "pcgrad:4" "adamw:3" "conv_c1|conv_n1|thin_wgrad:9" \
               "finish:8" "act_bwd:6" "conv_igemm|conv_wgrad_kernel:6" "upsample|pixel_shuffle|edge|sum_|loss:10"; do
     pat="${spec%%:*}"; cnt="${spec##*:}"; i=$((i+1))
     timeout 600 $NCU --set full --profile-from-start off -k "regex:$pat" -c $cnt -f -o /tmp/ncu_train_$i \
