@@ -381,10 +381,10 @@ def run_own(args):
 
 
 # Bytes of DRAM traffic per 512x512 slice measured by `ncu --set full` over one batch-1 generator forward (sum of
-# dram__bytes_read.sum + dram__bytes_write.sum over its 106 kernels; profiles/r02_ncu_infer512_launches.csv): 5.53 GB vs
+# dram__bytes_read.sum + dram__bytes_write.sum over its 105 kernels; profiles/r02_ncu_infer512_launches.csv): 5.51 GB vs
 # 3.22 GB algorithmic -- the half spectrum makes two HBM round trips per block (rows -> columns -> rows) that B_alg
 # assumes stay on chip.
-INFER_TRAFFIC_BYTES = 5526885632
+INFER_TRAFFIC_BYTES = 5513783296
 
 
 def run_inference(args, model, dev, rank, world, flush):
