@@ -734,15 +734,56 @@ __device__ __forceinline__ void pack_one(const float* __restrict__ w, float* __r
   }
 }
 
+// rows (n) of a pack handled by one block of the batched kernel
+__host__ __device__ inline int pack_rows_per_block(const PackArgs& p) {
+  const long long row = (long long)p.T * p.C;
+  return row >= kPackChunk ? 1 : (int)(kPackChunk / row);
+}
+
+constexpr int kPackTileC = 512, kPackLd = kPackTileC + 1;     // channels per shared-memory tile; +1: taps of a channel hit distinct banks
+
+// One block = a few whole rows n of one pack.  The source is walked with the TAP index fastest (the kh*kw taps of one
+// (n, c) pair are adjacent in every reference layout: 36 / 64 contiguous bytes), the packed copy is written with the
+// CHANNEL index fastest (its layout); the exchange goes through shared memory.  Reading in packed order instead costs a
+// 32-byte sector per element for the data-gradient packs (channel stride Cin*kh*kw floats).
 __global__ void __launch_bounds__(256) pack_batched_kernel(const __grid_constant__ PackBatch pb) {
   mtd_pdl_prologue();
+  __shared__ float tile[kMaxTaps * kPackLd];
   int s = 0;
   while (s + 1 < pb.n && (int)blockIdx.x >= pb.first_block[s + 1]) ++s;
   const PackArgs& p = pb.p[s];
-  const size_t total = (size_t)p.N * p.T * p.C;
-  const size_t begin = (size_t)((int)blockIdx.x - pb.first_block[s]) * kPackChunk;
-  const size_t end = min(total, begin + (size_t)kPackChunk);
-  for (size_t i = begin + threadIdx.x; i < end; i += blockDim.x) pack_one(pb.w[s], pb.out[s], p, i);
+  const float* __restrict__ w = pb.w[s];
+  float* __restrict__ out = pb.out[s];
+  const int rpb = pack_rows_per_block(p);
+  const int n_begin = ((int)blockIdx.x - pb.first_block[s]) * rpb, n_end = min(p.N, n_begin + rpb);
+  const size_t KS = (size_t)p.T * p.C / 32;
+  for (int n = n_begin; n < n_end; ++n) {
+    for (int c0 = 0; c0 < p.C; c0 += kPackTileC) {
+      const int ct = min(kPackTileC, p.C - c0);
+      __syncthreads();                                   // the previous tile has been written out
+      for (int j = threadIdx.x; j < ct * p.T; j += blockDim.x) {
+        const int c = j / p.T, t = j - c * p.T;
+        tile[t * kPackLd + c] = __ldg(w + (size_t)n * p.sN + (size_t)(c0 + c) * p.sC + p.toff[t]);
+      }
+      __syncthreads();
+      for (int j = threadIdx.x; j < ct * p.T; j += blockDim.x) {
+        const int t = j / ct, c = j - t * ct;
+        const float v = tile[t * kPackLd + c];
+        const size_t k = (size_t)t * p.C + c0 + c;
+        size_t o = (size_t)n * p.T * p.C + k;
+        if (p.blocked) o = ((((size_t)(n >> 5) * KS + (k >> 5)) * 32 + (n & 31)) << 5) + (k & 31);
+        if (p.tf32 == 0) { out[o] = v; continue; }
+        uint32_t h;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(v));
+        out[o] = __uint_as_float(h);
+        if (p.tf32 == 3) {
+          uint32_t l;
+          asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(v - __uint_as_float(h)));     // the residual is exact in fp32
+          out[o + p.lo_off] = __uint_as_float(l);
+        }
+      }
+    }
+  }
 }
 
 // dw_ref[n*sN + c*sC + toff[t]] = alpha * (gp[n][t][c] - beta * u[n_sn] * v[k_sn])
@@ -1425,8 +1466,8 @@ int mtd_conv_pack_batch_end(void* stream) {
       const PackRec& r = (*recs)[i0 + k];
       pb.w[k] = r.w; pb.out[k] = r.out; pb.p[k] = r.p;
       pb.first_block[k] = blocks;
-      const size_t total = (size_t)r.p.N * r.p.T * r.p.C;
-      blocks += (int)((total + kPackChunk - 1) / kPackChunk);
+      const int rpb = pack_rows_per_block(r.p);
+      blocks += (r.p.N + rpb - 1) / rpb;
     }
     pb.first_block[pb.n] = blocks;
     mtd_launch(pack_batched_kernel, blocks, 256, 0, st, pb);
