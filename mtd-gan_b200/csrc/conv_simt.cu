@@ -734,63 +734,15 @@ __device__ __forceinline__ void pack_one(const float* __restrict__ w, float* __r
   }
 }
 
-constexpr int kPackTileC = 512;                               // channels per shared-memory tile
-constexpr int kPackTileFloats = kMaxTaps * (kPackTileC + 1);  // tile lines are padded by one float: taps of a channel hit distinct banks
-
-// rows (n) of a pack handled by one block of the batched kernel: as many as fit the shared-memory tile
-__host__ __device__ inline int pack_rows_per_block(const PackArgs& p) {
-  const int ct = p.C < kPackTileC ? p.C : kPackTileC;
-  const int r = kPackTileFloats / (p.T * (ct + 1));
-  return r < 1 ? 1 : r;
-}
-
-// One block = a few whole rows n of one pack.  The source is walked with the TAP index fastest (the kh*kw taps of one
-// (n, c) pair are adjacent in every reference layout: 36 / 64 contiguous bytes), the packed copy is written with the
-// CHANNEL index fastest (its layout); the exchange goes through shared memory, all rows of the block in one exchange.
-// Reading in packed order instead costs a 32-byte sector per element for the data-gradient packs (channel stride
-// Cin*kh*kw floats).
 __global__ void __launch_bounds__(256) pack_batched_kernel(const __grid_constant__ PackBatch pb) {
   mtd_pdl_prologue();
-  __shared__ float tile[kPackTileFloats];
   int s = 0;
   while (s + 1 < pb.n && (int)blockIdx.x >= pb.first_block[s + 1]) ++s;
   const PackArgs& p = pb.p[s];
-  const float* __restrict__ w = pb.w[s];
-  float* __restrict__ out = pb.out[s];
-  const int rpb = pack_rows_per_block(p);
-  const int n_begin = ((int)blockIdx.x - pb.first_block[s]) * rpb;
-  const int rows = min(p.N, n_begin + rpb) - n_begin;
-  const int T = p.T, C = p.C;
-  const size_t KS = (size_t)T * C / 32;
-  for (int c0 = 0; c0 < C; c0 += kPackTileC) {           // one pass unless C > 512 (then rows == 1)
-    const int ct = min(kPackTileC, C - c0), ld = ct + 1;
-    const int total = rows * ct * T;
-    if (c0) __syncthreads();                             // the previous tile has been written out
-    for (int j = threadIdx.x; j < total; j += blockDim.x) {
-      const int q = j / T, t = j - q * T;
-      const int row = q / ct, c = q - row * ct;
-      tile[(row * T + t) * ld + c] = __ldg(w + (size_t)(n_begin + row) * p.sN + (size_t)(c0 + c) * p.sC + p.toff[t]);
-    }
-    __syncthreads();
-    for (int j = threadIdx.x; j < total; j += blockDim.x) {
-      const int q = j / ct, c = j - q * ct;              // q = row * T + t
-      const int row = q / T, t = q - row * T;
-      const float v = tile[q * ld + c];
-      const int n = n_begin + row;
-      const size_t k = (size_t)t * C + c0 + c;
-      size_t o = (size_t)n * T * C + k;
-      if (p.blocked) o = ((((size_t)(n >> 5) * KS + (k >> 5)) * 32 + (n & 31)) << 5) + (k & 31);
-      if (p.tf32 == 0) { out[o] = v; continue; }
-      uint32_t h;
-      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(v));
-      out[o] = __uint_as_float(h);
-      if (p.tf32 == 3) {
-        uint32_t l;
-        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(v - __uint_as_float(h)));     // the residual is exact in fp32
-        out[o + p.lo_off] = __uint_as_float(l);
-      }
-    }
-  }
+  const size_t total = (size_t)p.N * p.T * p.C;
+  const size_t begin = (size_t)((int)blockIdx.x - pb.first_block[s]) * kPackChunk;
+  const size_t end = min(total, begin + (size_t)kPackChunk);
+  for (size_t i = begin + threadIdx.x; i < end; i += blockDim.x) pack_one(pb.w[s], pb.out[s], p, i);
 }
 
 // dw_ref[n*sN + c*sC + toff[t]] = alpha * (gp[n][t][c] - beta * u[n_sn] * v[k_sn])
@@ -1473,8 +1425,8 @@ int mtd_conv_pack_batch_end(void* stream) {
       const PackRec& r = (*recs)[i0 + k];
       pb.w[k] = r.w; pb.out[k] = r.out; pb.p[k] = r.p;
       pb.first_block[k] = blocks;
-      const int rpb = pack_rows_per_block(r.p);
-      blocks += (r.p.N + rpb - 1) / rpb;
+      const size_t total = (size_t)r.p.N * r.p.T * r.p.C;
+      blocks += (int)((total + kPackChunk - 1) / kPackChunk);
     }
     pb.first_block[pb.n] = blocks;
     mtd_launch(pack_batched_kernel, blocks, 256, 0, st, pb);
