@@ -248,7 +248,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
   constexpr int kStageBytes = kNA * (kABytes + kBBytes);
   constexpr int kTxBytes = kABytes + kNA * kBBytes;                 // bytes TMA writes per stage (A_lo is produced on chip)
   constexpr int kOffAlo = kABytes, kOffB = kNA * kABytes, kOffBlo = kNA * kABytes + kBBytes;
-  constexpr uint32_t kTmemCols = (2 * BN) < 32 ? 32 : 2 * BN;      // two accumulators; power of two >= 32
+  // 3xTF32: [w_hi | w_lo] is ONE B operand of 2*BN rows, so a_hi * [w_hi | w_lo] is one N = 2*BN MMA (the A slice is read
+  // from shared memory once for both products) and a_lo * w_hi a second N = BN MMA into the upper accumulator half; the
+  // epilogue adds the halves.  Tensor-core operand reads per k-step: 80 KB instead of 96 KB (BN = 128).
+  constexpr uint32_t kAccCols = NPASS == 3 ? 2 * BN : BN;
+  constexpr uint32_t kTmemCols = (2 * kAccCols) < 32 ? 32 : 2 * kAccCols;      // two accumulators; power of two >= 32
 
   // 1024-byte alignment for SWIZZLE_128B
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -331,7 +335,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
     // ===== MMA issuer =====
     if (lane == 0) {
       PipeState st;
-      constexpr uint32_t idesc = make_idesc(BN);
+      constexpr uint32_t idesc_main = make_idesc((int)kAccCols), idesc_lo = make_idesc(BN);
       WorkIter wi(a, kiters);
       Work wk;
       for (int lt = 0; wi.next(a, kiters, wk); ++lt) {
@@ -340,7 +344,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
         const int k_begin = wk.kb, k_end = wk.ke;
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+        const uint32_t tmem_d = tmem_base + (uint32_t)acc * kAccCols;
         for (int it = k_begin; it < k_end; ++it) {
           mbar_wait(conv_bar(st.stage), st.phase);
           tc_fence_after();
@@ -348,13 +352,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
           const uint64_t da = make_sw128_desc(sa), db = make_sw128_desc(sa + kOffB);
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk) {      // 4 x (K = 8 tf32 = 32 B): +2 in 16-byte address units
-            if (NPASS == 3) {                   // small cross terms first, then the main product
-              const uint64_t dal = make_sw128_desc(sa + kOffAlo), dbl = make_sw128_desc(sa + kOffBlo);
-              umma_tf32(tmem_d, dal + 2u * kk, db + 2u * kk, idesc, (it > k_begin || kk > 0) ? 1u : 0u);
-              umma_tf32(tmem_d, da + 2u * kk, dbl + 2u * kk, idesc, 1u);
-              umma_tf32(tmem_d, da + 2u * kk, db + 2u * kk, idesc, 1u);
-            } else {
-              umma_tf32(tmem_d, da + 2u * kk, db + 2u * kk, idesc, (it > k_begin || kk > 0) ? 1u : 0u);
+            umma_tf32(tmem_d, da + 2u * kk, db + 2u * kk, idesc_main, (it > k_begin || kk > 0) ? 1u : 0u);
+            if (NPASS == 3) {                   // cross term a_lo * w_hi into the upper half (w_lo rows follow w_hi in the stage)
+              const uint64_t dal = make_sw128_desc(sa + kOffAlo);
+              umma_tf32(tmem_d + BN, dal + 2u * kk, db + 2u * kk, idesc_lo, 1u);
             }
           }
           umma_commit(empty_bar(st.stage));       // implies tcgen05.fence::before_thread_sync
@@ -425,7 +426,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
         uint32_t v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0), v);
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * kAccCols + (uint32_t)c0;
+        tmem_ld32(taddr, v);
+        if (NPASS == 3) {
+          uint32_t u[32];
+          tmem_ld32(taddr + BN, u);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(u[j]));
+        }
         if (wk.slot >= 0) {
           // stream-K piece: raw partial sums to the workspace tile (plain stores; rows past the batch are zeros)
           float* wrow = a.ws + ((size_t)wk.slot * kBM + r) * BN + c0;
