@@ -375,23 +375,27 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
         mbar_wait(full_bar(st.stage), st.phase);
         uint4* tileA = reinterpret_cast<uint4*>(gen_base + (size_t)st.stage * kStageBytes);
         // Integer arithmetic instead of cvt.rna.tf32.f32 (quarter-rate: it was the k-step bound for BN <= 64):
-        // (bits + 0x1000) & ~0x1fff == cvt.rna (nearest, ties away from zero).  a_hi replaces the raw tile (the
-        // tensor core would TRUNCATE the raw fp32, which biases the split and doubles the dropped lo*lo term);
-        // a_lo = rn_tf32(a - a_hi), the difference being exact in fp32.
+        // (bits + 0x1000) & ~0x1fff == cvt.rna (nearest, ties away from zero).
+        //   plain TF32: a_hi = rn_tf32(a) replaces the raw tile (the tensor core would TRUNCATE the raw fp32: a bias).
+        //   3xTF32: the raw tile STAYS -- the tensor core's truncation IS a_hi = trunc_tf32(a) -- and only
+        //   a_lo = rn_tf32(a - trunc_tf32(a)) is written (the difference is exact in fp32, so hi + lo carries no bias);
+        //   one 16 KB store pass less per k-step through the shared-memory pipe that bounds this kernel.  The dropped
+        //   a_lo * w_lo term is <= 2^-21 relative instead of 2^-22.
 #pragma unroll 8
         for (int j = 0; j < kABytes / 16 / 128; ++j) {
           const uint4 v = tileA[ct + 128 * j];
-          uint4 h;
-          h.x = (v.x + 0x1000u) & 0xffffe000u; h.y = (v.y + 0x1000u) & 0xffffe000u;
-          h.z = (v.z + 0x1000u) & 0xffffe000u; h.w = (v.w + 0x1000u) & 0xffffe000u;
-          tileA[ct + 128 * j] = h;
           if (NPASS == 3) {
             uint4 l;
-            l.x = (__float_as_uint(__uint_as_float(v.x) - __uint_as_float(h.x)) + 0x1000u) & 0xffffe000u;
-            l.y = (__float_as_uint(__uint_as_float(v.y) - __uint_as_float(h.y)) + 0x1000u) & 0xffffe000u;
-            l.z = (__float_as_uint(__uint_as_float(v.z) - __uint_as_float(h.z)) + 0x1000u) & 0xffffe000u;
-            l.w = (__float_as_uint(__uint_as_float(v.w) - __uint_as_float(h.w)) + 0x1000u) & 0xffffe000u;
+            l.x = (__float_as_uint(__uint_as_float(v.x) - __uint_as_float(v.x & 0xffffe000u)) + 0x1000u) & 0xffffe000u;
+            l.y = (__float_as_uint(__uint_as_float(v.y) - __uint_as_float(v.y & 0xffffe000u)) + 0x1000u) & 0xffffe000u;
+            l.z = (__float_as_uint(__uint_as_float(v.z) - __uint_as_float(v.z & 0xffffe000u)) + 0x1000u) & 0xffffe000u;
+            l.w = (__float_as_uint(__uint_as_float(v.w) - __uint_as_float(v.w & 0xffffe000u)) + 0x1000u) & 0xffffe000u;
             tileA[kOffAlo / 16 + ct + 128 * j] = l;
+          } else {
+            uint4 h;
+            h.x = (v.x + 0x1000u) & 0xffffe000u; h.y = (v.y + 0x1000u) & 0xffffe000u;
+            h.z = (v.z + 0x1000u) & 0xffffe000u; h.w = (v.w + 0x1000u) & 0xffffe000u;
+            tileA[ct + 128 * j] = h;
           }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> tensor-core (async proxy) reads

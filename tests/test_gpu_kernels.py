@@ -603,8 +603,9 @@ HALO_EQ_CASES = [
 @pytest.mark.parametrize("case", HALO_EQ_CASES, ids=lambda c: "x".join(map(str, c)))
 def test_streamed_halo_kernel_equals_tap_streaming_kernel(case, passes):
     """3x3 / stride-1 layers with more than 32 channels: the streamed-weight halo-tile kernel and the tap-streaming kernel
-    evaluate the same tf32 products (same operand rounding); they differ in summation order only (chunk-major k order,
-    cross terms in their own accumulator).  Forward and both data gradients of a two-source layer."""
+    evaluate the same error-compensated products; they differ in summation order (chunk-major k order) and, in 3xTF32
+    mode, in how the activation is split (halo: hi = nearest, tap streaming: hi = the tensor core's own truncation; both
+    keep hi + lo within 2^-21 of the value).  Forward and both data gradients of a two-source layer."""
     from mtdgan_b200 import _ext, ops
     B, H, W, C1, C2, N = case
     C = C1 + C2
