@@ -114,12 +114,6 @@ __device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint32_t dst
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
-__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint32_t dst, uint32_t bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
-      : "memory");
-}
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -269,7 +263,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kchunks = a.kc1 + a.kc2;
   const int kiters = a.T * kchunks;
-  const int Ctot = (a.kc1 + a.kc2) * 32;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&mapA1);
@@ -564,7 +557,6 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kchunks = a.kc1 + a.kc2;
   const int kiters = a.T * kchunks;
-  const int Ctot = kchunks * 32;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&mapA1);

@@ -91,7 +91,6 @@ __global__ void pixel_shuffle2_kernel(const float* __restrict__ in, float* __res
 
 // ---- float4 variants (C % 4 == 0, 16-byte aligned, < 2^31 pixels): 32-bit index arithmetic, one 16-byte access per
 //      tap instead of four 4-byte ones -- the scalar kernels above spend their time in 64-bit divisions ------------
-__device__ __forceinline__ float4 f4_scale(float4 a, float s) { return make_float4(a.x * s, a.y * s, a.z * s, a.w * s); }
 __device__ __forceinline__ float4 f4_fma(float s, float4 a, float4 b) {
   return make_float4(fmaf(s, a.x, b.x), fmaf(s, a.y, b.y), fmaf(s, a.z, b.z), fmaf(s, a.w, b.w));
 }
