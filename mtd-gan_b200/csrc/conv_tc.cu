@@ -1357,9 +1357,17 @@ __global__ void __launch_bounds__(256) tc_sk_finish_kernel(const __grid_constant
     if (b >= a.B) continue;
     const float* wsp = a.ws + ((size_t)st * a.sk_P * kBM + r) * BN + c;
     float4 sum = __ldcg(reinterpret_cast<const float4*>(wsp));
-    for (int p = 1; p <= last - first; ++p) {
-      const float4 t = __ldcg(reinterpret_cast<const float4*>(wsp + (size_t)p * kBM * BN));
-      sum.x += t.x; sum.y += t.y; sum.z += t.z; sum.w += t.w;
+    // four pieces in flight per thread (a dependent add after every load made the pass a chain of L2 latencies); the
+    // pieces are still ADDED strictly in order
+    const int P = last - first + 1;
+    for (int p = 1; p < P; p += 4) {
+      float4 t[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        t[q] = p + q < P ? __ldcg(reinterpret_cast<const float4*>(wsp + (size_t)(p + q) * kBM * BN)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (p + q < P) { sum.x += t[q].x; sum.y += t[q].y; sum.z += t[q].z; sum.w += t[q].w; }
     }
     int ncols, nloc;
     float* outp = tc_out_of(a, nt * BN, ncols, nloc);
